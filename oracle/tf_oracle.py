@@ -196,13 +196,14 @@ def istft(spec, frame_length=512, hop_length=256, window='hann',
 # mel filterbank                                                              #
 # --------------------------------------------------------------------------- #
 def _linspace_f32(start, end, steps):
-    """torch.linspace in float32: symmetric halves around the midpoint."""
-    start, end = np.float32(start), np.float32(end)
-    step = np.float32((end - start) / np.float32(steps - 1))
+    """torch.linspace in float32: float32 step, symmetric halves around the
+    midpoint, each point rounded once (fused multiply-add)."""
+    start = np.float64(np.float32(start))
+    end = np.float64(np.float32(end))
+    step = np.float64(np.float32((end - start) / (steps - 1)))
     i = np.arange(steps)
-    lo = (start + step * i.astype(np.float32)).astype(np.float32)
-    hi = (end - step * (steps - 1 - i).astype(np.float32)).astype(np.float32)
-    return np.where(i < steps // 2, lo, hi).astype(np.float32)
+    return np.where(i < steps // 2, start + step * i,
+                    end - step * (steps - 1 - i)).astype(np.float32)
 
 
 def fft_freqs(fs=16e3, n_fft=512):
@@ -219,8 +220,13 @@ def mel_filterbank(n_filters=64, n_fft=512, fs=16e3, fmin=50, fmax=8000):
     mel_min = 2595 * math.log10(1 + fmin / 700)
     mel_max = 2595 * math.log10(1 + fmax / 700)
     mel = _linspace_f32(mel_min, mel_max, n_filters + 2)
-    fc = (np.float32(700) * (np.float32(10) ** (mel / np.float32(2595))
-                             - np.float32(1))).astype(np.float32)
+    # torch evaluates 10**x with a ~1-ulp vectorised powf; a correctly rounded
+    # power differs from it in isolated last bits, so these constants are
+    # pinned to the reference within 1 ulp, not bit-exactly (the PRODUCT builds
+    # them with the reference's own torch calls and is pinned bit-exactly).
+    ratio = (mel / np.float32(2595)).astype(np.float32)
+    power = np.power(10.0, ratio.astype(np.float64)).astype(np.float32)
+    fc = (np.float32(700) * (power - np.float32(1))).astype(np.float32)
     f = fft_freqs(fs, n_fft).astype(np.float32)
     filters = np.zeros((n_filters, len(f)), dtype=np.float32)
     for row, i in enumerate(range(1, n_filters + 1)):
@@ -361,7 +367,10 @@ def snr(x, y, lengths):
     ratio = (y ** 2).sum(-1) / (((y - x) ** 2).sum(-1) + EPS32)
     db = 10 * np.log10(ratio + EPS32)
     axes = tuple(range(1, x.ndim - 1))
-    return -(db.mean(axes) if axes else db)
+    # quirk kept on purpose: for 2-D input `axes` is the empty tuple and
+    # torch's mean(()) reduces over ALL dims -> a 0-dim batch mean
+    # (this is what DCCRN hits: dccrn.py:115-122 passes (B, L) tensors)
+    return -(db.mean(axes) if axes else db.mean())
 
 
 def sisnr_matrix(x, y, lengths):
@@ -402,7 +411,7 @@ def snr_grad(x, y, lengths):
     p = (ym ** 2).sum(-1, keepdims=True)
     d = (diff ** 2).sum(-1, keepdims=True)
     r = p / (d + EPS32)
-    rows = int(np.prod(x.shape[1:-1])) if x.ndim > 2 else 1
+    rows = int(np.prod(x.shape[1:-1])) if x.ndim > 2 else x.shape[0]
     coef = -(10 / math.log(10)) * 2 * p / ((r + EPS32) * (d + EPS32) ** 2)
     mask = apply_mask(np.ones_like(x), y, lengths)[0]
     return coef * diff * mask / rows
