@@ -1,0 +1,19 @@
+"""brever_b200 — B200-native (sm_100a) time-frequency front-end for brever.
+
+Drop-in replacements for the hot-path classes of philgzl/brever:
+
+    from brever_b200.modules import STFT, MelFilterbank, FeatureExtractor
+    from brever_b200.criterion import CriterionRegistry, init_criterion, sisnr, snr
+
+backed by hand-written CUDA kernels behind a C ABI (include/brever_b200.h).
+CUDA tensors only; there is no CPU fallback.
+"""
+from . import criterion, ffnn, modules
+from .criterion import CriterionRegistry, apply_mask, init_criterion, sisnr, snr
+from .modules import STFT, FeatureExtractor, MelFilterbank
+from .registry import Registry
+
+__version__ = '0.1.0'
+__all__ = ['STFT', 'MelFilterbank', 'FeatureExtractor', 'CriterionRegistry',
+           'init_criterion', 'sisnr', 'snr', 'apply_mask', 'Registry',
+           'criterion', 'ffnn', 'modules']

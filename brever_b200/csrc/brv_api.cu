@@ -1,0 +1,87 @@
+// C entry points for the STFT / iSTFT pair: argument checks, geometry, and the
+// choice between the tensor-core kernels (brv_stft_tc.cu) and the generic
+// CUDA-core kernels (brv_stft_simt.cu).  There is no CPU path.
+#include <stdlib.h>
+
+#include "brv_common.cuh"
+
+// brv_stft_tc.cu
+bool brv_tc_supports_forward(const brv_stft_plan* p);
+int brv_tc_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
+                        int64_t x_stride, float2* out, int64_t n_frames, cudaStream_t st);
+
+static int force_generic() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("BRV_FORCE_GENERIC");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
+extern "C" int brv_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_signals,
+                                int64_t samples, int64_t x_stride, void* out, void* stream) {
+    BRV_REQUIRE(p && out, "null pointer argument");
+    BRV_REQUIRE(n_signals >= 0 && samples >= 0, "negative shape");
+    BRV_REQUIRE(x || n_signals * samples == 0, "input pointer is null");
+    BRV_REQUIRE(x_stride >= samples || n_signals <= 1, "row stride smaller than the row");
+    int64_t n_frames = 0;
+    int rc = brv_stft_geometry(p, samples, &n_frames, nullptr, nullptr);
+    if (rc != BRV_OK) return rc;
+    if (n_signals == 0) return BRV_OK;
+    if (!force_generic() && brv_tc_supports_forward(p))
+        return brv_tc_stft_forward(p, x, n_signals, samples, x_stride, (float2*)out, n_frames,
+                                   (cudaStream_t)stream);
+    return brv_simt_stft_forward(p, x, n_signals, samples, x_stride, (float2*)out, n_frames,
+                                 (cudaStream_t)stream);
+}
+
+extern "C" int brv_stft_forward_grad(const brv_stft_plan* p, const void* gX, int64_t ss,
+                                     int64_t sb, int64_t sf, int64_t n_signals, int64_t samples,
+                                     float* gx, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    BRV_REQUIRE(p && gX && gx, "null pointer argument");
+    if (p->compression != 1.0)
+        return brv_fail(BRV_ERR_UNSUPPORTED,
+                        "gradient of the compressed STFT (compression_factor != 1) is not "
+                        "implemented: no reference model back-propagates through it");
+    int64_t n_frames = 0;
+    int rc = brv_stft_geometry(p, samples, &n_frames, nullptr, nullptr);
+    if (rc != BRV_OK) return rc;
+    BRV_REQUIRE(workspace && workspace_bytes >= brv_stft_workspace_bytes(p, n_signals, n_frames),
+                "workspace too small");
+    return brv_simt_spec_to_signal(p, (const float2*)gX, ss, sb, sf, n_signals, n_frames, samples,
+                                   false, gx, (float*)workspace, (cudaStream_t)stream);
+}
+
+extern "C" int brv_istft_forward(const brv_stft_plan* p, const void* X, int64_t ss, int64_t sb,
+                                 int64_t sf, int64_t n_signals, int64_t n_frames, float* y,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+    BRV_REQUIRE(p && X, "null pointer argument");
+    BRV_REQUIRE(n_signals >= 0 && n_frames >= 1, "bad shape");
+    int64_t out_len = 0;
+    int rc = brv_istft_geometry(p, n_frames, &out_len);
+    if (rc != BRV_OK) return rc;
+    rc = brv_check_nola(p, n_frames);
+    if (rc != BRV_OK) return rc;
+    if (n_signals == 0 || out_len == 0) return BRV_OK;
+    BRV_REQUIRE(y, "output pointer is null");
+    BRV_REQUIRE(workspace && workspace_bytes >= brv_stft_workspace_bytes(p, n_signals, n_frames),
+                "workspace too small");
+    return brv_simt_spec_to_signal(p, (const float2*)X, ss, sb, sf, n_signals, n_frames, out_len,
+                                   true, y, (float*)workspace, (cudaStream_t)stream);
+}
+
+extern "C" int brv_istft_forward_grad(const brv_stft_plan* p, const float* gy, int64_t n_signals,
+                                      int64_t n_frames, void* gX, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    BRV_REQUIRE(p && gy && gX, "null pointer argument");
+    if (p->compression != 1.0)
+        return brv_fail(BRV_ERR_UNSUPPORTED,
+                        "gradient of the decompressing iSTFT (compression_factor != 1) is not "
+                        "implemented: the reference only runs it under no_grad");
+    BRV_REQUIRE(workspace && workspace_bytes >= brv_stft_workspace_bytes(p, n_signals, n_frames),
+                "workspace too small");
+    return brv_simt_istft_grad(p, gy, n_signals, n_frames, (float2*)gX, (float*)workspace,
+                               (cudaStream_t)stream);
+}

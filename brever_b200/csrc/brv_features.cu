@@ -1,0 +1,248 @@
+// Mel projection and the FFNN feature extractor: |X|^2 -> channel mean -> banded
+// (CSR) mel -> optional pdf normalisation -> log / cubic-root -> context stacking
+// with edge replication -> decimation -> static normalisation, in one kernel.
+//
+// Reference: brever/modules/stft.py:152-198 (MelFilterbank),
+// brever/modules/features.py:186-198 (FeatureExtractor.fbe),
+// brever/models/ffnn/ffnn.py:122-135,175-203 (stack, decimate, normalisers).
+//
+// The kernel is HBM-bound: per frame it reads C*F complex bins once (8 B each)
+// and writes n_mel*(stacks+1) floats.  The mel matrix is 97 % zeros (<= 2
+// filters per bin), so it is applied as a CSR gather from a shared-memory
+// power spectrum instead of a dense GEMM.
+#include "brv_common.cuh"
+
+namespace {
+
+constexpr int FT_TILE = 64;     // output frames (pre-decimation) per CTA
+constexpr int FT_THREADS = 256;
+constexpr int FT_MAX_STACK = 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// dynamic smem: power[warps][n_bins] | energy[(FT_TILE + stacks)][n_mel + 1]
+__global__ void __launch_bounds__(FT_THREADS)
+fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_t sf,
+                    int64_t st, int C, int n_bins, int64_t n_frames,
+                    const float* __restrict__ mel_vals, const int32_t* __restrict__ mel_cols,
+                    const int32_t* __restrict__ mel_rowptr, int n_mel, int normalize,
+                    int compression, float eps, int stacks, int decimation,
+                    const float* __restrict__ mean, const float* __restrict__ stdv,
+                    float* __restrict__ out, int64_t out_frames, int tiles_per_item) {
+    extern __shared__ float smem[];
+    const int warps = FT_THREADS / 32;
+    float* power = smem;                                   // [warps][n_bins]
+    float* energy = smem + (size_t)warps * n_bins;         // [FT_TILE+stacks][n_mel+1]
+    const int ldE = n_mel + 1;
+
+    const int64_t b = blockIdx.x / tiles_per_item;
+    const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_item) * FT_TILE;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int64_t first = t0 - stacks;                     // first frame staged (may be < 0)
+    const int staged = FT_TILE + stacks;
+    const float inv_c = 1.f / (float)C;
+
+    for (int s = warp; s < staged; s += warps) {
+        int64_t t = first + s;
+        if (t < 0 || t >= n_frames) continue;              // t < 0 is never read: the
+                                                           // stacker clamps to frame 0 (ffnn.py:126)
+        float* pw = power + (size_t)warp * n_bins;
+        const float2* base = X + b * sb + t * st;
+        for (int f = lane; f < n_bins; f += 32) {
+            float acc = 0.f;
+            for (int c = 0; c < C; ++c) {
+                float2 v = __ldg(base + (int64_t)c * sc + (int64_t)f * sf);
+                acc = fmaf(v.x, v.x, acc);
+                acc = fmaf(v.y, v.y, acc);
+            }
+            pw[f] = acc * inv_c;
+        }
+        __syncwarp();
+        float part = 0.f;
+        for (int m = lane; m < n_mel; m += 32) {
+            float e = 0.f;
+            for (int j = mel_rowptr[m]; j < mel_rowptr[m + 1]; ++j)
+                e = fmaf(__ldg(mel_vals + j), pw[__ldg(mel_cols + j)], e);
+            energy[s * ldE + m] = e;
+            part += e;
+        }
+        if (normalize) {                                    // features.py:192-193
+            float total = warp_sum(part) + eps;
+            __syncwarp();
+            for (int m = lane; m < n_mel; m += 32) energy[s * ldE + m] /= total;
+        }
+        __syncwarp();
+        for (int m = lane; m < n_mel; m += 32) {
+            float e = energy[s * ldE + m];
+            if (compression == 1) e = logf(e + eps);        // features.py:195-196
+            else if (compression == 2) e = cbrtf(e);        // features.py:197-198
+            energy[s * ldE + m] = e;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // out[b, k*n_mel + m, t/dec] = (E[m, max(t - k, 0)] - mean) / std
+    const int rows = n_mel * (stacks + 1);
+    const int64_t o0 = brv_ceil_div(t0, decimation);       // first output frame of this tile
+    int64_t t_end = t0 + FT_TILE < n_frames ? t0 + FT_TILE : n_frames;
+    const int64_t o1 = brv_ceil_div(t_end, decimation);
+    const int width = (int)(o1 - o0);
+    if (width <= 0) return;
+    for (int idx = threadIdx.x; idx < rows * width; idx += FT_THREADS) {
+        int r = idx / width, w = idx % width;
+        int k = r / n_mel, m = r % n_mel;
+        int64_t t = (o0 + w) * decimation;
+        int64_t src = t - k;
+        if (src < 0) src = 0;
+        float v = energy[(int)(src - first) * ldE + m];
+        if (mean) v -= __ldg(mean + r);
+        if (stdv) v /= __ldg(stdv + r);
+        out[(b * rows + r) * out_frames + o0 + w] = v;
+    }
+}
+
+__global__ void mel_apply_kernel(const float* __restrict__ x, int64_t sb, int64_t sr, int64_t st,
+                                 int64_t n_frames, const float* __restrict__ vals,
+                                 const int32_t* __restrict__ cols,
+                                 const int32_t* __restrict__ rowptr, int n_rows_out,
+                                 float* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y;
+    int64_t b = blockIdx.z;
+    if (t >= n_frames) return;
+    const float* base = x + b * sb + t * st;
+    float acc = 0.f;
+    for (int j = rowptr[r]; j < rowptr[r + 1]; ++j)
+        acc = fmaf(__ldg(vals + j), __ldg(base + (int64_t)cols[j] * sr), acc);
+    out[(b * n_rows_out + r) * n_frames + t] = acc;
+}
+
+__global__ void stack_normalize_kernel(const float* __restrict__ x, int nf, int64_t n_frames,
+                                       int stacks, int decimation,
+                                       const float* __restrict__ mean,
+                                       const float* __restrict__ stdv, float* __restrict__ out,
+                                       int64_t out_frames) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y;                      // output row = k*nf + f
+    int64_t b = blockIdx.z;
+    if (o >= out_frames) return;
+    int k = r / nf, f = r % nf;
+    int64_t src = o * decimation - k;
+    if (src < 0) src = 0;
+    float v = __ldg(x + (b * nf + f) * n_frames + src);
+    if (mean) v -= __ldg(mean + r);
+    if (stdv) v /= __ldg(stdv + r);
+    out[(b * (int64_t)nf * (stacks + 1) + r) * out_frames + o] = v;
+}
+
+// One warp per row: running mean / variance along frames (ffnn.py:195-203),
+// accumulated in float64 (the float32 reference cancels in E[x^2]-E[x]^2).
+__global__ void cumulative_normalize_kernel(const float* __restrict__ x, int64_t n_rows,
+                                            int64_t n_frames, float eps,
+                                            float* __restrict__ out) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    int lane = threadIdx.x % 32;
+    if (row >= n_rows) return;
+    const float* src = x + row * n_frames;
+    float* dst = out + row * n_frames;
+    double run_s = 0, run_q = 0;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += 32) {
+        int64_t t = t0 + lane;
+        float v = t < n_frames ? src[t] : 0.f;
+        double s = v, q = (double)v * v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {            // inclusive warp scan
+            double s2 = __shfl_up_sync(0xffffffffu, s, o);
+            double q2 = __shfl_up_sync(0xffffffffu, q, o);
+            if (lane >= o) { s += s2; q += q2; }
+        }
+        s += run_s;
+        q += run_q;
+        if (t < n_frames) {
+            double cnt = (double)(t + 1);
+            double mu = s / cnt;
+            double var = q / cnt - mu * mu;
+            dst[t] = (float)(((double)v - mu) / sqrt(var + (double)eps));
+        }
+        run_s = __shfl_sync(0xffffffffu, s, 31);
+        run_q = __shfl_sync(0xffffffffu, q, 31);
+    }
+}
+
+}  // namespace
+
+extern "C" int brv_fbe_features(const void* X, int64_t sb, int64_t sc, int64_t sf, int64_t st,
+                                int64_t n_batch, int n_channels, int n_bins, int64_t n_frames,
+                                const float* mel_vals, const int32_t* mel_cols,
+                                const int32_t* mel_rowptr, int n_mel, int normalize,
+                                int compression, float eps, int stacks, int decimation,
+                                const float* mean, const float* stdv, float* out, void* stream) {
+    BRV_REQUIRE(X && mel_vals && mel_cols && mel_rowptr && out, "null pointer argument");
+    BRV_REQUIRE(n_channels >= 1 && n_bins >= 1 && n_mel >= 1, "bad feature dimensions");
+    BRV_REQUIRE(compression >= 0 && compression <= 2, "compression must be 0 (none), 1 (log) or 2 (cubic)");
+    BRV_REQUIRE(stacks >= 0 && stacks <= FT_MAX_STACK, "stacks must be in [0, %d]", FT_MAX_STACK);
+    BRV_REQUIRE(decimation >= 1, "decimation must be >= 1");
+    if (n_batch == 0 || n_frames == 0) return BRV_OK;
+    const int64_t out_frames = brv_ceil_div(n_frames, decimation);
+    const int tiles = (int)brv_ceil_div(n_frames, FT_TILE);
+    const int64_t grid = n_batch * tiles;
+    BRV_REQUIRE(grid < (1LL << 31), "too many feature tiles");
+    size_t smem = ((size_t)(FT_THREADS / 32) * n_bins + (size_t)(FT_TILE + stacks) * (n_mel + 1)) * sizeof(float);
+    BRV_REQUIRE(smem <= 200 * 1024, "feature tile does not fit shared memory (%zu bytes)", smem);
+    if (smem > 48 * 1024)
+        BRV_CUDA(cudaFuncSetAttribute(fbe_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    fbe_features_kernel<<<(unsigned)grid, FT_THREADS, smem, (cudaStream_t)stream>>>(
+        (const float2*)X, sb, sc, sf, st, n_channels, n_bins, n_frames, mel_vals, mel_cols,
+        mel_rowptr, n_mel, normalize, compression, eps, stacks, decimation, mean, stdv, out,
+        out_frames, tiles);
+    BRV_LAUNCH_CHECK("fbe_features_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_mel_apply(const float* x, int64_t sb, int64_t sr, int64_t st, int64_t n_batch,
+                             int n_rows_in, int64_t n_frames, const float* vals,
+                             const int32_t* cols, const int32_t* rowptr, int n_rows_out,
+                             float* out, void* stream) {
+    BRV_REQUIRE(x && vals && cols && rowptr && out, "null pointer argument");
+    BRV_REQUIRE(n_rows_in >= 1 && n_rows_out >= 1 && n_rows_out < 65536, "bad row counts");
+    BRV_REQUIRE(n_batch < 65536, "more than 65535 batch items per call");
+    if (n_batch == 0 || n_frames == 0) return BRV_OK;
+    dim3 grid((unsigned)brv_ceil_div(n_frames, 128), (unsigned)n_rows_out, (unsigned)n_batch);
+    mel_apply_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, sb, sr, st, n_frames, vals, cols,
+                                                            rowptr, n_rows_out, out);
+    BRV_LAUNCH_CHECK("mel_apply_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_stack_normalize(const float* x, int64_t n_batch, int n_features,
+                                   int64_t n_frames, int stacks, int decimation,
+                                   const float* mean, const float* stdv, float* out,
+                                   void* stream) {
+    BRV_REQUIRE(x && out, "null pointer argument");
+    BRV_REQUIRE(n_features >= 1 && stacks >= 0 && decimation >= 1, "bad stacking parameters");
+    const int64_t rows = (int64_t)n_features * (stacks + 1);
+    BRV_REQUIRE(rows < 65536 && n_batch < 65536, "too many rows / batch items per call");
+    if (n_batch == 0 || n_frames == 0) return BRV_OK;
+    const int64_t out_frames = brv_ceil_div(n_frames, decimation);
+    dim3 grid((unsigned)brv_ceil_div(out_frames, 128), (unsigned)rows, (unsigned)n_batch);
+    stack_normalize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+        x, n_features, n_frames, stacks, decimation, mean, stdv, out, out_frames);
+    BRV_LAUNCH_CHECK("stack_normalize_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_cumulative_normalize(const float* x, int64_t n_rows, int64_t n_frames,
+                                        float eps, float* out, void* stream) {
+    BRV_REQUIRE(x && out, "null pointer argument");
+    if (n_rows == 0 || n_frames == 0) return BRV_OK;
+    const int warps = 4;
+    cumulative_normalize_kernel<<<(unsigned)brv_ceil_div(n_rows, warps), warps * 32, 0,
+                                  (cudaStream_t)stream>>>(x, n_rows, n_frames, eps, out);
+    BRV_LAUNCH_CHECK("cumulative_normalize_kernel");
+    return BRV_OK;
+}

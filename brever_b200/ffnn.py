@@ -1,0 +1,170 @@
+"""FFNN feature glue (brever/models/ffnn/ffnn.py:77-203) on the sm_100a kernels.
+
+The reference keeps these as methods of the ``FFNN`` model; the network itself
+(``_FFNN``, ffnn.py:151-172) is out of scope and stays in PyTorch, so this module
+exposes the glue as free functions / small modules with the same names and
+semantics, plus ``FFNNFrontEnd`` which chains STFT -> log-mel -> context stack ->
+static normalisation (and the ``_enhance`` tail: mask extrapolation -> iSTFT)
+through the fused kernels.  A maintainer swaps the bodies of ``FFNN.stack``,
+``FFNN.irm`` ... for these calls.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .modules import STFT, FeatureExtractor, MelFilterbank
+
+eps = np.finfo(float).eps  # ffnn.py:12 (float64 eps, 2.2e-16)
+
+
+def _stats(t, rows, device):
+    if t is None:
+        return None
+    t = t.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+    if t.numel() != rows:
+        raise RuntimeError(f'statistics must have {rows} entries, got {t.numel()}')
+    return t
+
+
+def _stack_raw(data, stacks, decimation=1, mean=None, std=None):
+    _lib.require_cuda(data, 'stack input')
+    unbatched = data.ndim == 2
+    x = data.unsqueeze(0) if unbatched else data
+    if x.ndim != 3:
+        raise ValueError(f'input must be 2 or 3 dimensional, got {data.ndim}')
+    x = x.float().contiguous()
+    batch, nf, frames = x.shape
+    rows = nf * (stacks + 1)
+    out_frames = -(-frames // decimation)
+    out = torch.empty((batch, rows, out_frames), dtype=torch.float32, device=x.device)
+    mean_t, std_t = _stats(mean, rows, x.device), _stats(std, rows, x.device)
+    for start in range(0, batch, 65535):
+        chunk = x[start:start + 65535]
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().brv_stack_normalize(
+                _lib.ptr(chunk), chunk.shape[0], nf, frames, int(stacks),
+                int(decimation), _lib.ptr(mean_t), _lib.ptr(std_t),
+                _lib.ptr(out[start:start + 65535]), _lib.stream_ptr(x.device)))
+    return out[0] if unbatched else out
+
+
+def stack(data, stacks):
+    """``out[k*nf + f, t] = data[f, max(t - k, 0)]``, k = 0..stacks (ffnn.py:122-132)."""
+    return _stack_raw(data, stacks)
+
+
+def decimate(data, decimation):
+    """ffnn.py:134-135."""
+    return data[..., ::decimation]
+
+
+def irm(foreground_mag, background_mag, mel_fb):
+    """Ideal ratio mask labels on ``(C, F, T)`` magnitudes (ffnn.py:113-120)."""
+    fg = mel_fb(foreground_mag.pow(2).mean(0))
+    bg = mel_fb(background_mag.pow(2).mean(0))
+    return (1 + bg / (fg + eps)).pow(-0.5)
+
+
+class StaticNormalizer(nn.Module):
+    """``(x - mean) / std`` with ``(input_size, 1)`` buffers (ffnn.py:175-187)."""
+
+    def __init__(self, input_size):
+        super().__init__()
+        self.register_buffer('mean', torch.zeros((input_size, 1)))
+        self.register_buffer('std', torch.ones((input_size, 1)))
+
+    def set_statistics(self, mean, std):
+        self.mean[:], self.std[:] = mean, std
+
+    def forward(self, x):
+        if x.requires_grad and torch.is_grad_enabled():
+            return (x - self.mean) / self.std   # autograd path: plain broadcast
+        return _stack_raw(x, 0, 1, self.mean, self.std)
+
+
+class CumulativeNormalizer(nn.Module):
+    """Running mean / variance normalisation along frames (ffnn.py:190-203)."""
+
+    def __init__(self, eps=1e-4):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, x):
+        _lib.require_cuda(x, 'CumulativeNormalizer input')
+        src = x.float().contiguous()
+        out = torch.empty_like(src)
+        if src.numel():
+            with torch.cuda.device(src.device):
+                _lib.check(_lib.lib().brv_cumulative_normalize(
+                    _lib.ptr(src), src.numel() // src.shape[-1], src.shape[-1],
+                    float(self.eps), _lib.ptr(out), _lib.stream_ptr(src.device)))
+        return out
+
+
+def training_statistics(items):
+    """FFNN.pre_train statistics (ffnn.py:137-148): unweighted mean over items of
+    the per-item time mean and mean square -> ``(mean, std)``."""
+    mean, msq = 0, 0
+    for data in items:
+        mean = mean + data.mean(-1, keepdim=True)
+        msq = msq + data.pow(2).mean(-1, keepdim=True)
+    mean, msq = mean / len(items), msq / len(items)
+    return mean, (msq - mean.pow(2)).sqrt()
+
+
+class FFNNFrontEnd:
+    """STFT -> log-mel -> stack -> (static) normalise, and the enhance tail.
+
+    Mirrors the data flow of ``FFNN.transform`` / ``FFNN._enhance``
+    (ffnn.py:77-111) with the kernels fused: the feature kernel reads the
+    spectrogram once and writes the stacked, normalised features directly.
+    """
+
+    def __init__(self, fs=16000, features=('logfbe',), stacks=5, decimation=1,
+                 stft_frame_length=512, stft_hop_length=256, stft_window='hann',
+                 mel_filters=64):
+        self.stacks = stacks
+        self.decimation = decimation
+        self.stft = STFT(frame_length=stft_frame_length,
+                         hop_length=stft_hop_length, window=stft_window)
+        self.mel_fb = MelFilterbank(n_filters=mel_filters,
+                                    n_fft=stft_frame_length, fs=fs)
+        self.feature_extractor = FeatureExtractor(
+            features=set(features), mel_fb=self.mel_fb,
+            hop_length=stft_hop_length, fs=fs)
+        self.input_size = self.feature_extractor.n_features * (stacks + 1)
+
+    def features(self, spec, mean=None, std=None):
+        """(B, C, F, T) complex -> (B, input_size, T') stacked [normalised] features."""
+        names = self.feature_extractor.features
+        if len(names) == 1 and names[0] in FeatureExtractor._FBE_FAMILY:
+            normalize, compression = FeatureExtractor._FBE_FAMILY[names[0]]
+            return self.feature_extractor.fbe(
+                spec, normalize=normalize, compression=compression,
+                stacks=self.stacks, decimation=self.decimation, mean=mean,
+                std=std)
+        feats = torch.cat([self.feature_extractor.calc_feature(spec, n)
+                           for n in names], dim=1)
+        return _stack_raw(feats, self.stacks, self.decimation, mean, std)
+
+    def transform(self, sources):
+        """FFNN.transform (ffnn.py:77-91) for one ``(2, C, L)`` utterance."""
+        assert sources.shape[0] == 2  # mixture, foreground
+        spec = self.stft(sources)
+        mix, foreground = spec
+        background = mix - foreground
+        x = self.features(mix.unsqueeze(0))[0]
+        labels = irm(foreground.abs(), background.abs(), self.mel_fb)
+        labels = decimate(labels, self.decimation)
+        return torch.cat([x, labels])
+
+    def enhance(self, x, mask_fn, mean=None, std=None):
+        """FFNN._enhance (ffnn.py:100-111); ``mask_fn`` is the network."""
+        length = x.shape[-1]
+        spec = self.stft(x)
+        feats = self.features(spec, mean, std)
+        mask = mask_fn(feats)
+        extrapolated = self.mel_fb.backward(mask)
+        out = self.stft.backward(spec.mean(1) * extrapolated)
+        return out[..., :length]

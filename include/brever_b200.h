@@ -1,0 +1,204 @@
+/*
+ * brever_b200.h — C ABI of the B200-native time-frequency front-end.
+ *
+ * This is the drop-in boundary for the hot path of philgzl/brever named in
+ * BASELINE.json (STFT / iSTFT, mel projection, FFNN feature extractor, SNR /
+ * SI-SNR criterion).  The reference has no FFI today (it is pure Python over
+ * torch); every entry point below states the reference interface (file:line,
+ * relative to the brever repository root) whose arithmetic it replaces.  The
+ * thin Python mirror of the reference classes lives in brever_b200/ and calls
+ * these symbols through ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every tensor pointer is a DEVICE pointer owned by the
+ *     caller (PyTorch), unless the parameter is documented as host memory;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it
+ *     and nothing synchronises the device;
+ *   - return value: BRV_OK (0) or a negative brv_status; brv_last_error() gives
+ *     a human-readable message for the calling thread;
+ *   - complex tensors are interleaved (re, im) float32 pairs ("float2");
+ *   - "frame-major" spectrogram layout = (signal, frame, bin) contiguous, which
+ *     is exactly the memory torch.stft produces behind its (..., bin, frame) view.
+ */
+#ifndef BREVER_B200_H
+#define BREVER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRV_ABI_VERSION 1
+
+typedef enum brv_status {
+    BRV_OK = 0,
+    BRV_ERR_INVALID = -1,     /* bad argument (maps to ValueError)            */
+    BRV_ERR_UNSUPPORTED = -2, /* valid but not implemented (NotImplementedError) */
+    BRV_ERR_CUDA = -3,        /* CUDA runtime error (RuntimeError)            */
+    BRV_ERR_NOLA = -4,        /* window overlap-add envelope ~ 0 (RuntimeError,
+                                 same condition torch.istft raises on)        */
+    BRV_ERR_ALLOC = -5
+} brv_status;
+
+typedef struct brv_stft_plan brv_stft_plan; /* opaque */
+
+/* ---- library ----------------------------------------------------------- */
+int brv_abi_version(void);
+const char* brv_status_string(int status);
+const char* brv_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's
+ * `gpu_launches` evidence). */
+uint64_t brv_launch_count(void);
+/* SM count / compute capability of the current device; fails without a GPU. */
+int brv_device_query(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- STFT plan ---------------------------------------------------------
+ * Replaces the constructor state of brever.modules.STFT
+ * (brever/modules/stft.py:32-54).  `window` is HOST memory: `frame_length`
+ * float64 samples exactly as the reference stores `self.window`
+ * (scipy.signal.get_window(name, frame_length), periodic).  The plan owns the
+ * device-resident DFT bases (window, normalisation 1/sqrt(sum w^2) and the
+ * Hermitian weights folded in) on the device that is current at creation.
+ * center=True and pad_mode='constant' are the only modes (stft.py:33).       */
+int brv_stft_plan_create(brv_stft_plan** plan, int frame_length, int hop_length,
+                         int n_fft, const double* window, int normalized,
+                         int onesided, double compression_factor,
+                         double scale_factor);
+int brv_stft_plan_destroy(brv_stft_plan* plan);
+
+/* Integer frame arithmetic of STFT.pad / STFT.frame_count + torch.stft
+ * (stft.py:140-149): for `samples` input samples returns the number of frames
+ * T, bins F and the right zero padding.  Bit-exact contract.                 */
+int brv_stft_geometry(const brv_stft_plan* plan, int64_t samples,
+                      int64_t* n_frames, int64_t* n_bins, int64_t* pad_right);
+/* Output samples of the inverse for T frames: hop*(T-1) (torch.istft, centre). */
+int brv_istft_geometry(const brv_stft_plan* plan, int64_t n_frames,
+                       int64_t* samples);
+
+/* ---- STFT.forward (stft.py:59-89) ---------------------------------------
+ * x   : (n_signals, samples) float32, row stride `x_stride` elements.
+ * out : (n_signals, T, F) complex64 frame-major.  Framing, zero padding,
+ *       windowing, DFT, 1/sqrt(sum w^2), |X|^c e^{j angle X}, *scale fused.  */
+int brv_stft_forward(const brv_stft_plan* plan, const float* x,
+                     int64_t n_signals, int64_t samples, int64_t x_stride,
+                     void* out, void* stream);
+
+/* Adjoint of brv_stft_forward w.r.t. x for compression_factor == 1 (what
+ * autograd gives the reference; needed by MultiResYuLoss, criterion.py:219).
+ * gX : complex64 (n_signals, F, T) with element strides (complex units).
+ * gx : (n_signals, samples) float32 contiguous.
+ * workspace: brv_stft_workspace_bytes(plan, n_signals, T) bytes.            */
+int brv_stft_forward_grad(const brv_stft_plan* plan, const void* gX,
+                          int64_t stride_signal, int64_t stride_bin,
+                          int64_t stride_frame, int64_t n_signals,
+                          int64_t samples, float* gx, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* ---- STFT.backward = iSTFT (stft.py:101-138) ------------------------------
+ * X : complex64 (n_signals, F, T) with arbitrary element strides (complex
+ *     units) — callers hand both frame-major views and bin-major tensors.
+ * y : (n_signals, hop*(T-1)) float32 contiguous.
+ * /scale, |X|^(1/c), *sqrt(sum w^2), inverse real DFT (imag of DC/Nyquist
+ * ignored), window, overlap-add, / overlap-added w^2, centre trim — fused.
+ * Returns BRV_ERR_NOLA where torch.istft raises.  X is NOT modified (the
+ * reference's in-place `x /= scale`, stft.py:114, is applied by the Python
+ * mirror when the caller relies on it).                                      */
+int brv_istft_forward(const brv_stft_plan* plan, const void* X,
+                      int64_t stride_signal, int64_t stride_bin,
+                      int64_t stride_frame, int64_t n_signals, int64_t n_frames,
+                      float* y, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* Adjoint of brv_istft_forward w.r.t. X (compression_factor == 1).
+ * gy : (n_signals, hop*(T-1)); gX : (n_signals, T, F) complex64 frame-major. */
+int brv_istft_forward_grad(const brv_stft_plan* plan, const float* gy,
+                           int64_t n_signals, int64_t n_frames, void* gX,
+                           void* workspace, size_t workspace_bytes,
+                           void* stream);
+size_t brv_stft_workspace_bytes(const brv_stft_plan* plan, int64_t n_signals,
+                                int64_t n_frames);
+
+/* ---- mel filterbank (stft.py:152-198) -------------------------------------
+ * Sparse (CSR) form of MelFilterbank.filters / inverse_filters applied along
+ * the second-to-last axis:  out[b, r, t] = sum_j vals[j] * x[b, cols[j], t],
+ * j in [rowptr[r], rowptr[r+1]).  x strides in elements; out contiguous
+ * (n_batch, n_rows_out, n_frames).                                           */
+int brv_mel_apply(const float* x, int64_t stride_batch, int64_t stride_row,
+                  int64_t stride_frame, int64_t n_batch, int n_rows_in,
+                  int64_t n_frames, const float* vals, const int32_t* cols,
+                  const int32_t* rowptr, int n_rows_out, float* out,
+                  void* stream);
+
+/* ---- FeatureExtractor.fbe family + FFNN.stack/decimate + StaticNormalizer ---
+ * (features.py:186-198, ffnn.py:122-135,175-187) in one pass over X:
+ *   P[f,t]   = mean_c |X[b,c,f,t]|^2
+ *   E[m,t]   = sum_f mel[m,f] P[f,t]             (CSR mel)
+ *   E       /= sum_m E + eps                      if normalize
+ *   E        = log(E + eps) | cbrt(E) | E         compression 1 | 2 | 0
+ *   out[b, k*n_mel + m, t'] = (E[m, max(t'*dec - k, 0)] - mean) / std,
+ *                              k = 0..stacks (mean/std nullable).
+ * X : complex64 (B, C, F, T) with element strides (complex units).
+ * out : (B, n_mel*(stacks+1), ceil(T/dec)) float32 contiguous.               */
+int brv_fbe_features(const void* X, int64_t stride_b, int64_t stride_c,
+                     int64_t stride_f, int64_t stride_t, int64_t n_batch,
+                     int n_channels, int n_bins, int64_t n_frames,
+                     const float* mel_vals, const int32_t* mel_cols,
+                     const int32_t* mel_rowptr, int n_mel, int normalize,
+                     int compression, float eps, int stacks, int decimation,
+                     const float* mean, const float* std, float* out,
+                     void* stream);
+
+/* FFNN.stack + decimate + StaticNormalizer on an existing feature tensor
+ * (ffnn.py:122-135,186-187): x (B, nf, T) contiguous -> (B, nf*(stacks+1), T'). */
+int brv_stack_normalize(const float* x, int64_t n_batch, int n_features,
+                        int64_t n_frames, int stacks, int decimation,
+                        const float* mean, const float* std, float* out,
+                        void* stream);
+/* CumulativeNormalizer.forward (ffnn.py:195-203): rows of length n_frames.   */
+int brv_cumulative_normalize(const float* x, int64_t n_rows, int64_t n_frames,
+                             float eps, float* out, void* stream);
+
+/* ---- criteria (criterion.py:21-101,229-234) --------------------------------
+ * One pass over estimate/target rows, masked to lengths[b], float64 moment
+ * accumulation (no (B,S,S,L) temporaries, no Python mask loop).
+ *   pairwise == 0 ("snr", criterion.py:96-101): x, y are (n_batch, n_rows, L);
+ *       out_db[b, r] = 10 log10( sum y^2 / (sum (y-x)^2 + eps) + eps ).
+ *   pairwise == 1 ("sisnr", criterion.py:45-61): x, y are (n_batch, S, L);
+ *       out_db[b, i, j] = SI-SNR of estimate j against target i (zero-mean over
+ *       the valid length).  The S! permutation max stays in the Python mirror.
+ * Row r of batch b starts at b*stride_batch + r*stride_row (elements).
+ * moments : (n_pairs, 6) float64 = [sum x, sum y, sum xy, sum x^2, sum y^2,
+ *           sum (y-x)^2] over the valid length, kept for the backward pass.
+ * workspace : brv_snr_workspace_bytes(n_pairs, length) bytes whose leading
+ *           4*n_pairs bytes (rounded up to 256) must be ZERO on entry; the
+ *           kernel leaves them zeroed again, so one cached buffer serves
+ *           every call on a stream.                                          */
+int brv_snr_forward(const float* x, const float* y, const int64_t* lengths,
+                    int64_t n_batch, int64_t n_rows, int64_t length,
+                    int64_t x_stride_batch, int64_t x_stride_row,
+                    int64_t y_stride_batch, int64_t y_stride_row, int pairwise,
+                    float eps, float* out_db, double* moments, void* workspace,
+                    size_t workspace_bytes, void* stream);
+size_t brv_snr_workspace_bytes(int64_t n_pairs, int64_t length);
+
+/* Gradient w.r.t. the estimate as an affine masked map per estimate row:
+ *   gx[b, r, n] = ca[b,r]*x[b,r,n] + cb[b,r]*y[b, ymap[b,r], n] + c0[b,r], n < lengths[b]
+ *   gx[b, r, n] = 0 otherwise.   (closed forms: SURVEY.md §8a')
+ * ca/cb/c0 : (n_batch*n_rows) float32; ymap : nullable int32 (identity).      */
+int brv_masked_affine(const float* x, const float* y, const int64_t* lengths,
+                      int64_t n_batch, int64_t n_rows, int64_t length,
+                      int64_t x_stride_batch, int64_t x_stride_row,
+                      int64_t y_stride_batch, int64_t y_stride_row,
+                      const float* ca, const float* cb, const float* c0,
+                      const int32_t* ymap, float* gx, void* stream);
+
+/* apply_mask (criterion.py:229-234) for callers that need the masked tensors
+ * themselves: out[b, ..., n] = n < lengths[b] ? x[b, ..., n] : 0.            */
+int brv_apply_mask(const float* x, const int64_t* lengths, int64_t n_batch,
+                   int64_t inner, int64_t length, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BREVER_B200_H */

@@ -1,0 +1,183 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports
+every symbol include/brever_b200.h declares, the host-side mirror keeps the
+reference's names / defaults / error behaviour, init-time constants are
+bit-identical to the reference's, and nothing silently falls back to CPU."""
+import inspect
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import brever_b200 as brv
+from brever_b200 import _lib
+from oracle import tf_oracle as O
+
+from _util import STFT_SHAPE_CASES, golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, 'include', 'brever_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(brv_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _header_functions()
+    assert len(names) >= 20
+    lib = _lib.lib()
+    for name in names:
+        assert hasattr(lib, name), f'{name} declared in the header but not exported'
+    assert set(names) == set(_lib.PROTOTYPES), \
+        set(names).symmetric_difference(_lib.PROTOTYPES)
+    assert lib.brv_abi_version() == 1
+    assert lib.brv_status_string(-4).decode() == 'window overlap add min: 1'
+
+
+def test_no_oracle_import_in_product():
+    """The product path must never route through the oracle."""
+    pkg = os.path.join(ROOT, 'brever_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src, os.path.join(dirpath, f)
+
+
+def test_cpu_tensors_fail_loudly():
+    stft = brv.STFT()
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        stft(torch.randn(4096))
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        stft.backward(torch.randn(257, 9, dtype=torch.complex64))
+    fb = brv.MelFilterbank()
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        fb(torch.rand(257, 4))
+    fe = brv.FeatureExtractor({'logfbe'}, fb)
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        fe(torch.randn(2, 257, 4, dtype=torch.complex64))
+    x = torch.randn(2, 1, 100)
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        brv.snr(x, x, torch.tensor([100, 100]))
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        brv.sisnr(x, x, torch.tensor([100, 100]))
+
+
+def test_stft_signature_and_attributes():
+    sig = inspect.signature(brv.STFT.__init__)
+    assert list(sig.parameters)[1:] == [
+        'frame_length', 'hop_length', 'window', 'center', 'pad_mode',
+        'normalized', 'onesided', 'compression_factor', 'scale_factor', 'n_fft']
+    defaults = {k: v.default for k, v in sig.parameters.items() if k != 'self'}
+    assert defaults == dict(frame_length=512, hop_length=256, window='hann',
+                            center=True, pad_mode='constant', normalized=True,
+                            onesided=True, compression_factor=1, scale_factor=1,
+                            n_fft=None)
+    st = brv.STFT()
+    assert (st.frame_length, st.hop_length, st.n_fft) == (512, 256, 512)
+    assert st.window.dtype == torch.float64 and st.window.shape == (512,)
+    assert abs(float(st.window.pow(2).sum()) - 192.0) < 1e-12
+    assert np.array_equal(st.window.numpy(), O.get_window('hann', 512)) or \
+        np.allclose(st.window.numpy(), O.get_window('hann', 512), atol=1e-16)
+    assert brv.STFT(window=None).window.eq(1).all()
+    assert brv.STFT(400, 100, n_fft=512).n_fft == 512
+    with pytest.raises(ValueError):
+        st(torch.zeros(10), return_type='nope')
+    with pytest.raises(ValueError):
+        st.backward(torch.zeros(10), input_type='nope')
+    # plain Python object, picklable, no nn.Module state
+    assert not isinstance(st, torch.nn.Module)
+    clone = pickle.loads(pickle.dumps(st))
+    assert clone.frame_length == 512 and clone._plans == {}
+
+
+@pytest.mark.parametrize('case', STFT_SHAPE_CASES)
+def test_frame_arithmetic_matches_reference(case):
+    """Integer frame arithmetic: bit-exact against shapes the reference produced."""
+    S, L, H, nfft, win = case
+    i = STFT_SHAPE_CASES.index(case)
+    ref = golden()[f'shape{i}_spec']
+    st = brv.STFT(frame_length=L, hop_length=H, window=win, n_fft=nfft)
+    assert st.n_bins == ref.shape[1]
+    assert st.n_frames(S) == ref.shape[2] == O.stft_frames(S, L, H, nfft)
+    assert st.frame_count(S) == O.frame_count(S, L, H)
+    assert st.pad(torch.zeros(S)).shape[-1] == S + O.right_padding(S, L, H)
+
+
+def test_frame_arithmetic_known_values():
+    st = brv.STFT(512, 256)
+    assert st.n_frames(64000) == 251 and st.n_frames(63999) == 251
+    assert st.n_frames(100) == 3 and st.n_frames(4000) == 17
+    assert brv.STFT(512, 128).n_frames(64000) == 501
+    assert brv.STFT(510, 128).n_frames(128000) == 1001
+    assert brv.STFT(510, 128).n_bins == 256
+    assert brv.STFT(256, 128).n_frames(64000) == 501
+    assert brv.STFT(400, 100, n_fft=512).n_frames(16000) == 161
+
+
+@pytest.mark.parametrize('tag,kw', [
+    ('mel512', {}), ('mel256', dict(n_fft=256)),
+    ('mel40', dict(n_filters=40, n_fft=400, fs=8000, fmax=4000))])
+def test_mel_constants_bit_identical_to_reference(tag, kw):
+    g = golden()
+    fb = brv.MelFilterbank(**kw)
+    assert np.array_equal(fb.filters.numpy(), g[tag + '_filters'])
+    assert np.array_equal(fb.fc.numpy(), g[tag + '_fc'])
+    assert np.array_equal(fb.scaling.numpy(), g[tag + '_scaling'])
+    assert np.array_equal(fb.inverse_filters.numpy(), g[tag + '_inverse'])
+    assert fb.n_filters == kw.get('n_filters', 64)
+    pickle.loads(pickle.dumps(fb))
+
+
+def test_feature_extractor_surface():
+    fb = brv.MelFilterbank()
+    fe = brv.FeatureExtractor({'logfbe', 'ild', 'mfcc'}, fb)
+    assert fe.features == ['ild', 'logfbe', 'mfcc']
+    assert fe.n_features == 64 + 64 + 13
+    assert fe.indices is None
+    with pytest.raises(ValueError, match='unrecognized feature'):
+        brv.FeatureExtractor({'nope'}, fb).n_features
+    with pytest.raises(ValueError, match='3 or 4 dimensional'):
+        fe.calc_feature(torch.zeros(257, 4, dtype=torch.complex64), 'logfbe')
+
+
+def test_registry_contract():
+    assert set(brv.CriterionRegistry.keys()) >= {'sisnr', 'snr'}
+    assert brv.init_criterion('snr') is brv.snr
+    assert brv.init_criterion('sisnr') is brv.sisnr
+    with pytest.raises(KeyError):
+        brv.CriterionRegistry.get('nope')
+    with pytest.raises(ValueError):
+        brv.CriterionRegistry.register('snr')(lambda: None)
+    reg = brv.Registry('thing')
+
+    @reg.register('cls')
+    class Thing:
+        def __init__(self, a=1):
+            self.a = a
+    assert reg.get('cls') is Thing
+
+
+def test_criterion_shape_asserts():
+    x = torch.zeros(2, 3, 10)
+    with pytest.raises(AssertionError):
+        brv.sisnr(x, torch.zeros(2, 3, 11), torch.tensor([10, 10]))
+    with pytest.raises(AssertionError):
+        brv.sisnr(x[0], x[0], torch.tensor([10, 10]))
+    with pytest.raises(AssertionError):
+        brv.snr(x[0, 0], x[0, 0], torch.tensor([10]))
+    with pytest.raises(AssertionError):
+        brv.apply_mask(x, x, torch.tensor([10]))
+
+
+def test_static_normalizer_state_dict_matches_reference_layout():
+    norm = brv.ffnn.StaticNormalizer(384)
+    sd = norm.state_dict()
+    assert set(sd) == {'mean', 'std'}
+    assert sd['mean'].shape == (384, 1) and sd['std'].shape == (384, 1)
+    front = brv.ffnn.FFNNFrontEnd()
+    assert front.input_size == 384
