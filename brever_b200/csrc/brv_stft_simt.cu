@@ -87,12 +87,16 @@ struct FrameEpilogue {  // (signal, frame, n_fft) time-domain frames into the wo
     }
 };
 
+// C tile = A tile (implicit) x basis, accumulated in float64: products of two
+// float32 values are exact in float64, so the result carries only the final
+// rounding to float32 (the reference's FFT has ~log2(N) roundings; a float32
+// dot product over n_fft terms would have ~n_fft/sqrt(2)).
 template <class ALoad, class Epi>
 __global__ void __launch_bounds__(THREADS)
 frame_gemm_kernel(ALoad aload, const float* __restrict__ B, int K, int n_cols,
                   int64_t n_frames, int tiles_per_signal, Epi epi) {
-    __shared__ float As[BK][BM + 4];
-    __shared__ __align__(16) float Bs[BK][BN];
+    __shared__ double As[BK][BM + 2];
+    __shared__ __align__(16) double Bs[BK][BN];
 
     const int tid = threadIdx.x;
     const int64_t sig = blockIdx.x / tiles_per_signal;
@@ -100,11 +104,11 @@ frame_gemm_kernel(ALoad aload, const float* __restrict__ B, int K, int n_cols,
     const int c0 = blockIdx.y * BN;
     const int tx = tid % 16, ty = tid / 16;
 
-    float acc[4][4];
+    double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
     for (int k0 = 0; k0 < K; k0 += BK) {
 #pragma unroll
@@ -115,7 +119,7 @@ frame_gemm_kernel(ALoad aload, const float* __restrict__ B, int K, int n_cols,
             else                 { k = e % BK; m = e / BK; }
             float v = 0.f;
             if (k0 + k < K && t0 + m < n_frames) v = aload(sig, t0 + m, k0 + k);
-            As[k][m] = v;
+            As[k][m] = (double)v;
         }
 #pragma unroll
         for (int r = 0; r < (BN * BK) / THREADS; ++r) {
@@ -123,20 +127,20 @@ frame_gemm_kernel(ALoad aload, const float* __restrict__ B, int K, int n_cols,
             int n = e % BN, k = e / BN;
             float v = 0.f;
             if (k0 + k < K && c0 + n < n_cols) v = __ldg(B + (int64_t)(k0 + k) * n_cols + c0 + n);
-            Bs[k][n] = v;
+            Bs[k][n] = (double)v;
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            float a[4];
+            double a[4], b[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
-            float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
@@ -144,7 +148,8 @@ frame_gemm_kernel(ALoad aload, const float* __restrict__ B, int K, int n_cols,
     for (int i = 0; i < 4; ++i) {
         int64_t t = t0 + ty * 4 + i;
         int col = c0 + tx * 4;
-        if (t < n_frames && col < n_cols) epi(sig, t, col, acc[i]);
+        float v[4] = {(float)acc[i][0], (float)acc[i][1], (float)acc[i][2], (float)acc[i][3]};
+        if (t < n_frames && col < n_cols) epi(sig, t, col, v);
     }
 }
 
