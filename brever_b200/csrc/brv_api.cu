@@ -10,13 +10,20 @@ bool brv_tc_supports_forward(const brv_stft_plan* p);
 int brv_tc_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
                         int64_t x_stride, float2* out, int64_t n_frames, cudaStream_t st);
 
+static int g_force_generic = -1;
+
 static int force_generic() {
-    static int v = -1;
-    if (v < 0) {
+    if (g_force_generic < 0) {
         const char* e = getenv("BRV_FORCE_GENERIC");
-        v = (e && e[0] == '1') ? 1 : 0;
+        g_force_generic = (e && e[0] == '1') ? 1 : 0;
     }
-    return v;
+    return g_force_generic;
+}
+
+extern "C" int brv_set_force_generic(int on) {
+    int prev = force_generic();
+    g_force_generic = on ? 1 : 0;
+    return prev;
 }
 
 extern "C" int brv_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_signals,

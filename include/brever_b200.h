@@ -51,6 +51,10 @@ const char* brv_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py's
  * `gpu_launches` evidence). */
 uint64_t brv_launch_count(void);
+/* Testing hook: route STFT calls through the generic CUDA-core kernels instead
+ * of the tensor-core kernels (also: env BRV_FORCE_GENERIC=1).  Returns the
+ * previous setting.  Both are CUDA paths; there is no CPU path to select. */
+int brv_set_force_generic(int on);
 /* SM count / compute capability of the current device; fails without a GPU. */
 int brv_device_query(int* sm_count, int* cc_major, int* cc_minor);
 
