@@ -6,7 +6,10 @@
 #include "brv_common.cuh"
 
 // brv_stft_tc.cu
-bool brv_tc_supports_forward(const brv_stft_plan* p);
+bool brv_tc_supported(const brv_stft_plan* p);
+int brv_tc_spec_to_frames(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t sb,
+                          int64_t sf, int64_t n_sig, int64_t n_frames, float* frames,
+                          cudaStream_t st);
 int brv_tc_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
                         int64_t x_stride, float2* out, int64_t n_frames, cudaStream_t st);
 
@@ -36,7 +39,7 @@ extern "C" int brv_stft_forward(const brv_stft_plan* p, const float* x, int64_t 
     int rc = brv_stft_geometry(p, samples, &n_frames, nullptr, nullptr);
     if (rc != BRV_OK) return rc;
     if (n_signals == 0) return BRV_OK;
-    if (!force_generic() && brv_tc_supports_forward(p))
+    if (!force_generic() && brv_tc_supported(p))
         return brv_tc_stft_forward(p, x, n_signals, samples, x_stride, (float2*)out, n_frames,
                                    (cudaStream_t)stream);
     return brv_simt_stft_forward(p, x, n_signals, samples, x_stride, (float2*)out, n_frames,
@@ -75,6 +78,15 @@ extern "C" int brv_istft_forward(const brv_stft_plan* p, const void* X, int64_t 
     BRV_REQUIRE(y, "output pointer is null");
     BRV_REQUIRE(workspace && workspace_bytes >= brv_stft_workspace_bytes(p, n_signals, n_frames),
                 "workspace too small");
+    if (!force_generic() && brv_tc_supported(p)) {
+        float* frames = (float*)workspace;
+        float* inv_env = frames + (size_t)n_signals * n_frames * p->n_fft;
+        rc = brv_tc_spec_to_frames(p, (const float2*)X, ss, sb, sf, n_signals, n_frames, frames,
+                                   (cudaStream_t)stream);
+        if (rc != BRV_OK) return rc;
+        return brv_overlap_add(p, frames, n_signals, n_frames, out_len, true, y, inv_env,
+                               (cudaStream_t)stream);
+    }
     return brv_simt_spec_to_signal(p, (const float2*)X, ss, sb, sf, n_signals, n_frames, out_len,
                                    true, y, (float*)workspace, (cudaStream_t)stream);
 }

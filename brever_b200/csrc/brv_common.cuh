@@ -68,5 +68,7 @@ int brv_simt_spec_to_signal(const brv_stft_plan* p, const float2* X, int64_t ss,
                             int64_t sb, int64_t sf, int64_t n_sig, int64_t n_frames,
                             int64_t out_len, bool inverse, float* y, float* ws,
                             cudaStream_t st);
+int brv_overlap_add(const brv_stft_plan* p, const float* frames, int64_t n_sig, int64_t n_frames,
+                    int64_t out_len, bool inverse, float* y, float* inv_env, cudaStream_t st);
 int brv_simt_istft_grad(const brv_stft_plan* p, const float* gy, int64_t n_sig,
                         int64_t n_frames, float2* gX, float* ws, cudaStream_t st);

@@ -233,13 +233,23 @@ int brv_simt_spec_to_signal(const brv_stft_plan* p, const float2* X, int64_t ss,
         rc = launch_gemm(a, basis, K, N, n_sig, n_frames, e, st);
     }
     if (rc != BRV_OK) return rc;
+    return brv_overlap_add(p, frames, n_sig, n_frames, out_len, inverse, y, inv_env, st);
+}
+
+// Overlap-add of (n_sig, T, n_fft) frames at stride hop with the centre trim;
+// inverse == true divides by the overlap-added squared window (torch.istft),
+// otherwise multiplies by scale_factor (adjoint of the forward transform).
+int brv_overlap_add(const brv_stft_plan* p, const float* frames, int64_t n_sig, int64_t n_frames,
+                    int64_t out_len, bool inverse, float* y, float* inv_env, cudaStream_t st) {
+    if (n_sig == 0 || out_len == 0) return BRV_OK;
+    const int N = p->n_fft;
     const int threads = 256;
     unsigned blocks = (unsigned)brv_ceil_div(out_len, threads);
     if (inverse) {
         inv_envelope_kernel<<<blocks, threads, 0, st>>>(p->window_sq, N, p->hop, n_frames, out_len, inv_env);
         BRV_LAUNCH_CHECK("inv_envelope_kernel");
     }
-    BRV_REQUIRE(n_sig < 65536, "more than 65535 signals per call on the generic path");
+    BRV_REQUIRE(n_sig < 65536, "more than 65535 signals per call");
     overlap_add_kernel<<<dim3(blocks, (unsigned)n_sig), threads, 0, st>>>(
         frames, N, p->hop, n_frames, out_len, inverse ? inv_env : nullptr,
         (float)p->scale, y);

@@ -1,30 +1,37 @@
-// Tensor-core STFT for sm_100a: framing + windowing + DFT as one tcgen05
-// contraction with fp32-grade accuracy.
+// Tensor-core DFT contractions for sm_100a (tcgen05 + TMEM + TMA), fp32-grade.
 //
-//   D[frame, col] = sum_k A[frame, k] * Bt[col, k]
+//   D[row, col] = sum_k A[row, k] * Bt[col, k]          (one 128 x 256 tile per CTA)
 //
-//   A  : 128 overlapping frames of one signal, built on the fly from the raw
-//        samples (centre / right zero padding by predication, never materialised
-//        in HBM), scaled per frame by a power of two and split into two fp16
-//        planes  a = a_hi + a_lo  (22 significant bits);
-//   Bt : the DFT basis with the window and 1/sqrt(sum w^2) folded in, transposed
-//        (K-major), split the same way at plan creation, streamed by TMA
-//        (SWIZZLE_64B) from L2 where it stays resident;
-//   D  : fp32 accumulators in tensor memory, three products per k-step
-//        (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo; the dropped a_lo*b_lo is 2^-22).
+// MODE_FWD  STFT.forward (brever/modules/stft.py:59-89)
+//   A   : 128 overlapping frames of one signal, built on the fly from the raw
+//         samples (centre / right zero padding by predication — never
+//         materialised in HBM);
+//   Bt  : DFT basis with the window and 1/sqrt(sum w^2) folded in;
+//   out : frame-major complex64 (signal, frame, bin) — the memory torch.stft
+//         returns — after |X|^(c-1) compression and scale_factor.
+// MODE_INV  the contraction inside STFT.backward (stft.py:111-136)
+//   A   : 128 spectrogram frames (any strides), /scale_factor and |X|^(1/c-1)
+//         applied in the loader;
+//   Bt  : inverse real-DFT basis with the Hermitian weights, 1/N, the window and
+//         sqrt(sum w^2) folded in;
+//   out : windowed time-domain frames (signal, frame, n_fft) for the overlap-add.
 //
-// Output columns are packed so that one-sided spectra of even n_fft need exactly
-// n_fft columns: col 0 = Re X[0], col 1 = Re X[N/2] (their imaginary parts are
-// identically zero), cols 2q, 2q+1 = Re, Im X[q].  The epilogue unpacks, applies
-// the per-frame scale, |X|^(c-1) compression and scale_factor, and writes the
-// frame-major complex64 layout torch.stft produces.
+// Precision: every A row is scaled by its own power of two and split into two
+// fp16 planes a = a_hi + a_lo (22 significant bits); the basis is split the same
+// way once at plan creation.  Three tensor-core products per k-step
+// (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, the dropped a_lo*b_lo is 2^-22) accumulate
+// in fp32 in tensor memory.  Measured max error vs float64: ~2e-6 of max|X|.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
-// issuer (one elected lane), warps 2-5 = A-tile builders, then epilogue.
+// Columns are packed so a one-sided spectrum of even n_fft is exactly n_fft wide:
+// col 0 = Re X[0], col 1 = Re X[N/2] (their imaginary parts are identically zero /
+// ignored), cols 2q, 2q+1 = Re, Im X[q].
+//
+// Warp roles (192 threads): warp 0 = TMA producer (basis k-blocks, SWIZZLE_64B),
+// warp 1 = TMEM owner + MMA issuer (one elected lane), warps 2-5 = A-tile
+// builders (global -> registers (prefetched) -> split -> swizzled smem), then the
+// epilogue (TMEM -> registers -> per-warp smem transpose -> coalesced stores).
 // Two CTAs are resident per SM (96 KB smem, 256 TMEM columns each) so one CTA's
 // epilogue overlaps the other's main loop.
-//
-// Reference semantics: brever/modules/stft.py:59-89.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -33,31 +40,40 @@
 
 namespace {
 
-constexpr int TILE_M = 128;          // frames per CTA (UMMA M)
-constexpr int TILE_N = 256;          // packed output columns per CTA (UMMA N)
+constexpr int MODE_FWD = 0, MODE_INV = 1;
+constexpr int TILE_M = 128;          // rows (frames) per CTA (UMMA M)
+constexpr int TILE_N = 256;          // output columns per CTA (UMMA N)
 constexpr int BK = 32;               // k per stage: 64-byte rows (SWIZZLE_64B)
 constexpr int UMMA_K = 16;
 constexpr int STAGES = 2;
 constexpr int A_PLANE = TILE_M * BK * 2;   // 8 KB  (one fp16 plane of the A tile)
 constexpr int B_PLANE = TILE_N * BK * 2;   // 16 KB
 constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;   // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 constexpr int NUM_THREADS = 192;
 constexpr int LOADER_THREADS = 128;
 constexpr int MAX_BLOCKS = 160;      // hop blocks spanned by one tile (127 + n_fft/hop)
+constexpr int EPI_PITCH = 36;        // floats per row of the per-warp transpose tile
 
 struct TcParams {
+    // forward: raw signal
     const float* x;
     int64_t x_stride, samples;
-    float2* out;
+    // inverse: spectrogram with element strides (complex units)
+    const float2* spec;
+    int64_t ss, sb, sf;
+    float pre_scale, pre_expo;   // 1/scale_factor, 1/c - 1
+    // output
+    float* out;                  // fwd: (sig, T, n_bins) complex ; inv: (sig, T, n_fft) floats
     int64_t n_frames;
     int n_fft, hop, n_bins;
-    int k_blocks;            // ceil(n_fft / BK)
-    int col_blocks;          // packed columns / TILE_N
-    int cols_pad;            // col_blocks * TILE_N (lo plane starts at this row)
+    int k_blocks;                // ceil(K / BK)
+    int col_blocks;              // packed columns / TILE_N
+    int cols_pad;                // col_blocks * TILE_N (lo plane starts at this row)
     int tiles_per_signal;
-    float basis_scale_inv;   // 1 / sB
-    float post_scale;        // scale_factor
-    float expo;              // compression_factor - 1
+    float basis_scale_inv;       // 1 / sB
+    float post_scale;            // fwd: scale_factor
+    float post_expo;             // fwd: compression_factor - 1
 };
 
 // ---- PTX helpers --------------------------------------------------------------
@@ -77,8 +93,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    const long long start = clock64();
-    while (true) {
+    long long start = 0;
+    for (uint32_t spins = 0;; ++spins) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -88,7 +104,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (ok) return;
-        if (clock64() - start > 4000000000LL) __trap();   // never hang the device
+        if ((spins & 1023) == 1023) {                        // never hang the device
+            if (start == 0) start = clock64();
+            else if (clock64() - start > 4000000000LL) __trap();
+        }
     }
 }
 __device__ __forceinline__ void fence_proxy_async() {
@@ -121,16 +140,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address
-    d |= (uint64_t)0 << 16;                                // LBO (unused: one swizzle atom along K)
-    d |= (uint64_t)(512 >> 4) << 32;                       // SBO: 8 rows * 64 B
+    d |= (uint64_t)(512 >> 4) << 32;                       // SBO: 8 rows * 64 B (LBO unused)
     d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
     d |= (uint64_t)4 << 61;                                // layout: SWIZZLE_64B
     return d;
 }
 // kind::f16, fp16 x fp16 -> fp32, both operands K-major
 __device__ __forceinline__ uint32_t umma_idesc_f16(int m, int n) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(m >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -160,29 +177,106 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// power of two s with max*s in [2^13, 2^14): fp16 keeps 11 bits of a_hi and the
+// power of two s with max*s in [2^13, 2^14): fp16 keeps 11 bits in a_hi and the
 // residual a_lo stays far above the fp16 subnormal floor.
-__device__ __forceinline__ float frame_scale(float mx) {
+__device__ __forceinline__ float row_scale(float mx) {
     if (!(mx > 0.f)) return 1.f;
     int e = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127;   // floor(log2(mx)), normal range
     if (e < -100) e = -100;
-    int se = 13 - e;                                            // in [-114, 113]
-    return __uint_as_float((uint32_t)(se + 127) << 23);
+    return __uint_as_float((uint32_t)(13 - e + 127) << 23);
+}
+__device__ __forceinline__ float finite_abs(float v) {       // |v|, or 0 for inf / nan
+    float a = fabsf(v);
+    return a <= 3.0e38f ? a : 0.f;
+}
+// X * |X|^expo for a complex value (expo = c - 1 or 1/c - 1); 0 stays 0
+__device__ __forceinline__ void compress(float& re, float& im, float expo) {
+    const float m2 = re * re + im * im;
+    const float g = m2 > 0.f ? powf(m2, 0.5f * expo) : 0.f;
+    re *= g;
+    im *= g;
+}
+__device__ __forceinline__ float compress_real(float v, float expo) {
+    return v != 0.f ? v * powf(fabsf(v), expo) : 0.f;
 }
 
+// ---- A-operand sources ----------------------------------------------------------
+// Forward: 32 consecutive samples of frame t starting at k0.
+struct FrameSource {
+    const float* xs;
+    int64_t samples, frame_start;     // sample index of k = 0 (may be negative)
+    int n_fft;
+    bool aligned;
+    __device__ __forceinline__ void load(int kb, float* v) const {
+        const int64_t i0 = frame_start + (int64_t)kb * BK;
+        const int k_left = n_fft - kb * BK;
+        if (aligned && i0 >= 0 && i0 + BK <= samples && k_left >= BK) {
+#pragma unroll
+            for (int c = 0; c < BK / 4; ++c) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(xs + i0) + c);
+                v[4 * c] = f.x; v[4 * c + 1] = f.y; v[4 * c + 2] = f.z; v[4 * c + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < BK; ++j) {
+                const int64_t idx = i0 + j;
+                v[j] = (j < k_left && idx >= 0 && idx < samples) ? __ldg(xs + idx) : 0.f;
+            }
+        }
+    }
+};
+// Inverse: 16 packed complex bins of spectrogram frame t starting at bin kb*16.
+struct SpectrumSource {
+    const float2* row;                // X[sig, 0, t]
+    int64_t sb;                       // bin stride (complex units)
+    int half;                         // n_fft / 2
+    float pre_scale, pre_expo;
+    bool live;                        // t < n_frames
+    __device__ __forceinline__ void load(int kb, float* v) const {
+#pragma unroll
+        for (int j = 0; j < BK / 2; ++j) {
+            const int qb = kb * (BK / 2) + j;
+            float re = 0.f, im = 0.f;
+            if (live && qb < half) {
+                const float2 c = __ldg(row + (int64_t)qb * sb);
+                re = c.x * pre_scale;
+                im = c.y * pre_scale;
+                if (qb == 0) {
+                    // packed pair: Re X[0], Re X[N/2].  The reference decompresses the
+                    // complex values (their imaginary parts count towards |X|) and the
+                    // c2r inverse then ignores the imaginary parts of both bins.
+                    float2 ny = __ldg(row + (int64_t)half * sb);
+                    ny.x *= pre_scale;
+                    ny.y *= pre_scale;
+                    if (pre_expo != 0.f) {
+                        compress(re, im, pre_expo);
+                        compress(ny.x, ny.y, pre_expo);
+                    }
+                    im = ny.x;
+                } else if (pre_expo != 0.f) {
+                    compress(re, im, pre_expo);
+                }
+            }
+            v[2 * j] = re;
+            v[2 * j + 1] = im;
+        }
+    }
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
-stft_tc_kernel(const __grid_constant__ CUtensorMap basis_map, const TcParams p) {
+dft_tc_kernel(const __grid_constant__ CUtensorMap basis_map, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float block_max[MAX_BLOCKS];
+    __shared__ uint32_t block_max[MAX_BLOCKS];
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
-    // work decomposition: blockIdx.x = (signal * tiles_per_signal + tile) * col_blocks + cb
+    // blockIdx.x = (signal * tiles_per_signal + tile) * col_blocks + cb
     const int cb = blockIdx.x % p.col_blocks;
     const int64_t tile_id = blockIdx.x / p.col_blocks;
     const int64_t sig = tile_id / p.tiles_per_signal;
@@ -196,6 +290,8 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap basis_map, const TcParams p) 
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (MODE == MODE_FWD)
+        for (int j = threadIdx.x; j < MAX_BLOCKS; j += NUM_THREADS) block_max[j] = 0u;
     if (warp == 1) {   // TMEM: 256 fp32 columns x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(&tmem_base_slot)),
@@ -252,58 +348,96 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap basis_map, const TcParams p) 
     } else {
         // ===================== A-tile builders, then epilogue ===================
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
-        const int row = q * 32 + lane;             // frame within the tile == TMEM lane
+        const int row = q * 32 + lane;             // row within the tile == TMEM lane
         const int lt = (warp - 2) * 32 + lane;     // 0..127 builder-thread index
         const int64_t t = t0 + row;
-        const float* xs = p.x + sig * p.x_stride;
         const int half = p.n_fft / 2;
+        float scale;
 
-        // per-hop-block maxima over the samples this tile touches
-        const int n_span = (p.n_fft + p.hop - 1) / p.hop;          // blocks per frame
-        const int n_blocks = TILE_M - 1 + n_span;
-        for (int j = lt; j < n_blocks; j += LOADER_THREADS) {
-            const int64_t i0 = (t0 + j) * p.hop - half;
-            float m = 0.f;
-            for (int i = 0; i < p.hop; ++i) {
-                const int64_t idx = i0 + i;
-                if (idx >= 0 && idx < p.samples) {
-                    float a = fabsf(__ldg(xs + idx));
-                    if (a <= 3.0e38f) m = fmaxf(m, a);           // ignore inf / nan
+        FrameSource fsrc;
+        SpectrumSource ssrc;
+        if (MODE == MODE_FWD) {
+            const float* xs = p.x + sig * p.x_stride;
+            // --- per-hop-block maxima over the samples this tile touches: one
+            //     coalesced pass, warp-reduced, then max over the blocks of a frame
+            const int64_t span0 = t0 * p.hop - half;                   // first sample (may be < 0)
+            const int span_len = (TILE_M - 1) * p.hop + p.n_fft;
+            const bool vec = ((((uintptr_t)xs) & 15) == 0) && ((span0 & 3) == 0) && ((p.hop & 3) == 0);
+            if (vec) {
+                // warp-uniform trip count: the warp votes inside the loop
+                for (int base = 0; base < span_len; base += 4 * LOADER_THREADS) {
+                    const int i = base + 4 * lt;
+                    const int64_t idx = span0 + i;
+                    float m = 0.f;
+                    int j = -1;
+                    if (i < span_len) {
+                        j = i / p.hop;                                  // 4 | hop: one block per float4
+                        if (idx >= 0 && idx + 4 <= p.samples) {
+                            const float4 f = __ldg(reinterpret_cast<const float4*>(xs + idx));
+                            m = fmaxf(fmaxf(finite_abs(f.x), finite_abs(f.y)),
+                                      fmaxf(finite_abs(f.z), finite_abs(f.w)));
+                        } else {
+                            for (int e = 0; e < 4; ++e)
+                                if (idx + e >= 0 && idx + e < p.samples)
+                                    m = fmaxf(m, finite_abs(__ldg(xs + idx + e)));
+                        }
+                    }
+                    const int j0 = __shfl_sync(0xffffffffu, j, 0);
+                    if (__all_sync(0xffffffffu, j == j0)) {
+                        const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+                        if (lane == 0 && j0 >= 0) atomicMax(&block_max[j0], wm);
+                    } else if (j >= 0) {
+                        atomicMax(&block_max[j], __float_as_uint(m));
+                    }
+                }
+            } else {
+                for (int i = lt; i < span_len; i += LOADER_THREADS) {
+                    const int64_t idx = span0 + i;
+                    if (idx >= 0 && idx < p.samples)
+                        atomicMax(&block_max[i / p.hop], __float_as_uint(finite_abs(__ldg(xs + idx))));
                 }
             }
-            block_max[j] = m;
+            asm volatile("bar.sync 1, %0;" ::"r"(LOADER_THREADS) : "memory");
+            const int n_span = (p.n_fft + p.hop - 1) / p.hop;          // blocks per frame
+            uint32_t mx = 0u;
+            for (int j = 0; j < n_span; ++j) mx = max(mx, block_max[row + j]);
+            scale = row_scale(__uint_as_float(mx));
+            fsrc.xs = xs;
+            fsrc.samples = p.samples;
+            fsrc.frame_start = t * p.hop - half;
+            fsrc.n_fft = p.n_fft;
+            fsrc.aligned = ((((uintptr_t)xs) & 15) == 0) && ((fsrc.frame_start & 3) == 0);
+        } else {
+            ssrc.live = t < p.n_frames;
+            ssrc.row = p.spec + sig * p.ss + (ssrc.live ? t : 0) * p.sf;
+            ssrc.sb = p.sb;
+            ssrc.half = half;
+            ssrc.pre_scale = p.pre_scale;
+            ssrc.pre_expo = p.pre_expo;
+            // --- row maximum (after the loader's own pre-processing)
+            float m = 0.f;
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                float v[BK];
+                ssrc.load(kb, v);
+#pragma unroll
+                for (int j = 0; j < BK; ++j) m = fmaxf(m, finite_abs(v[j]));
+            }
+            scale = row_scale(m);
         }
-        asm volatile("bar.sync 1, %0;" ::"r"(LOADER_THREADS) : "memory");
-        float mx = 0.f;
-        for (int j = 0; j < n_span; ++j) mx = fmaxf(mx, block_max[row + j]);
-        const float scale = frame_scale(mx);
 
-        const int64_t frame_start = t * p.hop - half;              // sample index of k = 0
-        const bool aligned = ((((uintptr_t)xs) & 15) == 0) && ((frame_start & 3) == 0);
         const uint32_t sw = (uint32_t)((row >> 1) & 3);
+        float cur[BK], nxt[BK];
+        if (MODE == MODE_FWD) fsrc.load(0, cur); else ssrc.load(0, cur);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
-            float v[BK];
-            const int64_t i0 = frame_start + (int64_t)kb * BK;
-            const int k_left = p.n_fft - kb * BK;                  // valid k in this block
-            if (aligned && i0 >= 0 && i0 + BK <= p.samples && k_left >= BK) {
-#pragma unroll
-                for (int c = 0; c < BK / 4; ++c) {
-                    float4 f = __ldg(reinterpret_cast<const float4*>(xs + i0) + c);
-                    v[4 * c] = f.x; v[4 * c + 1] = f.y; v[4 * c + 2] = f.z; v[4 * c + 3] = f.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < BK; ++j) {
-                    const int64_t idx = i0 + j;
-                    v[j] = (j < k_left && idx >= 0 && idx < p.samples) ? __ldg(xs + idx) : 0.f;
-                }
+            if (kb + 1 < p.k_blocks) {             // prefetch the next k-block into registers
+                if (MODE == MODE_FWD) fsrc.load(kb + 1, nxt); else ssrc.load(kb + 1, nxt);
             }
             uint32_t hi[BK / 2], lo[BK / 2];
 #pragma unroll
             for (int j = 0; j < BK; j += 2) {
-                const float a0 = v[j] * scale, a1 = v[j + 1] * scale;
+                const float a0 = cur[j] * scale, a1 = cur[j + 1] * scale;
                 const __half2 h = __floats2half2_rn(a0, a1);
                 const float2 hf = __half22float2(h);
                 const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
@@ -324,45 +458,60 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap basis_map, const TcParams p) 
             fence_proxy_async();                                   // generic -> async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
+#pragma unroll
+            for (int j = 0; j < BK; ++j) cur[j] = nxt[j];
         }
 
-        // ---- epilogue: TMEM -> registers -> unpack / scale / compress -> HBM ----
+        // ---- epilogue: TMEM -> registers -> per-warp transpose -> coalesced stores ----
         mbar_wait(&accum_bar, 0);
         tcgen05_fence_after();
-        const float g0 = p.basis_scale_inv / scale;   // undo the operand scalings
-        const float post = p.post_scale;             // scale_factor applies after compression
-        const bool live = t < p.n_frames;
-        float2* orow = p.out + (sig * p.n_frames + (live ? t : 0)) * (int64_t)p.n_bins;
+        // all MMAs have retired: the pipeline stages are free, reuse them as staging
+        float* stage = reinterpret_cast<float*>(tiles) + (size_t)(warp - 2) * 32 * EPI_PITCH;
+        const float g0 = p.basis_scale_inv / scale;                // undo the operand scalings
+        const int64_t row0 = t0 + q * 32;                          // first row of this warp
+        const int pitch = (MODE == MODE_FWD) ? 2 * p.n_bins : p.n_fft;   // floats per output row
+        float* obase = p.out + (sig * p.n_frames) * (int64_t)pitch;
 #pragma unroll 1
         for (int c = 0; c < TILE_N / 32; ++c) {
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            if (!live) continue;
             const int col0 = cb * TILE_N + c * 32;
+            if (col0 >= p.n_fft) break;                            // padded column block (uniform)
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                const int col = col0 + i;
-                if (col >= p.n_fft) break;                         // packed width == n_fft
-                float re = __uint_as_float(r[i]) * g0, im = __uint_as_float(r[i + 1]) * g0;
-                if (col == 0) {
-                    // packed pair: Re X[0] and Re X[N/2], both purely real
-                    float d = re, ny = im;
-                    if (p.expo != 0.f) {
-                        d = d != 0.f ? d * powf(fabsf(d), p.expo) : 0.f;
-                        ny = ny != 0.f ? ny * powf(fabsf(ny), p.expo) : 0.f;
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + 4 * j) =
+                    make_float4(__uint_as_float(r[4 * j]) * g0, __uint_as_float(r[4 * j + 1]) * g0,
+                                __uint_as_float(r[4 * j + 2]) * g0, __uint_as_float(r[4 * j + 3]) * g0);
+            __syncwarp();
+            // 16 lanes cover one 32-float row (128 contiguous bytes): two rows per pass
+            const int cp = (lane & 15) * 2;                        // column pair inside the chunk
+#pragma unroll 4
+            for (int rr = 0; rr < 32; rr += 2) {
+                const int rl = rr + (lane >> 4);
+                const int64_t tr = row0 + rl;
+                float2 v = *reinterpret_cast<const float2*>(stage + rl * EPI_PITCH + cp);
+                const int col = col0 + cp;
+                if (tr >= p.n_frames || col >= p.n_fft) continue;
+                float* orow = obase + tr * pitch;
+                if (MODE == MODE_FWD) {
+                    if (col == 0) {        // packed pair: Re X[0] and Re X[N/2], purely real
+                        float d = v.x, ny = v.y;
+                        if (p.post_expo != 0.f) {
+                            d = compress_real(d, p.post_expo);
+                            ny = compress_real(ny, p.post_expo);
+                        }
+                        *reinterpret_cast<float2*>(orow) = make_float2(d * p.post_scale, 0.f);
+                        *reinterpret_cast<float2*>(orow + 2 * half) = make_float2(ny * p.post_scale, 0.f);
+                    } else {
+                        if (p.post_expo != 0.f) compress(v.x, v.y, p.post_expo);
+                        *reinterpret_cast<float2*>(orow + col) =
+                            make_float2(v.x * p.post_scale, v.y * p.post_scale);
                     }
-                    orow[0] = make_float2(d * post, 0.f);
-                    orow[half] = make_float2(ny * post, 0.f);
                 } else {
-                    if (p.expo != 0.f) {
-                        const float m2 = re * re + im * im;
-                        const float g = m2 > 0.f ? powf(m2, 0.5f * p.expo) : 0.f;
-                        re *= g;
-                        im *= g;
-                    }
-                    orow[col >> 1] = make_float2(re * post, im * post);
+                    *reinterpret_cast<float2*>(orow + col) = v;
                 }
             }
+            __syncwarp();
         }
         tcgen05_fence_before();
     }
@@ -393,86 +542,116 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-struct TcPlan {
-    __half* basis;        // [2 planes][cols_pad][k_pad]
+struct TcBasis {
+    __half* data = nullptr;   // [2 planes][cols_pad][k_pad]
     CUtensorMap map;
-    int cols_pad, k_pad;
-    float scale_inv;
+    int cols_pad = 0, k_pad = 0;
+    float scale_inv = 1.f;
 };
+struct TcPlan {
+    TcBasis fwd, inv;
+};
+
+// Split `value(col, k)` (col < n_cols, k < n_k) into scaled fp16 hi/lo planes and
+// describe it with a SWIZZLE_64B tensor map of (BK x TILE_N) boxes.
+template <class F>
+int build_basis(TcBasis* b, int n_cols, int n_k, F value) {
+    EncodeTiledFn encode = encode_tiled();
+    if (!encode) return BRV_ERR_UNSUPPORTED;
+    b->cols_pad = (int)brv_ceil_div(n_cols, TILE_N) * TILE_N;
+    b->k_pad = (int)brv_ceil_div(n_k, BK) * BK;
+    double mx = 0;
+    for (int c = 0; c < n_cols; ++c)
+        for (int k = 0; k < n_k; ++k) mx = fmax(mx, fabs(value(c, k)));
+    if (!(mx > 0)) return BRV_ERR_UNSUPPORTED;
+    int e;
+    frexp(mx, &e);                                     // mx = m * 2^e, m in [0.5, 1)
+    const double sB = ldexp(1.0, 13 - e);              // mx * sB in [2^12, 2^13)
+    b->scale_inv = (float)(1.0 / sB);
+    std::vector<__half> host((size_t)2 * b->cols_pad * b->k_pad, __float2half_rn(0.f));
+    for (int c = 0; c < n_cols; ++c)
+        for (int k = 0; k < n_k; ++k) {
+            const double v = value(c, k) * sB;
+            const __half h = __float2half_rn((float)v);
+            const __half l = __float2half_rn((float)(v - (double)__half2float(h)));
+            host[(size_t)c * b->k_pad + k] = h;
+            host[((size_t)b->cols_pad + c) * b->k_pad + k] = l;
+        }
+    if (cudaMalloc((void**)&b->data, host.size() * sizeof(__half)) != cudaSuccess)
+        return brv_fail_cuda(cudaGetLastError(), "cudaMalloc(tensor-core basis)");
+    if (cudaMemcpy(b->data, host.data(), host.size() * sizeof(__half), cudaMemcpyHostToDevice) !=
+        cudaSuccess)
+        return brv_fail_cuda(cudaGetLastError(), "cudaMemcpy(tensor-core basis)");
+    cuuint64_t dims[2] = {(cuuint64_t)b->k_pad, (cuuint64_t)(2 * b->cols_pad)};
+    cuuint64_t strides[1] = {(cuuint64_t)b->k_pad * sizeof(__half)};
+    cuuint32_t box[2] = {BK, TILE_N};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = encode(&b->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b->data, dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS)
+        return brv_fail(BRV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+    return BRV_OK;
+}
+
+void fill_common(TcParams& prm, const brv_stft_plan* p, const TcBasis& b, int64_t n_frames) {
+    prm.n_frames = n_frames;
+    prm.n_fft = p->n_fft;
+    prm.hop = p->hop;
+    prm.n_bins = p->n_bins;
+    prm.k_blocks = b.k_pad / BK;
+    prm.col_blocks = b.cols_pad / TILE_N;
+    prm.cols_pad = b.cols_pad;
+    prm.tiles_per_signal = (int)brv_ceil_div(n_frames, TILE_M);
+    prm.basis_scale_inv = b.scale_inv;
+}
 
 }  // namespace
 
-bool brv_tc_supports_forward(const brv_stft_plan* p) {
-    return p->tc_fwd != nullptr;
-}
+bool brv_tc_supported(const brv_stft_plan* p) { return p->tc_fwd != nullptr; }
 
 int brv_tc_plan_init(brv_stft_plan* p, const std::vector<double>& fwd,
                      const std::vector<double>& inv) {
-    (void)inv;
     const int N = p->n_fft;
     // one-sided, even n_fft: packed width == n_fft; tiles must fit the hop-block table
     if (!p->onesided || (N % 2) != 0 || N < 32 || N > 4096) return BRV_OK;
     if (TILE_M - 1 + (N + p->hop - 1) / p->hop > MAX_BLOCKS) return BRV_OK;
-    EncodeTiledFn encode = encode_tiled();
-    if (!encode) return BRV_OK;   // driver too old for tensor maps: generic path only
+    if (!encode_tiled()) return BRV_OK;   // no tensor-map support: generic path only
 
-    const int F = p->n_bins;
-    const int cols_pad = (int)brv_ceil_div(N, TILE_N) * TILE_N;
-    const int k_pad = (int)brv_ceil_div(N, BK) * BK;
-    double mx = 0;
-    for (double v : fwd) mx = fmax(mx, fabs(v));
-    if (!(mx > 0)) return BRV_OK;
-    int e;
-    frexp(mx, &e);                                     // mx = m * 2^e, m in [0.5, 1)
-    const double sB = ldexp(1.0, 13 - e);              // mx * sB in [2^12, 2^13)
-    std::vector<__half> host((size_t)2 * cols_pad * k_pad, __float2half_rn(0.f));
-    for (int c = 0; c < N; ++c) {
-        // packed column c -> column of the interleaved (re, im) basis
-        int src = (c == 0) ? 0 : (c == 1) ? 2 * (N / 2) : c;
-        for (int k = 0; k < N; ++k) {
-            const double v = fwd[(size_t)k * 2 * F + src] * sB;
-            const __half h = __float2half_rn((float)v);
-            const __half l = __float2half_rn((float)(v - (double)__half2float(h)));
-            host[((size_t)c) * k_pad + k] = h;
-            host[((size_t)cols_pad + c) * k_pad + k] = l;
-        }
-    }
+    const int F = p->n_bins, half = N / 2;
+    // packed index c -> row / column of the interleaved (re, im) bases
+    auto unpack = [half](int c) { return c == 0 ? 0 : (c == 1 ? 2 * half : c); };
     TcPlan* tp = new TcPlan();
-    tp->cols_pad = cols_pad;
-    tp->k_pad = k_pad;
-    tp->scale_inv = (float)(1.0 / sB);
-    if (cudaMalloc((void**)&tp->basis, host.size() * sizeof(__half)) != cudaSuccess) {
+    // forward: Bt[col c][k] = fwd[k][unpack(c)]
+    int rc = build_basis(&tp->fwd, N, N, [&](int c, int k) {
+        return fwd[(size_t)k * 2 * F + unpack(c)];
+    });
+    // inverse: Bt[col n][k c] = inv[unpack(c)][n]
+    if (rc == BRV_OK)
+        rc = build_basis(&tp->inv, N, N, [&](int n, int c) {
+            return inv[(size_t)unpack(c) * N + n];
+        });
+    if (rc == BRV_OK &&
+        (cudaFuncSetAttribute(dft_tc_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              SMEM_BYTES) != cudaSuccess ||
+         cudaFuncSetAttribute(dft_tc_kernel<MODE_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              SMEM_BYTES) != cudaSuccess))
+        rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(dft_tc_kernel)");
+    if (rc != BRV_OK) {
+        cudaFree(tp->fwd.data);
+        cudaFree(tp->inv.data);
         delete tp;
-        return brv_fail_cuda(cudaGetLastError(), "cudaMalloc(tc basis)");
-    }
-    cudaMemcpy(tp->basis, host.data(), host.size() * sizeof(__half), cudaMemcpyHostToDevice);
-    cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)(2 * cols_pad)};
-    cuuint64_t strides[1] = {(cuuint64_t)k_pad * sizeof(__half)};
-    cuuint32_t box[2] = {BK, TILE_N};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult rc = encode(&tp->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, tp->basis, dims, strides,
-                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) {
-        cudaFree(tp->basis);
-        delete tp;
-        return brv_fail(BRV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
-    }
-    if (cudaFuncSetAttribute(stft_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             STAGES * STAGE_BYTES + 1024) != cudaSuccess) {
-        cudaFree(tp->basis);
-        delete tp;
-        return brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(stft_tc_kernel)");
+        return rc == BRV_ERR_UNSUPPORTED ? BRV_OK : rc;
     }
     p->tc_fwd = tp;
-    p->tc_fwd_cols = cols_pad;
     return BRV_OK;
 }
 
 void brv_tc_plan_free(brv_stft_plan* p) {
     TcPlan* tp = (TcPlan*)p->tc_fwd;
     if (tp) {
-        cudaFree(tp->basis);
+        cudaFree(tp->fwd.data);
+        cudaFree(tp->inv.data);
         delete tp;
         p->tc_fwd = nullptr;
     }
@@ -481,25 +660,38 @@ void brv_tc_plan_free(brv_stft_plan* p) {
 int brv_tc_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
                         int64_t x_stride, float2* out, int64_t n_frames, cudaStream_t st) {
     const TcPlan* tp = (const TcPlan*)p->tc_fwd;
-    TcParams prm;
+    TcParams prm = {};
+    fill_common(prm, p, tp->fwd, n_frames);
     prm.x = x;
     prm.x_stride = x_stride;
     prm.samples = samples;
-    prm.out = out;
-    prm.n_frames = n_frames;
-    prm.n_fft = p->n_fft;
-    prm.hop = p->hop;
-    prm.n_bins = p->n_bins;
-    prm.k_blocks = tp->k_pad / BK;
-    prm.col_blocks = tp->cols_pad / TILE_N;
-    prm.cols_pad = tp->cols_pad;
-    prm.tiles_per_signal = (int)brv_ceil_div(n_frames, TILE_M);
-    prm.basis_scale_inv = tp->scale_inv;
+    prm.out = reinterpret_cast<float*>(out);
     prm.post_scale = (float)p->scale;
-    prm.expo = (float)(p->compression - 1.0);
+    prm.post_expo = (float)(p->compression - 1.0);
     const int64_t grid = n_sig * prm.tiles_per_signal * prm.col_blocks;
     BRV_REQUIRE(grid < (1LL << 31), "too many tiles (%lld)", (long long)grid);
-    stft_tc_kernel<<<(unsigned)grid, NUM_THREADS, STAGES * STAGE_BYTES + 1024, st>>>(tp->map, prm);
-    BRV_LAUNCH_CHECK("stft_tc_kernel");
+    dft_tc_kernel<MODE_FWD><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(tp->fwd.map, prm);
+    BRV_LAUNCH_CHECK("dft_tc_kernel<fwd>");
+    return BRV_OK;
+}
+
+// Spectrogram (any strides) -> windowed time-domain frames (n_sig, T, n_fft) fp32.
+int brv_tc_spec_to_frames(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t sb,
+                          int64_t sf, int64_t n_sig, int64_t n_frames, float* frames,
+                          cudaStream_t st) {
+    const TcPlan* tp = (const TcPlan*)p->tc_fwd;
+    TcParams prm = {};
+    fill_common(prm, p, tp->inv, n_frames);
+    prm.spec = X;
+    prm.ss = ss;
+    prm.sb = sb;
+    prm.sf = sf;
+    prm.pre_scale = (float)(1.0 / p->scale);
+    prm.pre_expo = (float)(1.0 / p->compression - 1.0);
+    prm.out = frames;
+    const int64_t grid = n_sig * prm.tiles_per_signal * prm.col_blocks;
+    BRV_REQUIRE(grid < (1LL << 31), "too many tiles (%lld)", (long long)grid);
+    dft_tc_kernel<MODE_INV><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(tp->inv.map, prm);
+    BRV_LAUNCH_CHECK("dft_tc_kernel<inv>");
     return BRV_OK;
 }

@@ -111,3 +111,47 @@ def test_tensorcore_baseline_size_cfg2():
     e = rel_err(cpu(tc), cpu(gen))
     print(f'[tc-accuracy] cfg2 tc vs generic: {e}')
     assert e[0] < 2e-5
+
+
+@pytest.mark.parametrize('kw', CASES)
+@pytest.mark.parametrize('frames', [1, 9, 200])
+@pytest.mark.parametrize('layout', ['bin_major', 'frame_major'])
+def test_tensorcore_inverse_matches_generic_and_oracle(kw, frames, layout, capsys):
+    from _util import crandn
+    stft = brv.STFT(**kw)
+    spec = crandn((3, stft.n_bins, frames), 91)
+    spec[1] *= 1e-3
+    spec[2] *= 300.0
+    dev = spec.to(DEV)
+    if layout == 'frame_major':
+        dev = dev.transpose(1, 2).contiguous().transpose(1, 2)
+    try:
+        ref = O.istft(spec.numpy(), **kw)
+    except RuntimeError:
+        with pytest.raises(RuntimeError):
+            stft.backward(dev)
+        return
+    tc = stft.backward(dev)
+    with generic_path():
+        gen = stft.backward(dev)
+    assert tc.shape == gen.shape == ref.shape
+    worst = 0.0
+    for i in range(3):
+        e_tc = rel_err(cpu(tc[i]), ref[i])
+        worst = max(worst, e_tc[0])
+        assert e_tc[0] < 1e-4 and e_tc[1] < 1e-4, (kw, i, e_tc)
+        assert rel_err(cpu(gen[i]), ref[i])[0] < 1e-4
+    with capsys.disabled():
+        print(f'\n[tc-accuracy] inverse {kw} T={frames} {layout}: max-rel {worst:.2e}')
+
+
+def test_tensorcore_roundtrip_baseline_sizes():
+    for shape, kw in [((64, 64000), dict(frame_length=512, hop_length=128)),
+                      ((8, 128000), dict(frame_length=510, hop_length=128, normalized=False,
+                                         compression_factor=0.5, scale_factor=0.15))]:
+        mix, _ = synthetic_mixture(shape, 1000)
+        stft = brv.STFT(**kw)
+        y = stft.backward(stft(mix.to(DEV)))[..., :shape[-1]]
+        e = rel_err(cpu(y), mix.numpy())
+        print(f'[tc-accuracy] round trip {kw}: {e}')
+        assert e[0] < 1e-4 and e[1] < 1e-4
