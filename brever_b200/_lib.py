@@ -26,6 +26,7 @@ PROTOTYPES = {
     'brv_last_error': (_c.c_char_p, []),
     'brv_launch_count': (_c.c_uint64, []),
     'brv_set_force_generic': (_int, [_int]),
+    'brv_set_tc_variant': (_int, [_int]),
     'brv_device_query': (_int, [_ptr, _ptr, _ptr]),
     'brv_stft_plan_create': (_int, [_ptr, _int, _int, _int, _ptr, _int, _int,
                                     _f64, _f64]),

@@ -13,7 +13,20 @@ int brv_tc_spec_to_frames(const brv_stft_plan* p, const float2* X, int64_t ss, i
 int brv_tc_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
                         int64_t x_stride, float2* out, int64_t n_frames, cudaStream_t st);
 
+// brv_stft_fold.cu
+bool brv_fold_supported(const brv_stft_plan* p);
+int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
+                          int64_t x_stride, float2* out, int64_t n_frames, cudaStream_t st);
+
 static int g_force_generic = -1;
+static int g_tc_variant = 0;   // 0: folded kernels where supported, 1: dense contraction only
+
+extern "C" int brv_set_tc_variant(int variant) {
+    int prev = g_tc_variant;
+    g_tc_variant = variant == 1 ? 1 : 0;
+    return prev;
+}
+
 
 static int force_generic() {
     if (g_force_generic < 0) {
@@ -39,6 +52,9 @@ extern "C" int brv_stft_forward(const brv_stft_plan* p, const float* x, int64_t 
     int rc = brv_stft_geometry(p, samples, &n_frames, nullptr, nullptr);
     if (rc != BRV_OK) return rc;
     if (n_signals == 0) return BRV_OK;
+    if (!force_generic() && g_tc_variant == 0 && brv_fold_supported(p))
+        return brv_fold_stft_forward(p, x, n_signals, samples, x_stride, (float2*)out, n_frames,
+                                     (cudaStream_t)stream);
     if (!force_generic() && brv_tc_supported(p))
         return brv_tc_stft_forward(p, x, n_signals, samples, x_stride, (float2*)out, n_frames,
                                    (cudaStream_t)stream);

@@ -54,6 +54,7 @@ struct brv_stft_plan {
     void* tc_fwd;        // forward basis^T  [2 parts][cols_pad][n_fft] half
     void* tc_inv;        // inverse basis^T  [2 parts][n_fft][k_pad] half
     int tc_fwd_cols, tc_inv_k;
+    void* fold;          // symmetry-folded tensor-core plan, see brv_stft_fold.cu
     std::map<int64_t, bool> nola_cache;  // n_frames -> envelope is invertible
     std::mutex mu;
 };

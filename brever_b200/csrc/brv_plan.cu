@@ -87,6 +87,8 @@ static int upload(float** dst, const std::vector<float>& src) {
 int brv_tc_plan_init(brv_stft_plan* p, const std::vector<double>& fwd,
                      const std::vector<double>& inv);  // brv_stft_tc.cu
 void brv_tc_plan_free(brv_stft_plan* p);
+int brv_fold_plan_init(brv_stft_plan* p);                 // brv_stft_fold.cu
+void brv_fold_plan_free(brv_stft_plan* p);
 
 extern "C" int brv_stft_plan_create(brv_stft_plan** out, int frame_length,
                                     int hop_length, int n_fft,
@@ -114,6 +116,7 @@ extern "C" int brv_stft_plan_create(brv_stft_plan** out, int frame_length,
     p->scale = scale_factor;
     p->basis_fwd = p->basis_fwd_t = p->basis_inv = p->basis_inv_t = p->window_sq = nullptr;
     p->tc_fwd = p->tc_inv = nullptr;
+    p->fold = nullptr;
     p->tc_fwd_cols = p->tc_inv_k = 0;
     if (cudaGetDevice(&p->device) != cudaSuccess) {
         delete p;
@@ -173,6 +176,7 @@ extern "C" int brv_stft_plan_create(brv_stft_plan** out, int frame_length,
     if (rc == BRV_OK) rc = upload(&p->basis_inv_t, h_inv_t);
     if (rc == BRV_OK) rc = upload(&p->window_sq, h_wsq);
     if (rc == BRV_OK) rc = brv_tc_plan_init(p, fwd, inv);
+    if (rc == BRV_OK) rc = brv_fold_plan_init(p);
     if (rc != BRV_OK) {
         brv_stft_plan_destroy(p);
         return rc;
@@ -189,6 +193,7 @@ extern "C" int brv_stft_plan_destroy(brv_stft_plan* p) {
     cudaFree(p->basis_inv_t);
     cudaFree(p->window_sq);
     brv_tc_plan_free(p);
+    brv_fold_plan_free(p);
     delete p;
     return BRV_OK;
 }

@@ -55,6 +55,9 @@ uint64_t brv_launch_count(void);
  * of the tensor-core kernels (also: env BRV_FORCE_GENERIC=1).  Returns the
  * previous setting.  Both are CUDA paths; there is no CPU path to select. */
 int brv_set_force_generic(int on);
+/* Testing hook: 0 (default) = symmetry-folded tensor-core kernels where the plan
+ * supports them, 1 = the dense DFT contraction only.  Returns the previous value. */
+int brv_set_tc_variant(int variant);
 /* SM count / compute capability of the current device; fails without a GPU. */
 int brv_device_query(int* sm_count, int* cc_major, int* cc_minor);
 
