@@ -17,6 +17,9 @@ int brv_tc_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, i
 bool brv_fold_supported(const brv_stft_plan* p);
 int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
                           int64_t x_stride, float2* out, int64_t n_frames, cudaStream_t st);
+bool brv_fold_inverse_supported(const brv_stft_plan* p);
+int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t sb, int64_t sf,
+                   int64_t n_sig, int64_t n_frames, int64_t out_len, float* y, cudaStream_t st);
 
 static int g_force_generic = -1;
 static int g_tc_variant = 0;   // 0: folded kernels where supported, 1: dense contraction only
@@ -92,6 +95,9 @@ extern "C" int brv_istft_forward(const brv_stft_plan* p, const void* X, int64_t 
     if (rc != BRV_OK) return rc;
     if (n_signals == 0 || out_len == 0) return BRV_OK;
     BRV_REQUIRE(y, "output pointer is null");
+    if (!force_generic() && g_tc_variant == 0 && brv_fold_inverse_supported(p))
+        return brv_fold_istft(p, (const float2*)X, ss, sb, sf, n_signals, n_frames, out_len, y,
+                              (cudaStream_t)stream);   // fused overlap-add: no workspace
     BRV_REQUIRE(workspace && workspace_bytes >= brv_stft_workspace_bytes(p, n_signals, n_frames),
                 "workspace too small");
     if (!force_generic() && brv_tc_supported(p)) {

@@ -100,7 +100,9 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    uint8_t* stages = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // aligned by pointer arithmetic (not an integer round trip): the compiler keeps the
+    // shared address space and emits LDS / STS instead of generic loads and stores
+    uint8_t* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* span = reinterpret_cast<float*>(stages + SMEM_STAGES);
     float4* wtab = reinterpret_cast<float4*>(stages + SMEM_STAGES + SMEM_SPAN);
     float2* rowinfo = reinterpret_cast<float2*>(stages + SMEM_STAGES + SMEM_SPAN + SMEM_WTAB);
@@ -188,28 +190,39 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
         for (int j = bt; j < Q; j += BUILDER_THREADS) wtab[j] = __ldg(p.wtab + j);
 
         // ---- stage the sample span + per-32-sample maxima ------------------------
+        // SPAN_UNROLL independent 16-byte loads in flight per thread (the span is a
+        // first touch: HBM latency, not bandwidth, would bound a one-at-a-time loop)
         const bool vec = ((((uintptr_t)xs) & 15) == 0) && ((span0 & 3) == 0);
-        for (int wb = bw * 128; wb < span_pad; wb += BUILDERS * 128) {
-            const int i = wb + lane * 4;
-            const int64_t idx = span0 + i;
-            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < span_pad) {
-                if (vec && idx >= 0 && idx + 4 <= p.samples) {
-                    f = __ldg(reinterpret_cast<const float4*>(xs + idx));
-                } else {
-                    if (idx >= 0 && idx < p.samples) f.x = __ldg(xs + idx);
-                    if (idx + 1 >= 0 && idx + 1 < p.samples) f.y = __ldg(xs + idx + 1);
-                    if (idx + 2 >= 0 && idx + 2 < p.samples) f.z = __ldg(xs + idx + 2);
-                    if (idx + 3 >= 0 && idx + 3 < p.samples) f.w = __ldg(xs + idx + 3);
+        constexpr int SPAN_UNROLL = 6;
+        for (int wb0 = bw * 128; wb0 < span_pad; wb0 += SPAN_UNROLL * BUILDERS * 128) {
+            float4 f[SPAN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SPAN_UNROLL; ++u) {
+                const int i = wb0 + u * BUILDERS * 128 + lane * 4;
+                const int64_t idx = span0 + i;
+                f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < span_pad) {
+                    if (vec && idx >= 0 && idx + 4 <= p.samples) {
+                        f[u] = __ldg(reinterpret_cast<const float4*>(xs + idx));
+                    } else {
+                        if (idx >= 0 && idx < p.samples) f[u].x = __ldg(xs + idx);
+                        if (idx + 1 >= 0 && idx + 1 < p.samples) f[u].y = __ldg(xs + idx + 1);
+                        if (idx + 2 >= 0 && idx + 2 < p.samples) f[u].z = __ldg(xs + idx + 2);
+                        if (idx + 3 >= 0 && idx + 3 < p.samples) f[u].w = __ldg(xs + idx + 3);
+                    }
                 }
-                *reinterpret_cast<float4*>(span + i) = f;
             }
-            float m = fmaxf(fmaxf(finite_abs(f.x), finite_abs(f.y)),
-                            fmaxf(finite_abs(f.z), finite_abs(f.w)));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-            if ((lane & 7) == 0 && i < span_pad) bmax[i >> 5] = __float_as_uint(m);
+#pragma unroll
+            for (int u = 0; u < SPAN_UNROLL; ++u) {
+                const int i = wb0 + u * BUILDERS * 128 + lane * 4;
+                if (i < span_pad) *reinterpret_cast<float4*>(span + i) = f[u];
+                float m = fmaxf(fmaxf(finite_abs(f[u].x), finite_abs(f[u].y)),
+                                fmaxf(finite_abs(f[u].z), finite_abs(f[u].w)));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                if ((lane & 7) == 0 && i < span_pad) bmax[i >> 5] = __float_as_uint(m);
+            }
         }
         named_bar_sync(1, BUILDER_THREADS);
 
@@ -357,16 +370,522 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
     }
 }
 
+
+// =====================================================================================
+// Folded inverse: STFT.backward (brever/modules/stft.py:101-138) = per-frame real
+// inverse DFT, window, overlap-add, / overlap-added w^2, centre trim — one kernel,
+// no frames workspace in HBM.
+//
+// The transpose of the forward fold: with k = 2m / 2m+1 and n in [0, Q)
+//   Ce[n] = sum_m c_2m Re X[2m]   cos(2 pi 2m n / N)       (c_0 = 1, else 2)
+//   Co[n] = sum_m 2    Re X[2m+1] cos(2 pi (2m+1) n / N)
+//   Se[n] = sum_m 2    Im X[2m]   sin(2 pi 2m n / N)        (Im X[0] never contributes)
+//   So[n] = sum_m 2    Im X[2m+1] sin(2 pi (2m+1) n / N)
+//   f[n]      = Ce + Co - Se - So + (-1)^n Re X[N/2]
+//   f[N/2-n]  = Ce - Co + Se - So + (-1)^n Re X[N/2]
+//   f[N/2+n]  = Ce - Co - Se + So + (-1)^n Re X[N/2]
+//   f[N-n]    = Ce + Co + Se + So + (-1)^n Re X[N/2]
+// f[Q] and f[3Q] (the n = Q column) are accumulated in fp32 by the operand builders.
+// The frame is then multiplied by w[n] * sqrt(sum w^2) / N (window table).
+//
+// Overlap-add for hop = Q, 2Q or 4Q: in the epilogue a thread owns one frame (its
+// TMEM lane) and, per offset o in [0, Q), the four Q-long segments f[sQ + o].
+// Hop block u receives segment s of frame u - s / HQ: a lane rotation by s / HQ
+// (warp shuffle).  Lanes that rotate across the warp boundary deposit their partial
+// sum in a spill slot that is added at copy-out, so every output sample is written
+// once, in a fixed order (deterministic).  Tiles overlap by R - 1 frames so tile
+// boundaries need no exchange.  The finished hop blocks sit in shared memory (skewed
+// rows: conflict-free for lanes = frames) and leave as coalesced rows multiplied by
+// the cached 1 / envelope.
+constexpr int INV_REGION = 132096;             // stages (128 KB) aliased with the output rows
+constexpr int INV_SPILL = 12 * 256 * 4;        // 4 warp quarters x 3 halo blocks x H floats
+constexpr int INV_SMEM_BYTES = 1024 + INV_REGION + SMEM_WTAB + TILE_M * 16 + INV_SPILL + 2048;
+
+struct FoldInvParams {
+    const float2* spec;          // (sig, bin, frame) with element strides (complex units)
+    int64_t ss, sb, sf;
+    float pre_scale, pre_expo;   // 1 / scale_factor, 1 / c - 1
+    float* y;                    // (sig, out_len)
+    int64_t out_len;
+    const float* inv_env;        // out_len: 1 / overlap-added w^2 (trimmed grid)
+    const float4* wtab;          // Q entries: (w[n], w[N/2-n], w[N/2+n], w[N-n]) * norm / N
+    int64_t n_frames;
+    int n_fft, hop, q;
+    int halo, adv;               // R - 1 frames of overlap between tiles; 128 - halo
+    int tiles_per_signal;
+    int n_blocks;                // hop blocks that reach the output
+    int tmem_cols;
+    float wq, w3q;               // w[Q] * norm / N, w[3Q] * norm / N
+    float basis_scale_inv;
+};
+
+__device__ __forceinline__ float2 prep_bin(float2 c, float pre_scale, float pre_expo) {
+    c.x *= pre_scale;
+    c.y *= pre_scale;
+    if (pre_expo != 0.f) compress(c.x, c.y, pre_expo);
+    return c;
+}
+__device__ __forceinline__ float abs2_finite(float2 c) {
+    return fmaxf(finite_abs(c.x), finite_abs(c.y));
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld1_nowait(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(taddr));
+}
+__device__ __forceinline__ float rot(float v, int lane, int s) {
+    return __shfl_sync(0xffffffffu, v, (lane - s) & 31);
+}
+
+// HQ = hop / Q (1, 2 or 4); FRAMES_FAST: lanes run along frames when loading the
+// spectrogram (bin-major or arbitrary strides), else along bins (frame-major input).
+template <int HQ, bool FRAMES_FAST>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    uint8_t* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* orow = reinterpret_cast<float*>(stages);                 // aliases the stages
+    float4* wtab = reinterpret_cast<float4*>(stages + INV_REGION);
+    float4* rowinfo = reinterpret_cast<float4*>(stages + INV_REGION + SMEM_WTAB);
+    float* spill = reinterpret_cast<float*>(stages + INV_REGION + SMEM_WTAB + TILE_M * 16);
+    float* scratch = reinterpret_cast<float*>(stages + INV_REGION + SMEM_WTAB + TILE_M * 16 +
+                                              INV_SPILL);          // 2 KB: partial row sums
+
+    const int64_t sig = blockIdx.x / p.tiles_per_signal;
+    const int tile = (int)(blockIdx.x % p.tiles_per_signal);
+    const int64_t t0 = (int64_t)tile * p.adv;
+    const int N = p.n_fft, H = p.hop, Q = p.q, Hf = N / 2;
+    const int rows_eff = (int)max((int64_t)0, min((int64_t)TILE_M, p.n_frames - t0));
+    const int n_it = 2 * (Q / BK);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1 + BUILDERS);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: basis k-chunks =====================
+        if (elect_one()) {
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int kc = it >> 1, pair = it & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
+                uint8_t* sb = stages + (size_t)s * STAGE_BYTES + STAGE_A;
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl)
+                        tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
+                                    &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer ======================================
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_f16(TILE_M, Q);
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int kc = it >> 1, pair = it & 1;
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a0 = smem_u32(stages + (size_t)s * STAGE_BYTES);
+                const uint32_t b0 = a0 + STAGE_A;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t d = tmem_base + (uint32_t)((pair * 2 + j) * Q);
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                        const uint32_t off = ks * UMMA_K * 2;
+                        const uint64_t dah = umma_desc_sw64(a0 + (j * 2) * SUB_TILE + off);
+                        const uint64_t dal = umma_desc_sw64(a0 + (j * 2 + 1) * SUB_TILE + off);
+                        const uint64_t dbh = umma_desc_sw64(b0 + (j * 2) * SUB_TILE + off);
+                        const uint64_t dbl = umma_desc_sw64(b0 + (j * 2 + 1) * SUB_TILE + off);
+                        umma_f16(d, dah, dbh, idesc, (kc | ks) != 0);
+                        umma_f16(d, dal, dbh, idesc, 1);
+                        umma_f16(d, dah, dbl, idesc, 1);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&accum_bar);
+        }
+    } else {
+        // ===================== builders, then epilogue ==========================
+        const int bw = warp - 2;                   // 0..7
+        const int bt = bw * 32 + lane;             // 0..255
+        const float2* xs = p.spec + sig * p.ss;
+
+        for (int j = bt; j < Q; j += BUILDER_THREADS) wtab[j] = __ldg(p.wtab + j);
+
+        // ---- pass 1: per-row maximum (power-of-two scale) and the Nyquist bin -------
+        if (FRAMES_FAST) {
+            const int row = bt & 127, kh = bt >> 7;
+            const bool live = row < rows_eff;
+            const float2* xr = xs + (t0 + (live ? row : 0)) * p.sf;
+            float m = 0.f;
+            if (live) {
+                const int b0 = kh * Q;
+                for (int b = 0; b < Q; b += 8) {
+                    float2 c[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) c[e] = __ldg(xr + (int64_t)(b0 + b + e) * p.sb);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        c[e] = prep_bin(c[e], p.pre_scale, p.pre_expo);
+                        m = fmaxf(m, (b0 + b + e) == 0 ? finite_abs(c[e].x) : abs2_finite(c[e]));
+                    }
+                }
+            }
+            scratch[kh * 128 + row] = m;
+            named_bar_sync(1, BUILDER_THREADS);
+            if (kh == 0) {
+                float ny = 0.f;
+                if (live) ny = prep_bin(__ldg(xr + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x;
+                rowinfo[row] = make_float4(row_scale(fmaxf(m, scratch[128 + row])), 0.f, 0.f, ny);
+            }
+        } else {
+            // one warp per row, lanes along bins; two rows (18 loads per lane) in flight
+            for (int r0 = bw * 16; r0 < bw * 16 + 16; r0 += 2) {
+                float2 c[2][9];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const bool live = r0 + r < rows_eff;
+                    const float2* xr = xs + (t0 + r0 + r) * p.sf;
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) {
+                        const int b = e * 32 + lane;
+                        c[r][e] = (live && b <= Hf) ? __ldg(xr + (int64_t)b * p.sb)
+                                                    : make_float2(0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    float m = 0.f, ny = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) {
+                        const int b = e * 32 + lane;
+                        if (e * 32 > Hf) break;
+                        const float2 v = prep_bin(c[r][e], p.pre_scale, p.pre_expo);
+                        if (b == Hf) ny = v.x;
+                        else if (b < Hf) m = fmaxf(m, b == 0 ? finite_abs(v.x) : abs2_finite(v));
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                        ny += __shfl_xor_sync(0xffffffffu, ny, o);   // one lane holds it
+                    }
+                    if (lane == 0) rowinfo[r0 + r] = make_float4(row_scale(m), 0.f, 0.f, ny);
+                }
+            }
+        }
+        named_bar_sync(1, BUILDER_THREADS);
+
+        // ---- main loop: load, pre-process, scale, split, store -----------------------
+        if (FRAMES_FAST) {
+            const int row = bt & 127, kh = bt >> 7;
+            const bool live = row < rows_eff;
+            const float2* xr = xs + (t0 + (live ? row : 0)) * p.sf;
+            const float sc = rowinfo[row].x;
+            const uint32_t sw = (uint32_t)((row >> 1) & 3);
+            float pacc = 0.f, racc = 0.f;
+            for (int kc = 0; kc < Q / BK; ++kc) {
+                float2 c[32];                      // bins 64 kc + 32 kh + e
+                const int bin0 = 64 * kc + 32 * kh;
+                if (live) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) c[e] = __ldg(xr + (int64_t)(bin0 + e) * p.sb);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) c[e] = prep_bin(c[e], p.pre_scale, p.pre_expo);
+                    if (bin0 == 0) c[0].y = 0.f;   // Im X[0] is ignored by the c2r inverse
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        pacc += c[2 * j].x - c[2 * j + 2].x;          // (-1)^m Re X[2m]
+                        racc += c[2 * j + 1].y - c[2 * j + 3].y;      // (-1)^m Im X[2m+1]
+                    }
+                    if (bin0 == 0) pacc -= 0.5f * c[0].x;             // c_0 = 1, the others 2
+                }
+#pragma unroll
+                for (int pair = 0; pair < 2; ++pair) {
+                    const int it = kc * 2 + pair;
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (live) {
+                        uint8_t* sa = stages + (size_t)s * STAGE_BYTES + row * (BK * 2);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {          // sub-GEMM: even / odd bins
+#pragma unroll
+                            for (int ch = 0; ch < 2; ++ch) {   // 16-byte chunk = 8 k values
+                                uint32_t hi[4], lo[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int m0 = ch * 8 + 2 * e;     // local m of the k pair
+                                    const float2 ca = c[2 * m0 + j], cb = c[2 * m0 + 2 + j];
+                                    const float v0 = (pair ? ca.y : ca.x) * sc;
+                                    const float v1 = (pair ? cb.y : cb.x) * sc;
+                                    const __half2 h = __floats2half2_rn(v0, v1);
+                                    const float2 hf = __half22float2(h);
+                                    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                                    hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+                                    lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+                                }
+                                const uint32_t dst = (((uint32_t)(2 * kh + ch)) ^ sw) << 4;
+                                *reinterpret_cast<uint4*>(sa + (j * 2) * SUB_TILE + dst) =
+                                    make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                *reinterpret_cast<uint4*>(sa + (j * 2 + 1) * SUB_TILE + dst) =
+                                    make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            }
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);
+                }
+            }
+            scratch[kh * 128 + row] = pacc;
+            scratch[256 + kh * 128 + row] = racc;
+            named_bar_sync(1, BUILDER_THREADS);
+            if (kh == 0) {
+                rowinfo[row].y = 2.f * (scratch[row] + scratch[128 + row]);
+                rowinfo[row].z = 2.f * (scratch[256 + row] + scratch[384 + row]);
+            }
+        } else {
+            const int half = lane >> 4;            // which of the warp's two rows per pass
+            const int pr = lane & 15;              // m pair inside the 32-wide k-chunk
+            const uint32_t chunk = (uint32_t)(pr >> 2);
+            float pacc[8], racc[8], rscale[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                pacc[i] = racc[i] = 0.f;
+                const int row = bw * 16 + 2 * i + half;
+                rscale[i] = row < rows_eff ? rowinfo[row].x : 0.f;
+            }
+            for (int kc = 0; kc < Q / BK; ++kc) {
+                const int m0 = kc * BK + 2 * pr;   // bins 2 m0 .. 2 m0 + 3
+                float2 c[8][4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = bw * 16 + 2 * i + half;
+                    const float2* xr = xs + (t0 + row) * p.sf + (int64_t)(2 * m0) * p.sb;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        c[i][e] = row < rows_eff ? __ldg(xr + (int64_t)e * p.sb)
+                                                 : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) c[i][e] = prep_bin(c[i][e], p.pre_scale, p.pre_expo);
+                    if (m0 == 0) c[i][0].y = 0.f;  // Im X[0] is ignored by the c2r inverse
+                    pacc[i] += c[i][0].x - c[i][2].x;
+                    racc[i] += c[i][1].y - c[i][3].y;
+                    if (m0 == 0) pacc[i] -= 0.5f * c[i][0].x;
+                }
+#pragma unroll
+                for (int pair = 0; pair < 2; ++pair) {
+                    const int it = kc * 2 + pair;
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = stages + (size_t)s * STAGE_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = bw * 16 + 2 * i + half;
+                        if (row >= rows_eff) continue;
+                        const float sc = rscale[i];
+                        uint8_t* dst = sa + row * (BK * 2) +
+                                       ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
+                        if (pair == 0) {
+                            split_store(dst, dst + SUB_TILE, c[i][0].x * sc, c[i][2].x * sc);
+                            split_store(dst + 2 * SUB_TILE, dst + 3 * SUB_TILE, c[i][1].x * sc,
+                                        c[i][3].x * sc);
+                        } else {
+                            split_store(dst, dst + SUB_TILE, c[i][0].y * sc, c[i][2].y * sc);
+                            split_store(dst + 2 * SUB_TILE, dst + 3 * SUB_TILE, c[i][1].y * sc,
+                                        c[i][3].y * sc);
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float a = pacc[i], b = racc[i];
+#pragma unroll
+                for (int o = 8; o; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                }
+                const int row = bw * 16 + 2 * i + half;
+                if (pr == 0 && row < rows_eff) {
+                    rowinfo[row].y = 2.f * a;
+                    rowinfo[row].z = 2.f * b;
+                }
+            }
+        }
+        named_bar_sync(1, BUILDER_THREADS);
+
+        // ---- epilogue: TMEM -> segments -> lane-rotated overlap-add -> skewed rows ----
+        const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int hsel = bw >> 2;                  // which half of the offsets
+        const int row = q * 32 + lane;             // frame t0 + row == hop block t0 + row
+        const bool live = row < rows_eff;
+        const float4 ri = rowinfo[row];
+        const float g0 = live ? p.basis_scale_inv / ri.x : 0.f;
+        const float xny = live ? ri.w : 0.f;
+        // f[Q], f[3Q]: Q is even, so the Nyquist term enters with +1
+        const float fq = live ? (ri.y - ri.z + ri.w) * p.wq : 0.f;
+        const float f3q = live ? (ri.y + ri.z + ri.w) * p.w3q : 0.f;
+        mbar_wait(&accum_bar, 0);
+        tcgen05_fence_after();
+        const int pitch = H + 1;                   // skew: lanes (= frames) hit distinct banks
+        float* my_row = orow + row * pitch;
+        float* my_spill = spill + ((q + 1) * 3 + lane) * H;
+        const bool do_spill = q < 3 && lane < 3;
+        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int o_begin = hsel * (Q / 2), o_end = o_begin + Q / 2;
+        uint32_t carry[4];                         // column Q - c0 of Ce, Co, Se, So
+        if (o_begin > 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) tmem_ld1_nowait(tq + (uint32_t)(a * Q + Q - o_begin), &carry[a]);
+            tmem_ld_wait();
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) carry[a] = 0u;
+        }
+#pragma unroll 1
+        for (int c0 = o_begin; c0 < o_end; c0 += 8) {
+            uint32_t A[4][8], B[4][8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                tmem_ld8_nowait(tq + (uint32_t)(a * Q + c0), A[a]);
+                tmem_ld8_nowait(tq + (uint32_t)(a * Q + Q - c0 - 8), B[a]);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int o = c0 + i;
+                const float sg = (i & 1) ? -xny : xny;         // c0 is even
+                const float4 wa = wtab[o];
+                const float ce = __uint_as_float(A[0][i]), co = __uint_as_float(A[1][i]);
+                const float se = __uint_as_float(A[2][i]), so = __uint_as_float(A[3][i]);
+                float seg0 = (((ce + co) - (se + so)) * g0 + sg) * wa.x;
+                float seg2 = (((ce - co) - (se - so)) * g0 + sg) * wa.z;
+                float seg1, seg3;
+                if (o == 0) {
+                    seg1 = fq;
+                    seg3 = f3q;
+                } else {
+                    const float4 wb = wtab[Q - o];
+                    const float ce2 = __uint_as_float(i == 0 ? carry[0] : B[0][8 - i]);
+                    const float co2 = __uint_as_float(i == 0 ? carry[1] : B[1][8 - i]);
+                    const float se2 = __uint_as_float(i == 0 ? carry[2] : B[2][8 - i]);
+                    const float so2 = __uint_as_float(i == 0 ? carry[3] : B[3][8 - i]);
+                    seg1 = (((ce2 - co2) + (se2 - so2)) * g0 + sg) * wb.y;
+                    seg3 = (((ce2 + co2) + (se2 + so2)) * g0 + sg) * wb.w;
+                }
+                if (!live) seg0 = seg1 = seg2 = seg3 = 0.f;    // dead rows hold garbage
+                if (HQ == 1) {
+                    const float r1 = rot(seg1, lane, 1), r2 = rot(seg2, lane, 2),
+                                r3 = rot(seg3, lane, 3);
+                    float acc = seg0;
+                    if (lane >= 1) acc += r1;
+                    if (lane >= 2) acc += r2;
+                    if (lane >= 3) acc += r3;
+                    my_row[o] = acc;
+                    if (do_spill) {
+                        float sp = 0.f;
+                        if (lane < 1) sp += r1;
+                        if (lane < 2) sp += r2;
+                        sp += r3;
+                        my_spill[o] = sp;
+                    }
+                } else if (HQ == 2) {
+                    const float r2 = rot(seg2, lane, 1), r3 = rot(seg3, lane, 1);
+                    my_row[o] = lane >= 1 ? seg0 + r2 : seg0;
+                    my_row[Q + o] = lane >= 1 ? seg1 + r3 : seg1;
+                    if (do_spill && lane == 0) {
+                        my_spill[o] = r2;
+                        my_spill[Q + o] = r3;
+                    }
+                } else {
+                    my_row[o] = seg0;
+                    my_row[Q + o] = seg1;
+                    my_row[2 * Q + o] = seg2;
+                    my_row[3 * Q + o] = seg3;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) carry[a] = B[a][0];
+        }
+        tcgen05_fence_before();
+        named_bar_sync(1, BUILDER_THREADS);
+
+        // ---- copy-out: finished hop blocks, * 1 / envelope, centre trim ---------------
+        const int r_lo = tile == 0 ? 0 : p.halo;
+        float* ys = p.y + sig * p.out_len;
+        for (int r = r_lo + bw; r < TILE_M; r += BUILDERS) {
+            const int64_t u = t0 + r;
+            if (u >= p.n_blocks) break;
+            const float* src = orow + r * pitch;
+            const int qq = r >> 5, lr = r & 31;
+            const float* sp = (qq > 0 && lr < p.halo) ? spill + (qq * 3 + lr) * H : nullptr;
+            const int64_t i0 = u * H - Hf;
+            for (int off = lane; off < H; off += 32) {
+                const int64_t i = i0 + off;
+                if (i < 0 || i >= p.out_len) continue;
+                float v = src[off];
+                if (sp) v += sp[off];
+                ys[i] = v * __ldg(p.inv_env + i);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
 struct FoldBasis {
     __half* data = nullptr;      // [plane 2][sub 4][m Q][n Q]
     CUtensorMap map;
     float scale_inv = 1.f;
 };
 struct FoldPlan {
-    FoldBasis fwd;
+    FoldBasis fwd, inv;
     float4* wtab = nullptr;      // Q permuted, normalised window entries
+    float4* wtab_inv = nullptr;  // the same permutation of w * sqrt(sum w^2) / N
     float wq = 0.f, w3q = 0.f, wmax = 0.f;
+    float wq_inv = 0.f, w3q_inv = 0.f;
     int q = 0, tmem_cols = 0;
+    int hq = 0;                  // hop / Q when the fused overlap-add applies (1, 2, 4), else 0
+    std::map<int64_t, float*> inv_env;   // n_frames -> 1 / overlap-added w^2 (device)
 };
 
 // cos / sin of 2*pi*m/N with exact values on the axes
@@ -431,7 +950,10 @@ int build_fold_basis(FoldBasis* b, int Q, F value) {
 void free_fold(FoldPlan* fp) {
     if (!fp) return;
     cudaFree(fp->fwd.data);
+    cudaFree(fp->inv.data);
     cudaFree(fp->wtab);
+    cudaFree(fp->wtab_inv);
+    for (auto& kv : fp->inv_env) cudaFree(kv.second);
     delete fp;
 }
 
@@ -475,6 +997,46 @@ int brv_fold_plan_init(brv_stft_plan* p) {
         cudaFuncSetAttribute(stft_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SMEM_BYTES) != cudaSuccess)
         rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(stft_fold_kernel)");
+    // inverse: trigonometric basis with the Hermitian weights (c_0 = 1, else 2); the
+    // window, sqrt(sum w^2) and 1/N live in the permuted window table
+    if (rc == BRV_OK)
+        rc = build_fold_basis(&fp->inv, Q, [&](int sub, int n, int m) {
+            const long long k = (sub & 1) ? 2 * m + 1 : 2 * m;
+            double c, s;
+            unit_root(k * n, N, &c, &s);
+            const double wk = (k == 0) ? 1.0 : 2.0;
+            return wk * (sub < 2 ? c : s);
+        });
+    if (rc == BRV_OK) {
+        const double gw = p->norm / N;
+        std::vector<float4> wt(Q);
+        for (int n = 0; n < Q; ++n) {
+            wt[n].x = (float)(p->window[n] * gw);
+            wt[n].y = (float)(p->window[Hf - n] * gw);
+            wt[n].z = (float)(p->window[Hf + n] * gw);
+            wt[n].w = n ? (float)(p->window[N - n] * gw) : 0.f;
+        }
+        fp->wq_inv = (float)(p->window[Q] * gw);
+        fp->w3q_inv = (float)(p->window[3 * Q] * gw);
+        if (cudaMalloc((void**)&fp->wtab_inv, Q * sizeof(float4)) != cudaSuccess ||
+            cudaMemcpy(fp->wtab_inv, wt.data(), Q * sizeof(float4), cudaMemcpyHostToDevice) !=
+                cudaSuccess)
+            rc = brv_fail_cuda(cudaGetLastError(), "folded inverse window table");
+        const int H = p->hop;
+        if (H == Q || H == 2 * Q || H == 4 * Q)
+            if ((size_t)TILE_M * (H + 1) * sizeof(float) <= (size_t)INV_REGION && H <= 256)
+                fp->hq = H / Q;
+    }
+    if (rc == BRV_OK) {
+        const void* kernels[6] = {
+            (const void*)istft_fold_kernel<1, false>, (const void*)istft_fold_kernel<1, true>,
+            (const void*)istft_fold_kernel<2, false>, (const void*)istft_fold_kernel<2, true>,
+            (const void*)istft_fold_kernel<4, false>, (const void*)istft_fold_kernel<4, true>};
+        for (const void* k : kernels)
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     INV_SMEM_BYTES) != cudaSuccess)
+                rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_fold_kernel)");
+    }
     if (rc != BRV_OK) {
         free_fold(fp);
         return rc == BRV_ERR_UNSUPPORTED ? BRV_OK : rc;
@@ -518,5 +1080,98 @@ int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig,
     BRV_REQUIRE(grid < (1LL << 31), "too many tiles (%lld)", (long long)grid);
     stft_fold_kernel<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(fp->fwd.map, prm);
     BRV_LAUNCH_CHECK("stft_fold_kernel");
+    return BRV_OK;
+}
+
+
+bool brv_fold_inverse_supported(const brv_stft_plan* p) {
+    return p->fold != nullptr && ((const FoldPlan*)p->fold)->hq != 0;
+}
+
+// 1 / (overlap-added squared window) on the trimmed output grid, cached per frame
+// count (torch.istft divides by this envelope; NOLA was checked by the caller).
+static int fold_inv_envelope(const brv_stft_plan* p, int64_t n_frames, int64_t out_len,
+                             const float** out) {
+    brv_stft_plan* mp = const_cast<brv_stft_plan*>(p);
+    FoldPlan* fp = (FoldPlan*)p->fold;
+    std::lock_guard<std::mutex> lock(mp->mu);
+    auto it = fp->inv_env.find(n_frames);
+    if (it == fp->inv_env.end()) {
+        const int N = p->n_fft, H = p->hop;
+        std::vector<float> host((size_t)out_len);
+        for (int64_t i = 0; i < out_len; ++i) {
+            const int64_t pos = i + N / 2;
+            int64_t t_hi = pos / H;
+            if (t_hi > n_frames - 1) t_hi = n_frames - 1;
+            const int64_t t_lo = pos - N + 1 <= 0 ? 0 : (pos - N + H) / H;
+            double e = 0;
+            for (int64_t t = t_lo; t <= t_hi; ++t) {
+                const double w = p->window[pos - t * H];
+                e += w * w;
+            }
+            host[(size_t)i] = (float)(1.0 / e);
+        }
+        if (fp->inv_env.size() >= 64) {           // bounded cache
+            for (auto& kv : fp->inv_env) cudaFree(kv.second);
+            fp->inv_env.clear();
+        }
+        float* dev = nullptr;
+        BRV_CUDA(cudaMalloc((void**)&dev, (size_t)out_len * sizeof(float)));
+        cudaError_t e = cudaMemcpy(dev, host.data(), (size_t)out_len * sizeof(float),
+                                   cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(dev);
+            return brv_fail_cuda(e, "cudaMemcpy(inverse envelope; first call for this frame "
+                                    "count must not be inside a stream capture)");
+        }
+        it = fp->inv_env.emplace(n_frames, dev).first;
+    }
+    *out = it->second;
+    return BRV_OK;
+}
+
+int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t sb, int64_t sf,
+                   int64_t n_sig, int64_t n_frames, int64_t out_len, float* y, cudaStream_t st) {
+    const FoldPlan* fp = (const FoldPlan*)p->fold;
+    FoldInvParams prm = {};
+    int rc = fold_inv_envelope(p, n_frames, out_len, &prm.inv_env);
+    if (rc != BRV_OK) return rc;
+    prm.spec = X;
+    prm.ss = ss;
+    prm.sb = sb;
+    prm.sf = sf;
+    prm.pre_scale = (float)(1.0 / p->scale);
+    prm.pre_expo = (float)(1.0 / p->compression - 1.0);
+    prm.y = y;
+    prm.out_len = out_len;
+    prm.wtab = fp->wtab_inv;
+    prm.n_frames = n_frames;
+    prm.n_fft = p->n_fft;
+    prm.hop = p->hop;
+    prm.q = fp->q;
+    prm.halo = 4 / fp->hq - 1;
+    prm.adv = TILE_M - prm.halo;
+    prm.n_blocks = (int)brv_ceil_div(p->n_fft / 2 + out_len, p->hop);
+    prm.tiles_per_signal =
+        prm.n_blocks <= TILE_M ? 1 : 1 + (int)brv_ceil_div(prm.n_blocks - TILE_M, prm.adv);
+    prm.tmem_cols = fp->tmem_cols;
+    prm.wq = fp->wq_inv;
+    prm.w3q = fp->w3q_inv;
+    prm.basis_scale_inv = fp->inv.scale_inv;
+    const int64_t grid = n_sig * prm.tiles_per_signal;
+    BRV_REQUIRE(grid < (1LL << 31), "too many tiles (%lld)", (long long)grid);
+    const bool frames_fast = sb != 1;
+#define BRV_LAUNCH_INV(HQ_, FF_)                                                              \
+    istft_fold_kernel<HQ_, FF_><<<(unsigned)grid, NUM_THREADS, INV_SMEM_BYTES, st>>>(fp->inv.map, prm)
+    switch (fp->hq * 2 + (frames_fast ? 1 : 0)) {
+        case 2: BRV_LAUNCH_INV(1, false); break;
+        case 3: BRV_LAUNCH_INV(1, true); break;
+        case 4: BRV_LAUNCH_INV(2, false); break;
+        case 5: BRV_LAUNCH_INV(2, true); break;
+        case 8: BRV_LAUNCH_INV(4, false); break;
+        default: BRV_LAUNCH_INV(4, true); break;
+    }
+#undef BRV_LAUNCH_INV
+    BRV_LAUNCH_CHECK("istft_fold_kernel");
     return BRV_OK;
 }

@@ -155,3 +155,75 @@ def test_tensorcore_roundtrip_baseline_sizes():
         e = rel_err(cpu(y), mix.numpy())
         print(f'[tc-accuracy] round trip {kw}: {e}')
         assert e[0] < 1e-4 and e[1] < 1e-4
+
+
+# ---- folded inverse with the fused overlap-add (brv_stft_fold.cu) ----------------
+FOLD_INV_CASES = [
+    dict(frame_length=512, hop_length=128),                       # HQ = 1 (DCCRN)
+    dict(frame_length=512, hop_length=256),                       # HQ = 2 (FFNN)
+    dict(frame_length=256, hop_length=128, normalized=False),     # HQ = 2 (TF-GridNet)
+    dict(frame_length=256, hop_length=64),                        # HQ = 1
+    dict(frame_length=256, hop_length=256, window=None),          # HQ = 4 (no overlap)
+    dict(frame_length=128, hop_length=32, window='hamming'),      # Q = 32
+    dict(frame_length=384, hop_length=96),                        # Q = 96
+    dict(frame_length=400, hop_length=128, n_fft=512),            # window shorter than n_fft
+    dict(frame_length=512, hop_length=128, compression_factor=0.5, scale_factor=0.15,
+         normalized=False),                                        # SGMSE-style decompression
+]
+
+
+@pytest.mark.parametrize('kw', FOLD_INV_CASES)
+@pytest.mark.parametrize('frames', [2, 4, 127, 129, 131, 260, 501])
+@pytest.mark.parametrize('layout', ['bin_major', 'frame_major', 'strided'])
+def test_folded_inverse_matches_oracle(kw, frames, layout):
+    """Tile seams (128-frame tiles overlapping by R - 1 frames), warp seams (spill
+    slots) and all three load mappings against the float64 oracle."""
+    from _util import crandn
+    stft = brv.STFT(**kw)
+    spec = crandn((3, stft.n_bins, frames), 1234 + frames)
+    spec[1] *= 1e-3
+    spec[2, :, frames // 2:] *= 1e3       # loud second half: per-frame scales differ
+    if layout == 'bin_major':
+        dev = spec.to(DEV)
+    elif layout == 'frame_major':
+        dev = spec.to(DEV).transpose(1, 2).contiguous().transpose(1, 2)
+    else:   # every other frame of a wider buffer, bins not contiguous either
+        wide = torch.zeros((3, stft.n_bins + 3, 2 * frames), dtype=torch.complex64, device=DEV)
+        wide[:, 1:1 + stft.n_bins, ::2] = spec.to(DEV)
+        dev = wide[:, 1:1 + stft.n_bins, ::2]
+    try:
+        ref = O.istft(spec.numpy(), **kw)
+    except RuntimeError:
+        with pytest.raises(RuntimeError):
+            stft.backward(dev)
+        return
+    lib = _lib.lib()
+    n0 = lib.brv_launch_count()
+    got = stft.backward(dev)
+    assert lib.brv_launch_count() - n0 == 1, 'expected the single fused kernel'
+    assert got.shape == ref.shape
+    for i in range(3):
+        e = rel_err(cpu(got[i]), ref[i])
+        assert e[0] < 1e-4 and e[1] < 1e-4, (kw, frames, layout, i, e)
+    prev = lib.brv_set_tc_variant(1)       # dense contraction + separate overlap-add
+    try:
+        dense = stft.backward(dev)
+    finally:
+        lib.brv_set_tc_variant(prev)
+    assert rel_err(cpu(got), cpu(dense))[0] < 2e-5
+
+
+def test_folded_inverse_is_deterministic_and_nan_local():
+    stft = brv.STFT(512, 128)
+    from _util import crandn
+    spec = crandn((2, 257, 300), 5).to(DEV)
+    a = stft.backward(spec)
+    b = stft.backward(spec)
+    assert torch.equal(a, b)
+    spec[0, 40, 150] = complex(float('nan'), 0.0)
+    y = stft.backward(spec)
+    bad = ~torch.isfinite(y[0])
+    idx = bad.nonzero().flatten().cpu().numpy()
+    # frame 150 covers trimmed samples [150*128 - 256, 150*128 + 256)
+    assert idx.min() == 150 * 128 - 256 and idx.max() == 150 * 128 + 255
+    assert torch.isfinite(y[1]).all()
