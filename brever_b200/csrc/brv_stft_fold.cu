@@ -373,8 +373,8 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
 
 // =====================================================================================
 // Folded inverse: STFT.backward (brever/modules/stft.py:101-138) = per-frame real
-// inverse DFT, window, overlap-add, / overlap-added w^2, centre trim — one kernel,
-// no frames workspace in HBM.
+// inverse DFT, window, overlap-add, / overlap-added w^2, centre trim — one persistent
+// kernel, no frames workspace in HBM.
 //
 // The transpose of the forward fold: with k = 2m / 2m+1 and n in [0, Q)
 //   Ce[n] = sum_m c_2m Re X[2m]   cos(2 pi 2m n / N)       (c_0 = 1, else 2)
@@ -396,10 +396,34 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
 // once, in a fixed order (deterministic).  Tiles overlap by R - 1 frames so tile
 // boundaries need no exchange.  The finished hop blocks sit in shared memory (skewed
 // rows: conflict-free for lanes = frames) and leave as coalesced rows multiplied by
-// the cached 1 / envelope.
+// 1 / envelope (periodic in the interior: held in registers; edges from a cached table).
+//
+// Persistent CTAs (one per SM) walk the tile list.  Warp roles (512 threads, registers
+// re-balanced with setmaxnreg: 64 for warps 0-7, 192 for the builders):
+//   warp 0      TMA producer (basis k-chunks, 2-stage mbarrier ring)
+//   warp 1      TMEM owner + MMA issuer          (warps 2-3 idle)
+//   warps 8-15  operand builders (spectrogram -> scaled fp16 hi/lo planes), then the
+//               epilogue and copy-out of the same tile
+//   warps 4-7   scouts: stream the NEXT tile's spectrogram HBM -> shared-memory ring
+//               with cp.async (no registers held, ~48 KB in flight), take the per-row
+//               maxima the power-of-two scales need, and leave the tile L2-resident
+//               for the builders.  HBM streaming of tile i+1 overlaps the tensor-core
+//               work, epilogue and stores of tile i.
 constexpr int INV_REGION = 132096;             // stages (128 KB) aliased with the output rows
 constexpr int INV_SPILL = 12 * 256 * 4;        // 4 warp quarters x 3 halo blocks x H floats
-constexpr int INV_SMEM_BYTES = 1024 + INV_REGION + SMEM_WTAB + TILE_M * 16 + INV_SPILL + 2048;
+constexpr int INV_SCOUT_WARPS = 4;
+constexpr int INV_SCOUT_THREADS = INV_SCOUT_WARPS * 32;
+constexpr int INV_THREADS = 512;              // 4 warpgroups: control, scouts, 2 x builders
+constexpr int INV_FIRST_BUILDER = 8;
+constexpr int RING_DEPTH = 4;
+constexpr int RING_ROW = 258;                  // float2 per staged spectrogram row (257 + 1)
+constexpr int RING_CHUNK = 8 * RING_ROW * 8;   // 16512 B: 8 frames (or 16 bins x 128 frames)
+constexpr int INV_OFF_WTAB = INV_REGION;
+constexpr int INV_OFF_ROWINFO = INV_OFF_WTAB + SMEM_WTAB;
+constexpr int INV_OFF_SPILL = INV_OFF_ROWINFO + 2 * TILE_M * 16;
+constexpr int INV_OFF_SCRATCH = INV_OFF_SPILL + INV_SPILL;
+constexpr int INV_OFF_RING = INV_OFF_SCRATCH + 2048;
+constexpr int INV_SMEM_BYTES = 1024 + INV_OFF_RING + RING_DEPTH * RING_CHUNK;
 
 struct FoldInvParams {
     const float2* spec;          // (sig, bin, frame) with element strides (complex units)
@@ -408,21 +432,24 @@ struct FoldInvParams {
     float* y;                    // (sig, out_len)
     int64_t out_len;
     const float* inv_env;        // out_len: 1 / overlap-added w^2 (trimmed grid)
+    const float* env_per;        // hop: the same for interior hop blocks (periodic)
     const float4* wtab;          // Q entries: (w[n], w[N/2-n], w[N/2+n], w[N-n]) * norm / N
     int64_t n_frames;
     int n_fft, hop, q;
     int halo, adv;               // R - 1 frames of overlap between tiles; 128 - halo
     int tiles_per_signal;
+    int64_t total_tiles;
     int n_blocks;                // hop blocks that reach the output
     int tmem_cols;
     float wq, w3q;               // w[Q] * norm / N, w[3Q] * norm / N
     float basis_scale_inv;
 };
 
+template <bool DECOMP>
 __device__ __forceinline__ float2 prep_bin(float2 c, float pre_scale, float pre_expo) {
     c.x *= pre_scale;
     c.y *= pre_scale;
-    if (pre_expo != 0.f) compress(c.x, c.y, pre_expo);
+    if (DECOMP) compress(c.x, c.y, pre_expo);
     return c;
 }
 __device__ __forceinline__ float abs2_finite(float2 c) {
@@ -441,32 +468,48 @@ __device__ __forceinline__ void tmem_ld1_nowait(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ float rot(float v, int lane, int s) {
     return __shfl_sync(0xffffffffu, v, (lane - s) & 31);
 }
+// max over |re|, |im| as unsigned bit patterns (|x| ordering == uint ordering for
+// non-negative floats); a result >= 0x7f800000 flags an inf / nan in the set
+__device__ __forceinline__ uint32_t absbits_max(uint32_t m, float2 v) {
+    return max(m, max(__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu));
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N_PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
+}
 
 // HQ = hop / Q (1, 2 or 4); FRAMES_FAST: lanes run along frames when loading the
-// spectrogram (bin-major or arbitrary strides), else along bins (frame-major input).
-template <int HQ, bool FRAMES_FAST>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// spectrogram (bin-major or arbitrary strides), else along bins (frame-major input);
+// DECOMP: |X|^(1/c - 1) decompression in the loaders (keeps powf out of the common path).
+template <int HQ, bool FRAMES_FAST, bool DECOMP>
+__global__ void __launch_bounds__(INV_THREADS, 1)
 istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ __align__(8) uint64_t region_free;      // output rows copied out: stages reusable
+    __shared__ __align__(8) uint64_t scale_full[2];    // scouts -> builders (row scales ready)
+    __shared__ __align__(8) uint64_t scale_empty[2];   // builders -> scouts (slot reusable)
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     uint8_t* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* orow = reinterpret_cast<float*>(stages);                 // aliases the stages
-    float4* wtab = reinterpret_cast<float4*>(stages + INV_REGION);
-    float4* rowinfo = reinterpret_cast<float4*>(stages + INV_REGION + SMEM_WTAB);
-    float* spill = reinterpret_cast<float*>(stages + INV_REGION + SMEM_WTAB + TILE_M * 16);
-    float* scratch = reinterpret_cast<float*>(stages + INV_REGION + SMEM_WTAB + TILE_M * 16 +
-                                              INV_SPILL);          // 2 KB: partial row sums
+    float4* wtab = reinterpret_cast<float4*>(stages + INV_OFF_WTAB);
+    float4* rowinfo2 = reinterpret_cast<float4*>(stages + INV_OFF_ROWINFO);
+    float* spill = reinterpret_cast<float*>(stages + INV_OFF_SPILL);
+    float* scratch = reinterpret_cast<float*>(stages + INV_OFF_SCRATCH);
+    uint8_t* ring = stages + INV_OFF_RING;
 
-    const int64_t sig = blockIdx.x / p.tiles_per_signal;
-    const int tile = (int)(blockIdx.x % p.tiles_per_signal);
-    const int64_t t0 = (int64_t)tile * p.adv;
     const int N = p.n_fft, H = p.hop, Q = p.q, Hf = N / 2;
-    const int rows_eff = (int)max((int64_t)0, min((int64_t)TILE_M, p.n_frames - t0));
     const int n_it = 2 * (Q / BK);
 
     if (threadIdx.x == 0) {
@@ -475,393 +518,510 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&accum_bar, 1);
+        mbar_init(&region_free, BUILDERS);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&scale_full[b], INV_SCOUT_WARPS);
+            mbar_init(&scale_empty[b], BUILDERS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    for (int j = threadIdx.x; j < Q; j += INV_THREADS) wtab[j] = __ldg(p.wtab + j);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
+    if (warp < INV_FIRST_BUILDER) {
+    // ---- control + scout warpgroups: give registers back to the builders ----
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
         // ===================== TMA producer: basis k-chunks =====================
         if (elect_one()) {
-            for (int it = 0; it < n_it; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                const int kc = it >> 1, pair = it & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
-                uint8_t* sb = stages + (size_t)s * STAGE_BYTES + STAGE_A;
+            int g = 0;
+            int n = 0;
+            for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
+                if (n > 0) mbar_wait(&region_free, (uint32_t)((n - 1) & 1));
+                for (int it = 0; it < n_it; ++it, ++g) {
+                    const int s = g % STAGES;
+                    const uint32_t ph = (g / STAGES) & 1;
+                    const int kc = it >> 1, pair = it & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
+                    uint8_t* sb = stages + (size_t)s * STAGE_BYTES + STAGE_A;
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                    for (int j = 0; j < 2; ++j)
 #pragma unroll
-                    for (int pl = 0; pl < 2; ++pl)
-                        tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
-                                    &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
+                        for (int pl = 0; pl < 2; ++pl)
+                            tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
+                                        &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer ======================================
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_f16(TILE_M, Q);
-            for (int it = 0; it < n_it; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                const int kc = it >> 1, pair = it & 1;
-                mbar_wait(&full_bar[s], ph);
-                tcgen05_fence_after();
-                const uint32_t a0 = smem_u32(stages + (size_t)s * STAGE_BYTES);
-                const uint32_t b0 = a0 + STAGE_A;
+            int g = 0;
+            for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x) {
+                for (int it = 0; it < n_it; ++it, ++g) {
+                    const int s = g % STAGES;
+                    const uint32_t ph = (g / STAGES) & 1;
+                    const int kc = it >> 1, pair = it & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t a0 = smem_u32(stages + (size_t)s * STAGE_BYTES);
+                    const uint32_t b0 = a0 + STAGE_A;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const uint32_t d = tmem_base + (uint32_t)((pair * 2 + j) * Q);
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t d = tmem_base + (uint32_t)((pair * 2 + j) * Q);
 #pragma unroll
-                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                        const uint32_t off = ks * UMMA_K * 2;
-                        const uint64_t dah = umma_desc_sw64(a0 + (j * 2) * SUB_TILE + off);
-                        const uint64_t dal = umma_desc_sw64(a0 + (j * 2 + 1) * SUB_TILE + off);
-                        const uint64_t dbh = umma_desc_sw64(b0 + (j * 2) * SUB_TILE + off);
-                        const uint64_t dbl = umma_desc_sw64(b0 + (j * 2 + 1) * SUB_TILE + off);
-                        umma_f16(d, dah, dbh, idesc, (kc | ks) != 0);
-                        umma_f16(d, dal, dbh, idesc, 1);
-                        umma_f16(d, dah, dbl, idesc, 1);
+                        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                            const uint32_t off = ks * UMMA_K * 2;
+                            const uint64_t dah = umma_desc_sw64(a0 + (j * 2) * SUB_TILE + off);
+                            const uint64_t dal = umma_desc_sw64(a0 + (j * 2 + 1) * SUB_TILE + off);
+                            const uint64_t dbh = umma_desc_sw64(b0 + (j * 2) * SUB_TILE + off);
+                            const uint64_t dbl = umma_desc_sw64(b0 + (j * 2 + 1) * SUB_TILE + off);
+                            umma_f16(d, dah, dbh, idesc, (kc | ks) != 0);
+                            umma_f16(d, dal, dbh, idesc, 1);
+                            umma_f16(d, dah, dbl, idesc, 1);
+                        }
                     }
+                    umma_commit(&empty_bar[s]);
                 }
-                umma_commit(&empty_bar[s]);
-            }
-            umma_commit(&accum_bar);
-        }
-    } else {
-        // ===================== builders, then epilogue ==========================
-        const int bw = warp - 2;                   // 0..7
-        const int bt = bw * 32 + lane;             // 0..255
-        const float2* xs = p.spec + sig * p.ss;
-
-        for (int j = bt; j < Q; j += BUILDER_THREADS) wtab[j] = __ldg(p.wtab + j);
-
-        // ---- pass 1: per-row maximum (power-of-two scale) and the Nyquist bin -------
-        if (FRAMES_FAST) {
-            const int row = bt & 127, kh = bt >> 7;
-            const bool live = row < rows_eff;
-            const float2* xr = xs + (t0 + (live ? row : 0)) * p.sf;
-            float m = 0.f;
-            if (live) {
-                const int b0 = kh * Q;
-                for (int b = 0; b < Q; b += 8) {
-                    float2 c[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) c[e] = __ldg(xr + (int64_t)(b0 + b + e) * p.sb);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        c[e] = prep_bin(c[e], p.pre_scale, p.pre_expo);
-                        m = fmaxf(m, (b0 + b + e) == 0 ? finite_abs(c[e].x) : abs2_finite(c[e]));
-                    }
-                }
-            }
-            scratch[kh * 128 + row] = m;
-            named_bar_sync(1, BUILDER_THREADS);
-            if (kh == 0) {
-                float ny = 0.f;
-                if (live) ny = prep_bin(__ldg(xr + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x;
-                rowinfo[row] = make_float4(row_scale(fmaxf(m, scratch[128 + row])), 0.f, 0.f, ny);
-            }
-        } else {
-            // one warp per row, lanes along bins; two rows (18 loads per lane) in flight
-            for (int r0 = bw * 16; r0 < bw * 16 + 16; r0 += 2) {
-                float2 c[2][9];
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const bool live = r0 + r < rows_eff;
-                    const float2* xr = xs + (t0 + r0 + r) * p.sf;
-#pragma unroll
-                    for (int e = 0; e < 9; ++e) {
-                        const int b = e * 32 + lane;
-                        c[r][e] = (live && b <= Hf) ? __ldg(xr + (int64_t)b * p.sb)
-                                                    : make_float2(0.f, 0.f);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    float m = 0.f, ny = 0.f;
-#pragma unroll
-                    for (int e = 0; e < 9; ++e) {
-                        const int b = e * 32 + lane;
-                        if (e * 32 > Hf) break;
-                        const float2 v = prep_bin(c[r][e], p.pre_scale, p.pre_expo);
-                        if (b == Hf) ny = v.x;
-                        else if (b < Hf) m = fmaxf(m, b == 0 ? finite_abs(v.x) : abs2_finite(v));
-                    }
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                        ny += __shfl_xor_sync(0xffffffffu, ny, o);   // one lane holds it
-                    }
-                    if (lane == 0) rowinfo[r0 + r] = make_float4(row_scale(m), 0.f, 0.f, ny);
-                }
+                umma_commit(&accum_bar);
             }
         }
-        named_bar_sync(1, BUILDER_THREADS);
-
-        // ---- main loop: load, pre-process, scale, split, store -----------------------
-        if (FRAMES_FAST) {
-            const int row = bt & 127, kh = bt >> 7;
-            const bool live = row < rows_eff;
-            const float2* xr = xs + (t0 + (live ? row : 0)) * p.sf;
-            const float sc = rowinfo[row].x;
-            const uint32_t sw = (uint32_t)((row >> 1) & 3);
-            float pacc = 0.f, racc = 0.f;
-            for (int kc = 0; kc < Q / BK; ++kc) {
-                float2 c[32];                      // bins 64 kc + 32 kh + e
-                const int bin0 = 64 * kc + 32 * kh;
-                if (live) {
+    } else if (warp >= 4) {
+        // ===================== scouts: row maxima of the next tile ===================
+        const int sw = warp - 4;                   // 0..3
+        const int st = sw * 32 + lane;             // 0..127
+        int n = 0;
+        for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
+            const int slot = n & 1;
+            mbar_wait(&scale_empty[slot], (uint32_t)(((n >> 1) & 1) ^ 1));
+            float4* ri = rowinfo2 + slot * TILE_M;
+            const int64_t sig = tile_id / p.tiles_per_signal;
+            const int64_t t0 = (int64_t)(tile_id % p.tiles_per_signal) * p.adv;
+            const int rows_eff = (int)max((int64_t)0, min((int64_t)TILE_M, p.n_frames - t0));
+            const float2* xs = p.spec + sig * p.ss;
+            if (FRAMES_FAST) {
+                // thread = frame; chunk = 16 bins x 128 frames; a thread scans only what it
+                // copied itself: cp.async group waits are the only synchronisation
+                const int nch = Hf / 16;
+                const bool live = st < rows_eff;
+                const float2* col = xs + (t0 + (live ? st : 0)) * p.sf;
+                float m = 0.f;
+                for (int c = 0; c < nch + RING_DEPTH - 1; ++c) {
+                    if (c < nch && live) {
+                        float2* dst = reinterpret_cast<float2*>(ring + (c % RING_DEPTH) * RING_CHUNK) + st;
+                        const float2* src = col + (int64_t)(16 * c) * p.sb;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) c[e] = __ldg(xr + (int64_t)(bin0 + e) * p.sb);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) c[e] = prep_bin(c[e], p.pre_scale, p.pre_expo);
-                    if (bin0 == 0) c[0].y = 0.f;   // Im X[0] is ignored by the c2r inverse
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        pacc += c[2 * j].x - c[2 * j + 2].x;          // (-1)^m Re X[2m]
-                        racc += c[2 * j + 1].y - c[2 * j + 3].y;      // (-1)^m Im X[2m+1]
+                        for (int e = 0; e < 16; ++e) cp_async8(dst + e * TILE_M, src + (int64_t)e * p.sb);
                     }
-                    if (bin0 == 0) pacc -= 0.5f * c[0].x;             // c_0 = 1, the others 2
-                }
+                    cp_async_commit();
+                    if (c >= RING_DEPTH - 1) {
+                        cp_async_wait<RING_DEPTH - 1>();
+                        const int cc = c - (RING_DEPTH - 1);
+                        const float2* src =
+                            reinterpret_cast<const float2*>(ring + (cc % RING_DEPTH) * RING_CHUNK) + st;
+                        if (live) {
+                            if (DECOMP) {
 #pragma unroll
-                for (int pair = 0; pair < 2; ++pair) {
-                    const int it = kc * 2 + pair;
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    if (live) {
-                        uint8_t* sa = stages + (size_t)s * STAGE_BYTES + row * (BK * 2);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {          // sub-GEMM: even / odd bins
-#pragma unroll
-                            for (int ch = 0; ch < 2; ++ch) {   // 16-byte chunk = 8 k values
-                                uint32_t hi[4], lo[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int m0 = ch * 8 + 2 * e;     // local m of the k pair
-                                    const float2 ca = c[2 * m0 + j], cb = c[2 * m0 + 2 + j];
-                                    const float v0 = (pair ? ca.y : ca.x) * sc;
-                                    const float v1 = (pair ? cb.y : cb.x) * sc;
-                                    const __half2 h = __floats2half2_rn(v0, v1);
-                                    const float2 hf = __half22float2(h);
-                                    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                                    hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-                                    lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+                                for (int e = 0; e < 16; ++e) {
+                                    float2 v = prep_bin<true>(src[e * TILE_M], p.pre_scale, p.pre_expo);
+                                    if (cc == 0 && e == 0) v.y = 0.f;
+                                    m = fmaxf(m, abs2_finite(v));
                                 }
-                                const uint32_t dst = (((uint32_t)(2 * kh + ch)) ^ sw) << 4;
-                                *reinterpret_cast<uint4*>(sa + (j * 2) * SUB_TILE + dst) =
-                                    make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                                *reinterpret_cast<uint4*>(sa + (j * 2 + 1) * SUB_TILE + dst) =
-                                    make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            } else {
+                                float2 v[16];
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) v[e] = src[e * TILE_M];
+                                if (cc == 0) v[0].y = 0.f;
+                                uint32_t mb = 0u;
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) mb = absbits_max(mb, v[e]);
+                                if (mb >= 0x7f800000u) {      // inf / nan: exclude them
+                                    float mf = 0.f;
+#pragma unroll
+                                    for (int e = 0; e < 16; ++e) mf = fmaxf(mf, abs2_finite(v[e]));
+                                    mb = __float_as_uint(mf);
+                                }
+                                m = fmaxf(m, __uint_as_float(mb) * fabsf(p.pre_scale));
                             }
                         }
                     }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[s]);
+                }
+                float ny = 0.f;
+                if (live)
+                    ny = prep_bin<DECOMP>(__ldg(col + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x;
+                ri[st] = make_float4(row_scale(m), 0.f, 0.f, ny);
+            } else {
+                // chunk = 8 frames; warp sw owns rows sw and sw + 4 of every chunk (bins contiguous),
+                // lanes along bins, so only warp-level synchronisation is needed
+                const int nch = TILE_M / 8;
+                constexpr int ROWS_PER_WARP = 8 / INV_SCOUT_WARPS;
+                for (int c = 0; c < nch + RING_DEPTH - 1; ++c) {
+                    if (c < nch) {
+                        float2* dst = reinterpret_cast<float2*>(ring + (c % RING_DEPTH) * RING_CHUNK);
+#pragma unroll
+                        for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+                            const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * c + r;
+                            if (row < rows_eff) {
+                                const float2* xr = xs + (t0 + row) * p.sf;
+#pragma unroll
+                                for (int j = 0; j < 9; ++j) {
+                                    const int b = j * 32 + lane;
+                                    if (b <= Hf) cp_async8(dst + r * RING_ROW + b, xr + b);   // sb == 1
+                                }
+                            }
+                        }
+                    }
+                    cp_async_commit();
+                    if (c >= RING_DEPTH - 1) {
+                        cp_async_wait<RING_DEPTH - 1>();
+                        __syncwarp();
+                        const int cc = c - (RING_DEPTH - 1);
+                        const float2* src =
+                            reinterpret_cast<const float2*>(ring + (cc % RING_DEPTH) * RING_CHUNK);
+#pragma unroll
+                        for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+                            const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * cc + r;
+                            float m = 0.f, ny = 0.f;
+                            if (row < rows_eff) {
+                                float2 v[8];                 // bins lane + 32 j < Hf (Hf <= 256)
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    v[j] = j * 32 < Hf ? src[r * RING_ROW + j * 32 + lane]
+                                                       : make_float2(0.f, 0.f);
+                                if (lane == 0) v[0].y = 0.f; // Im X[0] never reaches the output
+                                if (DECOMP) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        m = fmaxf(m, abs2_finite(prep_bin<true>(v[j], p.pre_scale, p.pre_expo)));
+                                } else {
+                                    uint32_t mb = 0u;
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) mb = absbits_max(mb, v[j]);
+                                    if (mb >= 0x7f800000u) {  // inf / nan: exclude them
+                                        float mf = 0.f;
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) mf = fmaxf(mf, abs2_finite(v[j]));
+                                        mb = __float_as_uint(mf);
+                                    }
+                                    m = __uint_as_float(mb) * fabsf(p.pre_scale);
+                                }
+                                if (lane == 0)
+                                    ny = prep_bin<DECOMP>(src[r * RING_ROW + Hf], p.pre_scale, p.pre_expo).x;
+                            }
+#pragma unroll
+                            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                            if (lane == 0) ri[row] = make_float4(row_scale(m), 0.f, 0.f, ny);
+                        }
+                        __syncwarp();
+                    }
                 }
             }
-            scratch[kh * 128 + row] = pacc;
-            scratch[256 + kh * 128 + row] = racc;
-            named_bar_sync(1, BUILDER_THREADS);
-            if (kh == 0) {
-                rowinfo[row].y = 2.f * (scratch[row] + scratch[128 + row]);
-                rowinfo[row].z = 2.f * (scratch[256 + row] + scratch[384 + row]);
-            }
-        } else {
-            const int half = lane >> 4;            // which of the warp's two rows per pass
-            const int pr = lane & 15;              // m pair inside the 32-wide k-chunk
-            const uint32_t chunk = (uint32_t)(pr >> 2);
-            float pacc[8], racc[8], rscale[8];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&scale_full[slot]);
+        }
+    }
+    } else {
+        // ===================== builders, then epilogue ==========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+        const int bw = warp - INV_FIRST_BUILDER;   // 0..7
+        const int bt = bw * 32 + lane;             // 0..255
+        const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int hsel = bw >> 2;                  // which half of the offsets (epilogue)
+        const int pitch = H + 1;                   // skew: lanes (= frames) hit distinct banks
+        constexpr int R = 4 / HQ;                  // frames overlapping one hop block
+        float env_reg[8];                          // 1 / envelope of interior hop blocks
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                pacc[i] = racc[i] = 0.f;
-                const int row = bw * 16 + 2 * i + half;
-                rscale[i] = row < rows_eff ? rowinfo[row].x : 0.f;
-            }
-            for (int kc = 0; kc < Q / BK; ++kc) {
-                const int m0 = kc * BK + 2 * pr;   // bins 2 m0 .. 2 m0 + 3
-                float2 c[8][4];
+        for (int j = 0; j < 8; ++j) env_reg[j] = lane + 32 * j < H ? __ldg(p.env_per + lane + 32 * j) : 0.f;
+
+        int g = 0, n = 0;
+        for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
+            const int slot = n & 1;
+            float4* rowinfo = rowinfo2 + slot * TILE_M;
+            const int64_t sig = tile_id / p.tiles_per_signal;
+            const int tile = (int)(tile_id % p.tiles_per_signal);
+            const int64_t t0 = (int64_t)tile * p.adv;
+            const int rows_eff = (int)max((int64_t)0, min((int64_t)TILE_M, p.n_frames - t0));
+            const float2* xs = p.spec + sig * p.ss;
+            mbar_wait(&scale_full[slot], (uint32_t)((n >> 1) & 1));
+
+            // ---- main loop: load (L2-resident after the scouts), scale, split, store ----
+            if (FRAMES_FAST) {
+                const int row = bt & 127, kh = bt >> 7;
+                const bool live = row < rows_eff;
+                const float2* xr = xs + (t0 + (live ? row : 0)) * p.sf;
+                const float sc = rowinfo[row].x;
+                const uint32_t sw = (uint32_t)((row >> 1) & 3);
+                float pacc = 0.f, racc = 0.f;
+                for (int kc = 0; kc < Q / BK; ++kc) {
+                    float2 c[32];                      // bins 64 kc + 32 kh + e
+                    const int bin0 = 64 * kc + 32 * kh;
+                    if (live) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) c[e] = __ldg(xr + (int64_t)(bin0 + e) * p.sb);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) c[e] = prep_bin<DECOMP>(c[e], p.pre_scale, p.pre_expo);
+                        if (bin0 == 0) c[0].y = 0.f;   // Im X[0] is ignored by the c2r inverse
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            pacc += c[2 * j].x - c[2 * j + 2].x;          // (-1)^m Re X[2m]
+                            racc += c[2 * j + 1].y - c[2 * j + 3].y;      // (-1)^m Im X[2m+1]
+                        }
+                        if (bin0 == 0) pacc -= 0.5f * c[0].x;             // c_0 = 1, the others 2
+                    }
+#pragma unroll
+                    for (int pair = 0; pair < 2; ++pair, ++g) {
+                        const int s = g % STAGES;
+                        const uint32_t ph = (g / STAGES) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        if (live) {
+                            uint8_t* sa = stages + (size_t)s * STAGE_BYTES + row * (BK * 2);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {          // sub-GEMM: even / odd bins
+#pragma unroll
+                                for (int ch = 0; ch < 2; ++ch) {   // 16-byte chunk = 8 k values
+                                    uint32_t hi[4], lo[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int m0 = ch * 8 + 2 * e;     // local m of the k pair
+                                        const float2 ca = c[2 * m0 + j], cb = c[2 * m0 + 2 + j];
+                                        const float v0 = (pair ? ca.y : ca.x) * sc;
+                                        const float v1 = (pair ? cb.y : cb.x) * sc;
+                                        const __half2 h = __floats2half2_rn(v0, v1);
+                                        const float2 hf = __half22float2(h);
+                                        const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                                        hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+                                        lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+                                    }
+                                    const uint32_t dst = (((uint32_t)(2 * kh + ch)) ^ sw) << 4;
+                                    *reinterpret_cast<uint4*>(sa + (j * 2) * SUB_TILE + dst) =
+                                        make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                    *reinterpret_cast<uint4*>(sa + (j * 2 + 1) * SUB_TILE + dst) =
+                                        make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                }
+                            }
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full_bar[s]);
+                    }
+                }
+                scratch[kh * 128 + row] = pacc;
+                scratch[256 + kh * 128 + row] = racc;
+                named_bar_sync(1, BUILDER_THREADS);
+                if (kh == 0) {
+                    rowinfo[row].y = 2.f * (scratch[row] + scratch[128 + row]);
+                    rowinfo[row].z = 2.f * (scratch[256 + row] + scratch[384 + row]);
+                }
+            } else {
+                const int half = lane >> 4;            // which of the warp's two rows per pass
+                const int pr = lane & 15;              // m pair inside the 32-wide k-chunk
+                const uint32_t chunk = (uint32_t)(pr >> 2);
+                float pacc[8], racc[8], rscale[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
+                    pacc[i] = racc[i] = 0.f;
                     const int row = bw * 16 + 2 * i + half;
-                    const float2* xr = xs + (t0 + row) * p.sf + (int64_t)(2 * m0) * p.sb;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        c[i][e] = row < rows_eff ? __ldg(xr + (int64_t)e * p.sb)
-                                                 : make_float2(0.f, 0.f);
+                    rscale[i] = row < rows_eff ? rowinfo[row].x : 0.f;
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) c[i][e] = prep_bin(c[i][e], p.pre_scale, p.pre_expo);
-                    if (m0 == 0) c[i][0].y = 0.f;  // Im X[0] is ignored by the c2r inverse
-                    pacc[i] += c[i][0].x - c[i][2].x;
-                    racc[i] += c[i][1].y - c[i][3].y;
-                    if (m0 == 0) pacc[i] -= 0.5f * c[i][0].x;
-                }
-#pragma unroll
-                for (int pair = 0; pair < 2; ++pair) {
-                    const int it = kc * 2 + pair;
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* sa = stages + (size_t)s * STAGE_BYTES;
+                for (int kc = 0; kc < Q / BK; ++kc) {
+                    const int m0 = kc * BK + 2 * pr;   // bins 2 m0 .. 2 m0 + 3
+                    float2 c[8][4];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = bw * 16 + 2 * i + half;
-                        if (row >= rows_eff) continue;
-                        const float sc = rscale[i];
-                        uint8_t* dst = sa + row * (BK * 2) +
-                                       ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
-                        if (pair == 0) {
-                            split_store(dst, dst + SUB_TILE, c[i][0].x * sc, c[i][2].x * sc);
-                            split_store(dst + 2 * SUB_TILE, dst + 3 * SUB_TILE, c[i][1].x * sc,
-                                        c[i][3].x * sc);
+                        const float2* xr = xs + (t0 + row) * p.sf + (int64_t)(2 * m0) * p.sb;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            c[i][e] = row < rows_eff ? __ldg(xr + (int64_t)e * p.sb)
+                                                     : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            c[i][e] = prep_bin<DECOMP>(c[i][e], p.pre_scale, p.pre_expo);
+                        if (m0 == 0) c[i][0].y = 0.f;  // Im X[0] is ignored by the c2r inverse
+                        pacc[i] += c[i][0].x - c[i][2].x;
+                        racc[i] += c[i][1].y - c[i][3].y;
+                        if (m0 == 0) pacc[i] -= 0.5f * c[i][0].x;
+                    }
+#pragma unroll
+                    for (int pair = 0; pair < 2; ++pair, ++g) {
+                        const int s = g % STAGES;
+                        const uint32_t ph = (g / STAGES) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        uint8_t* sa = stages + (size_t)s * STAGE_BYTES;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = bw * 16 + 2 * i + half;
+                            if (row >= rows_eff) continue;
+                            const float sc = rscale[i];
+                            uint8_t* dst = sa + row * (BK * 2) +
+                                           ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
+                            if (pair == 0) {
+                                split_store(dst, dst + SUB_TILE, c[i][0].x * sc, c[i][2].x * sc);
+                                split_store(dst + 2 * SUB_TILE, dst + 3 * SUB_TILE, c[i][1].x * sc,
+                                            c[i][3].x * sc);
+                            } else {
+                                split_store(dst, dst + SUB_TILE, c[i][0].y * sc, c[i][2].y * sc);
+                                split_store(dst + 2 * SUB_TILE, dst + 3 * SUB_TILE, c[i][1].y * sc,
+                                            c[i][3].y * sc);
+                            }
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full_bar[s]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float a = pacc[i], b = racc[i];
+#pragma unroll
+                    for (int o = 8; o; o >>= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, o);
+                        b += __shfl_xor_sync(0xffffffffu, b, o);
+                    }
+                    const int row = bw * 16 + 2 * i + half;
+                    if (pr == 0 && row < rows_eff) {
+                        rowinfo[row].y = 2.f * a;
+                        rowinfo[row].z = 2.f * b;
+                    }
+                }
+            }
+            named_bar_sync(1, BUILDER_THREADS);
+
+            // ---- epilogue: TMEM -> segments -> lane-rotated overlap-add -> skewed rows ----
+            {
+                const int row = q * 32 + lane;         // frame t0 + row == hop block t0 + row
+                const bool live = row < rows_eff;
+                const float4 ri = rowinfo[row];
+                const float g0 = live ? p.basis_scale_inv / ri.x : 0.f;
+                const float xny = live ? ri.w : 0.f;
+                // f[Q], f[3Q]: Q is even, so the Nyquist term enters with +1
+                const float fq = live ? (ri.y - ri.z + ri.w) * p.wq : 0.f;
+                const float f3q = live ? (ri.y + ri.z + ri.w) * p.w3q : 0.f;
+                mbar_wait(&accum_bar, (uint32_t)(n & 1));
+                tcgen05_fence_after();
+                float* my_row = orow + row * pitch;
+                float* my_spill = spill + ((q + 1) * 3 + lane) * H;
+                const bool do_spill = q < 3 && lane < 3;
+                const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+                const int o_begin = hsel * (Q / 2), o_end = o_begin + Q / 2;
+                uint32_t carry[4];                     // column Q - c0 of Ce, Co, Se, So
+                if (o_begin > 0) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                        tmem_ld1_nowait(tq + (uint32_t)(a * Q + Q - o_begin), &carry[a]);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) carry[a] = 0u;
+                }
+#pragma unroll 1
+                for (int c0 = o_begin; c0 < o_end; c0 += 8) {
+                    uint32_t A[4][8], B[4][8];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        tmem_ld8_nowait(tq + (uint32_t)(a * Q + c0), A[a]);
+                        tmem_ld8_nowait(tq + (uint32_t)(a * Q + Q - c0 - 8), B[a]);
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int o = c0 + i;
+                        const float sg = (i & 1) ? -xny : xny;         // c0 is even
+                        const float4 wa = wtab[o];
+                        const float ce = __uint_as_float(A[0][i]), co = __uint_as_float(A[1][i]);
+                        const float se = __uint_as_float(A[2][i]), so = __uint_as_float(A[3][i]);
+                        float seg0 = (((ce + co) - (se + so)) * g0 + sg) * wa.x;
+                        float seg2 = (((ce - co) - (se - so)) * g0 + sg) * wa.z;
+                        float seg1, seg3;
+                        if (o == 0) {
+                            seg1 = fq;
+                            seg3 = f3q;
                         } else {
-                            split_store(dst, dst + SUB_TILE, c[i][0].y * sc, c[i][2].y * sc);
-                            split_store(dst + 2 * SUB_TILE, dst + 3 * SUB_TILE, c[i][1].y * sc,
-                                        c[i][3].y * sc);
+                            const float4 wb = wtab[Q - o];
+                            const float ce2 = __uint_as_float(i == 0 ? carry[0] : B[0][8 - i]);
+                            const float co2 = __uint_as_float(i == 0 ? carry[1] : B[1][8 - i]);
+                            const float se2 = __uint_as_float(i == 0 ? carry[2] : B[2][8 - i]);
+                            const float so2 = __uint_as_float(i == 0 ? carry[3] : B[3][8 - i]);
+                            seg1 = (((ce2 - co2) + (se2 - so2)) * g0 + sg) * wb.y;
+                            seg3 = (((ce2 + co2) + (se2 + so2)) * g0 + sg) * wb.w;
+                        }
+                        if (!live) seg0 = seg1 = seg2 = seg3 = 0.f;    // dead rows hold garbage
+                        if (HQ == 1) {
+                            const float r1 = rot(seg1, lane, 1), r2 = rot(seg2, lane, 2),
+                                        r3 = rot(seg3, lane, 3);
+                            float acc = seg0;
+                            if (lane >= 1) acc += r1;
+                            if (lane >= 2) acc += r2;
+                            if (lane >= 3) acc += r3;
+                            my_row[o] = acc;
+                            if (do_spill) {
+                                float sp = 0.f;
+                                if (lane < 1) sp += r1;
+                                if (lane < 2) sp += r2;
+                                sp += r3;
+                                my_spill[o] = sp;
+                            }
+                        } else if (HQ == 2) {
+                            const float r2 = rot(seg2, lane, 1), r3 = rot(seg3, lane, 1);
+                            my_row[o] = lane >= 1 ? seg0 + r2 : seg0;
+                            my_row[Q + o] = lane >= 1 ? seg1 + r3 : seg1;
+                            if (do_spill && lane == 0) {
+                                my_spill[o] = r2;
+                                my_spill[Q + o] = r3;
+                            }
+                        } else {
+                            my_row[o] = seg0;
+                            my_row[Q + o] = seg1;
+                            my_row[2 * Q + o] = seg2;
+                            my_row[3 * Q + o] = seg3;
                         }
                     }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[s]);
-                }
-            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float a = pacc[i], b = racc[i];
-#pragma unroll
-                for (int o = 8; o; o >>= 1) {
-                    a += __shfl_xor_sync(0xffffffffu, a, o);
-                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                    for (int a = 0; a < 4; ++a) carry[a] = B[a][0];
                 }
-                const int row = bw * 16 + 2 * i + half;
-                if (pr == 0 && row < rows_eff) {
-                    rowinfo[row].y = 2.f * a;
-                    rowinfo[row].z = 2.f * b;
-                }
+                tcgen05_fence_before();
             }
-        }
-        named_bar_sync(1, BUILDER_THREADS);
+            named_bar_sync(1, BUILDER_THREADS);
 
-        // ---- epilogue: TMEM -> segments -> lane-rotated overlap-add -> skewed rows ----
-        const int q = warp & 3;                    // TMEM lane quarter this warp may read
-        const int hsel = bw >> 2;                  // which half of the offsets
-        const int row = q * 32 + lane;             // frame t0 + row == hop block t0 + row
-        const bool live = row < rows_eff;
-        const float4 ri = rowinfo[row];
-        const float g0 = live ? p.basis_scale_inv / ri.x : 0.f;
-        const float xny = live ? ri.w : 0.f;
-        // f[Q], f[3Q]: Q is even, so the Nyquist term enters with +1
-        const float fq = live ? (ri.y - ri.z + ri.w) * p.wq : 0.f;
-        const float f3q = live ? (ri.y + ri.z + ri.w) * p.w3q : 0.f;
-        mbar_wait(&accum_bar, 0);
-        tcgen05_fence_after();
-        const int pitch = H + 1;                   // skew: lanes (= frames) hit distinct banks
-        float* my_row = orow + row * pitch;
-        float* my_spill = spill + ((q + 1) * 3 + lane) * H;
-        const bool do_spill = q < 3 && lane < 3;
-        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int o_begin = hsel * (Q / 2), o_end = o_begin + Q / 2;
-        uint32_t carry[4];                         // column Q - c0 of Ce, Co, Se, So
-        if (o_begin > 0) {
+            // ---- copy-out: finished hop blocks, * 1 / envelope, centre trim ---------------
+            {
+                const int r_lo = tile == 0 ? 0 : p.halo;
+                float* ys = p.y + sig * p.out_len;
+                for (int r = r_lo + bw; r < TILE_M; r += BUILDERS) {
+                    const int64_t u = t0 + r;
+                    if (u >= p.n_blocks) break;
+                    const float* src = orow + r * pitch;
+                    const int qq = r >> 5, lr = r & 31;
+                    const float* sp = (qq > 0 && lr < p.halo) ? spill + (qq * 3 + lr) * H : nullptr;
+                    const int64_t i0 = u * H - Hf;
+                    const bool interior = u >= R - 1 && u <= p.n_frames - 1;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) tmem_ld1_nowait(tq + (uint32_t)(a * Q + Q - o_begin), &carry[a]);
-            tmem_ld_wait();
-        } else {
-#pragma unroll
-            for (int a = 0; a < 4; ++a) carry[a] = 0u;
-        }
-#pragma unroll 1
-        for (int c0 = o_begin; c0 < o_end; c0 += 8) {
-            uint32_t A[4][8], B[4][8];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                tmem_ld8_nowait(tq + (uint32_t)(a * Q + c0), A[a]);
-                tmem_ld8_nowait(tq + (uint32_t)(a * Q + Q - c0 - 8), B[a]);
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int o = c0 + i;
-                const float sg = (i & 1) ? -xny : xny;         // c0 is even
-                const float4 wa = wtab[o];
-                const float ce = __uint_as_float(A[0][i]), co = __uint_as_float(A[1][i]);
-                const float se = __uint_as_float(A[2][i]), so = __uint_as_float(A[3][i]);
-                float seg0 = (((ce + co) - (se + so)) * g0 + sg) * wa.x;
-                float seg2 = (((ce - co) - (se - so)) * g0 + sg) * wa.z;
-                float seg1, seg3;
-                if (o == 0) {
-                    seg1 = fq;
-                    seg3 = f3q;
-                } else {
-                    const float4 wb = wtab[Q - o];
-                    const float ce2 = __uint_as_float(i == 0 ? carry[0] : B[0][8 - i]);
-                    const float co2 = __uint_as_float(i == 0 ? carry[1] : B[1][8 - i]);
-                    const float se2 = __uint_as_float(i == 0 ? carry[2] : B[2][8 - i]);
-                    const float so2 = __uint_as_float(i == 0 ? carry[3] : B[3][8 - i]);
-                    seg1 = (((ce2 - co2) + (se2 - so2)) * g0 + sg) * wb.y;
-                    seg3 = (((ce2 + co2) + (se2 + so2)) * g0 + sg) * wb.w;
-                }
-                if (!live) seg0 = seg1 = seg2 = seg3 = 0.f;    // dead rows hold garbage
-                if (HQ == 1) {
-                    const float r1 = rot(seg1, lane, 1), r2 = rot(seg2, lane, 2),
-                                r3 = rot(seg3, lane, 3);
-                    float acc = seg0;
-                    if (lane >= 1) acc += r1;
-                    if (lane >= 2) acc += r2;
-                    if (lane >= 3) acc += r3;
-                    my_row[o] = acc;
-                    if (do_spill) {
-                        float sp = 0.f;
-                        if (lane < 1) sp += r1;
-                        if (lane < 2) sp += r2;
-                        sp += r3;
-                        my_spill[o] = sp;
+                    for (int j = 0; j < 8; ++j) {
+                        const int off = lane + 32 * j;
+                        const int64_t i = i0 + off;
+                        if (off < H && i >= 0 && i < p.out_len) {
+                            float v = src[off];
+                            if (sp) v += sp[off];
+                            ys[i] = v * (interior ? env_reg[j] : __ldg(p.inv_env + i));
+                        }
                     }
-                } else if (HQ == 2) {
-                    const float r2 = rot(seg2, lane, 1), r3 = rot(seg3, lane, 1);
-                    my_row[o] = lane >= 1 ? seg0 + r2 : seg0;
-                    my_row[Q + o] = lane >= 1 ? seg1 + r3 : seg1;
-                    if (do_spill && lane == 0) {
-                        my_spill[o] = r2;
-                        my_spill[Q + o] = r3;
-                    }
-                } else {
-                    my_row[o] = seg0;
-                    my_row[Q + o] = seg1;
-                    my_row[2 * Q + o] = seg2;
-                    my_row[3 * Q + o] = seg3;
                 }
             }
-#pragma unroll
-            for (int a = 0; a < 4; ++a) carry[a] = B[a][0];
-        }
-        tcgen05_fence_before();
-        named_bar_sync(1, BUILDER_THREADS);
-
-        // ---- copy-out: finished hop blocks, * 1 / envelope, centre trim ---------------
-        const int r_lo = tile == 0 ? 0 : p.halo;
-        float* ys = p.y + sig * p.out_len;
-        for (int r = r_lo + bw; r < TILE_M; r += BUILDERS) {
-            const int64_t u = t0 + r;
-            if (u >= p.n_blocks) break;
-            const float* src = orow + r * pitch;
-            const int qq = r >> 5, lr = r & 31;
-            const float* sp = (qq > 0 && lr < p.halo) ? spill + (qq * 3 + lr) * H : nullptr;
-            const int64_t i0 = u * H - Hf;
-            for (int off = lane; off < H; off += 32) {
-                const int64_t i = i0 + off;
-                if (i < 0 || i >= p.out_len) continue;
-                float v = src[off];
-                if (sp) v += sp[off];
-                ys[i] = v * __ldg(p.inv_env + i);
+            // the output rows alias the operand stages: nobody may start building the
+            // next tile before every warp has copied its rows out
+            named_bar_sync(1, BUILDER_THREADS);
+            if (lane == 0) {
+                mbar_arrive(&region_free);
+                mbar_arrive(&scale_empty[slot]);
             }
         }
     }
@@ -885,6 +1045,8 @@ struct FoldPlan {
     float wq_inv = 0.f, w3q_inv = 0.f;
     int q = 0, tmem_cols = 0;
     int hq = 0;                  // hop / Q when the fused overlap-add applies (1, 2, 4), else 0
+    float* env_per = nullptr;    // hop: 1 / overlap-added w^2 for interior hop blocks
+    int sm_count = 0;
     std::map<int64_t, float*> inv_env;   // n_frames -> 1 / overlap-added w^2 (device)
 };
 
@@ -953,6 +1115,7 @@ void free_fold(FoldPlan* fp) {
     cudaFree(fp->inv.data);
     cudaFree(fp->wtab);
     cudaFree(fp->wtab_inv);
+    cudaFree(fp->env_per);
     for (auto& kv : fp->inv_env) cudaFree(kv.second);
     delete fp;
 }
@@ -1027,11 +1190,31 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             if ((size_t)TILE_M * (H + 1) * sizeof(float) <= (size_t)INV_REGION && H <= 256)
                 fp->hq = H / Q;
     }
+    if (rc == BRV_OK && fp->hq) {
+        // interior hop blocks see all R = N / hop frames: the envelope is periodic
+        const int H = p->hop;
+        std::vector<float> per(H);
+        for (int off = 0; off < H; ++off) {
+            double e = 0;
+            for (int pos = off; pos < N; pos += H) e += p->window[pos] * p->window[pos];
+            per[off] = (float)(1.0 / e);
+        }
+        if (cudaMalloc((void**)&fp->env_per, H * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(fp->env_per, per.data(), H * sizeof(float), cudaMemcpyHostToDevice) !=
+                cudaSuccess)
+            rc = brv_fail_cuda(cudaGetLastError(), "folded inverse periodic envelope");
+        if (cudaDeviceGetAttribute(&fp->sm_count, cudaDevAttrMultiProcessorCount, p->device) !=
+            cudaSuccess)
+            rc = brv_fail_cuda(cudaGetLastError(), "cudaDeviceGetAttribute(SM count)");
+    }
     if (rc == BRV_OK) {
-        const void* kernels[6] = {
-            (const void*)istft_fold_kernel<1, false>, (const void*)istft_fold_kernel<1, true>,
-            (const void*)istft_fold_kernel<2, false>, (const void*)istft_fold_kernel<2, true>,
-            (const void*)istft_fold_kernel<4, false>, (const void*)istft_fold_kernel<4, true>};
+        const void* kernels[12] = {
+            (const void*)istft_fold_kernel<1, false, false>, (const void*)istft_fold_kernel<1, true, false>,
+            (const void*)istft_fold_kernel<2, false, false>, (const void*)istft_fold_kernel<2, true, false>,
+            (const void*)istft_fold_kernel<4, false, false>, (const void*)istft_fold_kernel<4, true, false>,
+            (const void*)istft_fold_kernel<1, false, true>, (const void*)istft_fold_kernel<1, true, true>,
+            (const void*)istft_fold_kernel<2, false, true>, (const void*)istft_fold_kernel<2, true, true>,
+            (const void*)istft_fold_kernel<4, false, true>, (const void*)istft_fold_kernel<4, true, true>};
         for (const void* k : kernels)
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      INV_SMEM_BYTES) != cudaSuccess)
@@ -1158,11 +1341,18 @@ int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t 
     prm.wq = fp->wq_inv;
     prm.w3q = fp->w3q_inv;
     prm.basis_scale_inv = fp->inv.scale_inv;
-    const int64_t grid = n_sig * prm.tiles_per_signal;
-    BRV_REQUIRE(grid < (1LL << 31), "too many tiles (%lld)", (long long)grid);
+    prm.env_per = fp->env_per;
+    prm.total_tiles = n_sig * prm.tiles_per_signal;
+    const unsigned grid = (unsigned)(prm.total_tiles < fp->sm_count ? prm.total_tiles : fp->sm_count);
     const bool frames_fast = sb != 1;
-#define BRV_LAUNCH_INV(HQ_, FF_)                                                              \
-    istft_fold_kernel<HQ_, FF_><<<(unsigned)grid, NUM_THREADS, INV_SMEM_BYTES, st>>>(fp->inv.map, prm)
+    const bool decomp = p->compression != 1.0;
+#define BRV_LAUNCH_INV(HQ_, FF_)                                                                  \
+    do {                                                                                          \
+        if (decomp)                                                                               \
+            istft_fold_kernel<HQ_, FF_, true><<<grid, INV_THREADS, INV_SMEM_BYTES, st>>>(fp->inv.map, prm); \
+        else                                                                                      \
+            istft_fold_kernel<HQ_, FF_, false><<<grid, INV_THREADS, INV_SMEM_BYTES, st>>>(fp->inv.map, prm); \
+    } while (0)
     switch (fp->hq * 2 + (frames_fast ? 1 : 0)) {
         case 2: BRV_LAUNCH_INV(1, false); break;
         case 3: BRV_LAUNCH_INV(1, true); break;
