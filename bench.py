@@ -42,6 +42,8 @@ WORKLOADS = {
                  desc='FFNN front-end: 16x2ch x 4 s, STFT 512/256 -> 64 log-mel -> stack 5 -> normalise; mean_c(X) -> iSTFT'),
     'cfg2': dict(batch=64, channels=1, seconds=4, frame_length=512, hop=128, kw={},
                  desc='DCCRN round trip: 64 x 4 s, STFT 512/128 -> iSTFT -> SI-SNR'),
+    'cfg3': dict(batch=256, channels=1, seconds=4, frame_length=512, hop=128, kw={},
+                 desc='Conv-TasNet-style criterion: SI-SNR on 256 x 4 s resynthesised waveforms (no STFT on the path)'),
     'cfg4': dict(batch=128, channels=1, seconds=8, frame_length=510, hop=128,
                  kw=dict(normalized=False, compression_factor=0.5, scale_factor=0.15),
                  desc='SGMSE+: 128 x 8 s, compressed STFT 510/128 (c=0.5, scale 0.15) -> iSTFT'),
@@ -64,51 +66,104 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-             'clocks_event_reasons.sw_power_cap')
+    """Samples SM clocks / throttle reasons DURING the timed region.
+
+    NVML in-process (pynvml, ~1 ms period: the timed region of a 50-step run is only
+    a few milliseconds long); `nvidia-smi -lms` as a fallback, started early because
+    its start-up stalls CUDA launches of other processes for ~100 ms."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown',
+               0x4: 'sw_power_cap', 0x80: 'hw_power_brake_slowdown'}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.handle, self.proc = index, [], None, None
+        self.stop_flag = threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                if not uuid.startswith('GPU-'):
+                    uuid = 'GPU-' + uuid
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.handle = None
+
+    def _poll(self):
+        nv = self.nv
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                t = time.perf_counter()
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                mask = get_reasons(self.handle)
+                self.rows.append((t, float(mhz), int(mask)))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line))
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
-                 '--format=csv,noheader,nounits', '-lms', '100'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        """Call BEFORE the warm-up so start-up costs stay out of the timed region."""
+        if self.handle is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
+            return
+        try:
+            q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+                 'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+                 'clocks_event_reasons.sw_power_cap')
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}',
+                 '--format=csv,noheader,nounits', '-lms', '20'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
+            t_end = time.time() + 5.0
+            while not self.rows and time.time() < t_end:   # wait out nvidia-smi's start-up
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
-
-    def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for name, val in zip(names, r[3:7]):
-                    if val.lower().startswith('active'):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in [t0, t1] (perf_counter; all if None)."""
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.handle is None and self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no NVML / nvidia-smi'], 'samples': 0}
+        rows = [r for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)]
+        window = 'timed region'
+        if not rows:                       # region shorter than one sampling period
+            rows, window = self.rows[-3:], 'nearest samples (region shorter than the sampling period)'
+        sm, reasons, mx = [], set(), self.max_mhz
+        if self.handle is not None:
+            for _, mhz, mask in rows:
+                sm.append(mhz)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
                         reasons.add(name)
-            except (ValueError, IndexError):
-                continue
-        return {'sm_mhz': statistics.median(sm) if sm else None,
-                'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        else:
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            for _, line in rows:
+                c = [v.strip() for v in line.split(',')]
+                try:
+                    sm.append(float(c[0]))
+                    mx = float(c[1])
+                    reasons.update(n for n, v in zip(names, c[2:6]) if v.lower().startswith('active'))
+                except (ValueError, IndexError):
+                    continue
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': mx,
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window,
+                'source': 'nvml' if self.handle is not None else 'nvidia-smi'}
 
 
 def make_batch(wl, seed):
@@ -117,7 +172,10 @@ def make_batch(wl, seed):
     shape = (wl['batch'], wl['channels'], wl['seconds'] * FS)
     if wl['channels'] == 1:
         shape = (wl['batch'], wl['seconds'] * FS)
-    return synthetic_mixture(shape, seed)
+    mix, fg = synthetic_mixture(shape, seed)
+    if fg.ndim == 3:
+        fg = fg.mean(1)      # single-channel training target (ffnn.py:107, tfgridnet.py:137)
+    return mix, fg
 
 
 # --------------------------------------------------------------------------- #
@@ -161,8 +219,30 @@ class Pipeline:
             self.std = torch.ones(384, 1, device=device)
         self.stage_names = {'cfg1': ['stft', 'features', 'istft', 'sisnr'],
                             'cfg2': ['stft', 'istft', 'sisnr'],
+                            'cfg3': ['sisnr'],
                             'cfg4': ['stft', 'istft', 'sisnr'],
                             'cfg5': ['stft', 'istft', 'sisnr']}[name]
+
+    # the stages, each one public-API call (plus the view the model takes between them)
+    def stage_stft(self, mix):
+        return self.stft(mix)
+
+    def stage_features(self, spec):
+        return self.front.features(spec, self.mean, self.std)
+
+    def select(self, spec):
+        """What goes back through the iSTFT: channel mean (FFNN), source 0 (TF-GridNet)."""
+        if self.name == 'cfg1':
+            return spec.mean(1)
+        if self.name == 'cfg5':
+            return spec[:, 0]
+        return spec
+
+    def stage_istft(self, spec):
+        return self.stft.backward(spec)[..., :self.samples]
+
+    def stage_sisnr(self, y, target):
+        return self.brv.sisnr(y.unsqueeze(1), target.unsqueeze(1), self.lengths)
 
     def step(self, mix, target, marks=None):
         """mix/target: device tensors.  Returns the (batch,) loss tensor."""
@@ -170,29 +250,68 @@ class Pipeline:
             if marks is not None:
                 marks[i].record()
         mark(0)
-        spec = self.stft(mix)
+        if self.name == 'cfg3':          # the estimate comes from a learned decoder: criterion only
+            loss = self.stage_sisnr(mix, target)
+            mark(1)
+            return loss
+        spec = self.stage_stft(mix)
         mark(1)
         k = 2
         if self.name == 'cfg1':
-            feats = self.front.features(spec, self.mean, self.std)   # noqa: F841
+            feats = self.stage_features(spec)   # noqa: F841
             mark(k)
             k += 1
-            spec = spec.mean(1)
-        elif self.name == 'cfg5':
-            spec = spec[:, 0]
-        y = self.stft.backward(spec)[..., :self.samples]
+        y = self.stage_istft(self.select(spec))
         mark(k)
-        tgt = target if target.ndim == 2 else target.mean(1)
-        loss = self.brv.sisnr(y.unsqueeze(1), tgt.unsqueeze(1), self.lengths)
+        loss = self.stage_sisnr(y, target)
         mark(k + 1)
         return loss
 
 
+def time_stages(pipe, sets, reps, only=None):
+    """Device time of each stage in isolation: the stage's launches for every input
+    set are captured in one CUDA graph and replayed `reps` times between two CUDA
+    events on the launching stream (no host gaps; inputs rotate, so nothing is
+    L2-resident from the previous launch of the same stage)."""
+    from brever_b200 import graphs
+    if pipe.name == 'cfg3':
+        specs, sel, ys = [], [], [m for m, _ in sets]
+    else:
+        specs = [pipe.stage_stft(m) for m, _ in sets]
+        sel = [pipe.select(sp) for sp in specs]
+        ys = [pipe.stage_istft(sp) for sp in sel]
+    calls = {
+        'stft': lambda: [pipe.stage_stft(m) for m, _ in sets],
+        'features': lambda: [pipe.stage_features(sp) for sp in specs],
+        'istft': lambda: [pipe.stage_istft(sp) for sp in sel],
+        'sisnr': lambda: [pipe.stage_sisnr(y, f) for y, (_, f) in zip(ys, sets)],
+    }
+    out = {}
+    for name in pipe.stage_names:
+        if only and name not in only:
+            continue
+        g = graphs.capture(calls[name])
+        for _ in range(2):
+            g()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            g()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / (reps * len(sets))
+        del g
+    return out
+
+
 def run_ours(args, rank, world, device):
     import torch.distributed as dist
-    from brever_b200 import _lib
+    from brever_b200 import _lib, graphs
     wl = WORKLOADS[args.workload]
     peaks = load_peaks()
+    sampler = ClockSampler(device.index)
+    sampler.start()
     pipe = Pipeline(args.workload, wl, device)
     work, n_frames = stage_work(wl)
     audio_s = wl['batch'] * wl['seconds']            # per rank per step
@@ -211,27 +330,46 @@ def run_ours(args, rank, world, device):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n_marks = len(pipe.stage_names) + 1
-    for i in range(args.warmup):
-        pipe.step(*sets[i % n_sets])
-    marks = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)]
-             for _ in range(args.steps)]
-    sampler = ClockSampler(device.index)
-    barrier()
-    sampler.start()
-    launches0 = _lib.lib().brv_launch_count()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
     total = torch.zeros((), device=device)
+
+    def full_step(mix, target):
+        loss = pipe.step(mix, target)
+        total.add_(loss.mean())                      # running metric (training.py:369-373)
+        return loss
+
+    use_graph = not args.no_graph
+    lib = _lib.lib()
+    if use_graph:
+        # one captured step per input set: a replay is ONE host call for the whole chain
+        graphed = [graphs.capture(full_step, m, f) for m, f in sets]
+        launches_per_step = graphed[0].launches
+
+        def run(i):
+            return graphed[i % n_sets]()
+    else:
+        c0 = lib.brv_launch_count()
+        full_step(*sets[0])
+        launches_per_step = int(lib.brv_launch_count() - c0)
+
+        def run(i):
+            return full_step(*sets[i % n_sets])
+
+    for i in range(args.warmup):
+        run(i)
+    barrier()
+    total.zero_()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_begin = time.perf_counter()
+    start.record()
     for i in range(args.steps):
-        loss = pipe.step(*sets[i % n_sets], marks=marks[i])
-        total += loss.mean()
+        run(i)
     if world > 1:   # the one collective: final metric all-reduce (training.py:369-373)
         dist.all_reduce(total)
     stop.record()
     barrier()
-    launches = _lib.lib().brv_launch_count() - launches0
-    clocks = sampler.stop()
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_begin, t_end)
     elapsed_ms = start.elapsed_time(stop)
     t = torch.tensor([elapsed_ms], device=device)
     if world > 1:
@@ -239,11 +377,10 @@ def run_ours(args, rank, world, device):
     elapsed_ms = float(t)
     ms_per_step = elapsed_ms / args.steps
     value = world * audio_s / (ms_per_step * 1e-3)
+    mean_loss = float(total) / (args.steps * world)
 
-    # per-stage device time (events inside the timed region, same stream)
-    stage_ms = {}
-    for j, name in enumerate(pipe.stage_names):
-        stage_ms[name] = statistics.mean(m[j].elapsed_time(m[j + 1]) for m in marks)
+    # per-stage device time, each stage isolated (CUDA events around graph replays)
+    stage_ms = time_stages(pipe, sets, reps=max(5, min(args.steps, 20)))
     dominant = max(stage_ms, key=stage_ms.get)
     w = work[dominant]
     if w['flops'] > 0:
@@ -263,6 +400,14 @@ def run_ours(args, rank, world, device):
     roofline['stage_ms'] = {k: round(v, 4) for k, v in stage_ms.items()}
     roofline['stage_hbm_frac'] = {
         k: round(work[k]['bytes'] / (v * 1e-3) / 1e9 / peaks['hbm'], 4) for k, v in stage_ms.items()}
+    roofline['stage_timing'] = 'each stage alone: CUDA events around CUDA-graph replays over the rotating input sets'
+    # the whole chain against its own roofline: max(bytes / HBM, flops / (bf16 / 3))
+    tot_bytes = sum(work[s]['bytes'] for s in pipe.stage_names)
+    tot_flops = sum(work[s]['flops'] for s in pipe.stage_names)
+    t_roof = max(tot_bytes / (peaks['hbm'] * 1e9), tot_flops / (peaks['bf16'] / 3 * 1e12))
+    roofline['chain'] = {'alg_bytes': tot_bytes, 'alg_flops': tot_flops,
+                         'roofline_ms': round(t_roof * 1e3, 4),
+                         'frac': round(t_roof * 1e3 / ms_per_step, 4)}
 
     # ---- end to end: pinned host buffers, H2D + D2H inside the timed region ----
     host = [(m.cpu().pin_memory(), f.cpu().pin_memory()) for m, f in sets[:2]]
@@ -273,6 +418,10 @@ def run_ours(args, rank, world, device):
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     result = torch.empty(wl['batch'], dtype=torch.float32).pin_memory()
+    if use_graph:
+        e2e_steps = [graphs.capture(full_step, *dev_bufs[b]) for b in range(2)]
+    else:
+        e2e_steps = [lambda b=b: full_step(*dev_bufs[b]) for b in range(2)]
 
     def e2e_loop(steps):
         main = torch.cuda.current_stream(device)
@@ -287,7 +436,7 @@ def run_ours(args, rank, world, device):
             if i >= 1:                     # compute step i-1
                 b = (i - 1) % 2
                 main.wait_event(ready[b])
-                loss = pipe.step(*dev_bufs[b])
+                loss = e2e_steps[b]()
                 consumed[b].record(main)
                 result.copy_(loss, non_blocking=True)   # D2H read of the step result
         main.synchronize()
@@ -316,14 +465,29 @@ def run_ours(args, rank, world, device):
                    'frame_length': wl['frame_length'], 'hop_length': wl['hop'],
                    'frames': n_frames, 'parallelism': f'dp{world} (utterances sharded by rank)',
                    'l2': f'{n_sets} rotating input sets (> 2x L2) so steps never hit L2-resident inputs',
+                   'launch': 'one CUDA-graph replay per step (brever_b200.graphs.capture of the public API calls)'
+                             if use_graph else 'eager Python launches',
                    'stft_path': os.environ.get('BRV_FORCE_GENERIC', '0') == '1' and 'generic' or 'default'},
         'e2e': {'value': round(e2e_value, 1), 'unit': 'audio-s/s',
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'note': 'pinned host -> device copy of mixture+target every step, double-buffered on a copy stream; loss read back every step'},
-        'gpu_launches': int(launches),
+        'gpu_launches': int(launches_per_step * args.steps),
+        'mean_loss_db': round(mean_loss, 4),
         'roofline': roofline,
         'clocks': clocks,
     }
+    if use_graph and args.eager_compare:
+        # the same steps launched eagerly from Python, for the launch-overhead picture
+        for i in range(3):
+            full_step(*sets[i % n_sets])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            full_step(*sets[i % n_sets])
+        e1.record()
+        torch.cuda.synchronize()
+        out['eager_ms_per_step'] = round(e0.elapsed_time(e1) / args.steps, 4)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_reference(args.workload, budget_s=15.0)
     return out
@@ -347,6 +511,9 @@ def cpu_reference(workload, budget_s=15.0, steps=None, warmup=1):
 
     def run(mix, fg):
         with torch.no_grad():
+            if workload == 'cfg3':
+                lengths = torch.full((mix.shape[0],), S)
+                return P.sisnr(mix.unsqueeze(1), fg.unsqueeze(1), lengths)
             spec = P.stft(mix, win, **kw)
             if workload == 'cfg1':
                 feats = P.stack(P.logfbe(spec, filters), 5)
@@ -355,9 +522,8 @@ def cpu_reference(workload, budget_s=15.0, steps=None, warmup=1):
             elif workload == 'cfg5':
                 spec = spec[:, 0]
             y = P.istft(spec, win, **kw)[..., :S]
-            tgt = fg if fg.ndim == 2 else fg.mean(1)
             lengths = torch.full((mix.shape[0],), S)
-            return P.sisnr(y.unsqueeze(1), tgt.unsqueeze(1), lengths)
+            return P.sisnr(y.unsqueeze(1), fg.unsqueeze(1), lengths)
 
     # bounded sample: shrink the batch until one pass fits the budget
     sample = wl['batch']
@@ -418,6 +584,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch eagerly from Python instead of replaying CUDA graphs')
+    ap.add_argument('--no-eager-compare', dest='eager_compare', action='store_false',
+                    help='skip the extra eagerly-launched pass reported as eager_ms_per_step')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 

@@ -44,14 +44,14 @@ PROTOTYPES = {
     'brv_mel_apply': (_int, [_ptr, _i64, _i64, _i64, _i64, _int, _i64, _ptr,
                              _ptr, _ptr, _int, _ptr, _ptr]),
     'brv_fbe_features': (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _int, _int,
-                                _i64, _ptr, _ptr, _ptr, _int, _int, _int, _f32,
-                                _int, _int, _ptr, _ptr, _ptr, _ptr]),
+                                _i64, _ptr, _ptr, _ptr, _int, _int, _int, _int,
+                                _f32, _int, _int, _ptr, _ptr, _ptr, _ptr]),
     'brv_stack_normalize': (_int, [_ptr, _i64, _int, _i64, _int, _int, _ptr,
                                    _ptr, _ptr, _ptr]),
     'brv_cumulative_normalize': (_int, [_ptr, _i64, _i64, _f32, _ptr, _ptr]),
     'brv_snr_forward': (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64,
-                               _i64, _i64, _int, _f32, _ptr, _ptr, _ptr, _sz,
-                               _ptr]),
+                               _i64, _i64, _int, _f32, _f32, _ptr, _ptr, _ptr,
+                               _sz, _ptr]),
     'brv_snr_workspace_bytes': (_sz, [_i64, _i64]),
     'brv_masked_affine': (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64,
                                  _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr,
@@ -101,6 +101,24 @@ def require_cuda(t, what):
             f'{what} is on {t.device}: brever_b200 runs on CUDA tensors only '
             '(there is deliberately no CPU fallback; move the tensor to the '
             'GPU or keep using brever.modules on CPU)')
+
+
+class _NullContext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullContext()
+
+
+def on_device(device):
+    """Context that makes `device` current for a launch; free when it already is."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(device)
 
 
 def stream_ptr(device):

@@ -61,8 +61,8 @@ def _workspace(nbytes, device):
     return ws
 
 
-def _moments(x3, y3, lengths, pairwise):
-    """Launch the fused reduction -> (dB (pairs,), moments (pairs, 6) float64)."""
+def _moments(x3, y3, lengths, pairwise, sign=1.0):
+    """Launch the fused reduction -> (sign * dB (pairs,), moments (pairs, 6) float64)."""
     batch, rows, length = x3.shape
     pairs = batch * rows * rows if pairwise else batch * rows
     db = torch.empty(pairs, dtype=torch.float32, device=x3.device)
@@ -71,12 +71,13 @@ def _moments(x3, y3, lengths, pairwise):
         lib = _lib.lib()
         nbytes = lib.brv_snr_workspace_bytes(pairs, length)
         ws = _workspace(nbytes, x3.device)
-        with torch.cuda.device(x3.device):
+        with _lib.on_device(x3.device):
             _lib.check(lib.brv_snr_forward(
                 _lib.ptr(x3), _lib.ptr(y3), _lib.ptr(lengths), batch, rows,
                 length, x3.stride(0), x3.stride(1), y3.stride(0), y3.stride(1),
-                int(pairwise), float(eps), _lib.ptr(db), _lib.ptr(mom),
-                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(x3.device)))
+                int(pairwise), float(eps), float(sign), _lib.ptr(db),
+                _lib.ptr(mom), _lib.ptr(ws), ws.numel(),
+                _lib.stream_ptr(x3.device)))
     return db, mom
 
 
@@ -84,7 +85,7 @@ def _masked_affine(x3, y3, lengths, ca, cb, c0, ymap=None):
     batch, rows, length = x3.shape
     gx = torch.empty((batch, rows, length), dtype=torch.float32, device=x3.device)
     if gx.numel():
-        with torch.cuda.device(x3.device):
+        with _lib.on_device(x3.device):
             _lib.check(_lib.lib().brv_masked_affine(
                 _lib.ptr(x3), _lib.ptr(y3), _lib.ptr(lengths), batch, rows,
                 length, x3.stride(0), x3.stride(1), y3.stride(0), y3.stride(1),
@@ -99,13 +100,13 @@ class _SnrFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, lengths):
         x3, y3 = _rows(x), _rows(y)
-        db, mom = _moments(x3, y3, lengths, False)
+        db, mom = _moments(x3, y3, lengths, False, -1.0)   # the kernel negates
         ctx.save_for_backward(x3, y3, lengths, mom)
         ctx.shape, ctx.dtype = x.shape, x.dtype
         db = db.view(x3.shape[0], x3.shape[1])
         if x.ndim == 2:       # torch's mean(()) reduces over every dim
-            return -db.mean()
-        return -db.mean(1)
+            return db.mean()
+        return db.view(-1) if x3.shape[1] == 1 else db.mean(1)
 
     @staticmethod
     def backward(ctx, grad):
@@ -132,27 +133,32 @@ class _SiSnrFunction(torch.autograd.Function):
     def forward(ctx, x, y, lengths):
         batch, n_src, _ = x.shape
         x3, y3 = _rows(x), _rows(y)
+        if n_src == 1:                             # no permutation: the kernel negates
+            loss, mom = _moments(x3, y3, lengths, True, -1.0)
+            ctx.save_for_backward(x3, y3, lengths, mom)
+            ctx.shape, ctx.dtype = x.shape, x.dtype
+            return loss
         db, mom = _moments(x3, y3, lengths, True)
         si_snr = db.view(batch, n_src, n_src)      # [b, target i, estimate j]
-        if n_src == 1:
-            best = si_snr.view(batch)
-            perm = torch.zeros((batch, 1), dtype=torch.int64, device=x.device)
-        else:
-            perms = torch.tensor(list(permutations(range(n_src))),
-                                 dtype=torch.int64, device=x.device)
-            # snr_set[b, p] = sum_i si_snr[b, i, perms[p, i]]   (criterion.py:66-68)
-            gathered = si_snr[:, torch.arange(n_src, device=x.device), perms]
-            totals = gathered.sum(-1)
-            best, which = totals.max(1)
-            perm = perms[which]                    # target i <- estimate perm[b, i]
-            best = best / n_src
+        perms = torch.tensor(list(permutations(range(n_src))),
+                             dtype=torch.int64, device=x.device)
+        # snr_set[b, p] = sum_i si_snr[b, i, perms[p, i]]   (criterion.py:66-68)
+        gathered = si_snr[:, torch.arange(n_src, device=x.device), perms]
+        totals = gathered.sum(-1)
+        best, which = totals.max(1)
+        perm = perms[which]                        # target i <- estimate perm[b, i]
+        best = best / n_src
         ctx.save_for_backward(x3, y3, lengths, mom, perm)
         ctx.shape, ctx.dtype = x.shape, x.dtype
         return -best
 
     @staticmethod
     def backward(ctx, grad):
-        x3, y3, lengths, mom, perm = ctx.saved_tensors
+        if len(ctx.saved_tensors) == 4:
+            x3, y3, lengths, mom = ctx.saved_tensors
+            perm = torch.zeros((x3.shape[0], 1), dtype=torch.int64, device=x3.device)
+        else:
+            x3, y3, lengths, mom, perm = ctx.saved_tensors
         batch, n_src, _ = x3.shape
         dev = x3.device
         # moments of the matched pairs: pair index = (b*S + i)*S + perm[b, i]
@@ -227,7 +233,7 @@ def _mask_raw(t, lengths):
     out = torch.empty_like(src)
     if src.numel():
         inner = src.numel() // (src.shape[0] * src.shape[-1])
-        with torch.cuda.device(src.device):
+        with _lib.on_device(src.device):
             _lib.check(_lib.lib().brv_apply_mask(
                 _lib.ptr(src), _lib.ptr(lengths), src.shape[0], inner,
                 src.shape[-1], _lib.ptr(out), _lib.stream_ptr(src.device)))

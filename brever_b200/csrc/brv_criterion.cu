@@ -12,26 +12,33 @@
 // ~1e-15 relative, so it does not cancel at high SNR.
 //
 // HBM-bound: 8 algorithmic bytes per (estimate, target) sample pair.
+#include <stdlib.h>
+
 #include "brv_common.cuh"
 
 namespace {
 
 constexpr int CR_THREADS = 256;
-constexpr int CR_CHUNK = 8192;   // samples per CTA (32 per thread)
+constexpr int CR_UNROLL = 4;                            // 16-byte loads in flight per array per thread
+constexpr int CR_BLOCK = CR_THREADS * 4 * CR_UNROLL;    // samples per CTA per iteration (4096)
 constexpr int CR_MOMENTS = 6;
 
 struct Moments {
     double sx, sy, sxy, sxx, syy, sdd;
     __device__ void zero() { sx = sy = sxy = sxx = syy = sdd = 0.0; }
-    __device__ void add(float xf, float yf) {
-        double x = xf, y = yf;
-        double d = (double)(yf - xf);
-        sx += x;
-        sy += y;
-        sxy = fma(x, y, sxy);
-        sxx = fma(x, x, sxx);
+    template <bool PAIRWISE>
+    __device__ __forceinline__ void add(float xf, float yf) {
+        const double x = xf, y = yf;
         syy = fma(y, y, syy);
-        sdd = fma(d, d, sdd);
+        if (PAIRWISE) {                 // SI-SNR: the five centred-moment sums
+            sx += x;
+            sy += y;
+            sxy = fma(x, y, sxy);
+            sxx = fma(x, x, sxx);
+        } else {                        // SNR: sum y^2 and sum (y - x)^2 (difference in float32,
+            const double d = (double)(yf - xf);   // as the reference forms it)
+            sdd = fma(d, d, sdd);
+        }
     }
 };
 
@@ -41,18 +48,39 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    return __ldcs(reinterpret_cast<const float4*>(p));
+}
+
+// Loads the 4 samples i .. i+3 of a row masked to `length` samples (exact zeros beyond it).
+__device__ __forceinline__ float4 load4(const float* row, int64_t i, int64_t length, bool vec) {
+    if (vec && i + 4 <= length) return ld_stream4(row + i);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < length) v.x = __ldcs(row + i);
+    if (i + 1 < length) v.y = __ldcs(row + i + 1);
+    if (i + 2 < length) v.z = __ldcs(row + i + 2);
+    if (i + 3 < length) v.w = __ldcs(row + i + 3);
+    return v;
+}
+
 // workspace layout: partial[n_pairs][chunks][6] doubles | ticket[n_pairs] uint32
+//
+// One CTA = one 4096-sample chunk of one (estimate, target) row pair.  Every thread
+// first issues all of its loads (4 x 16 B per array, 32 KB in flight per CTA, several
+// CTAs per SM: enough bytes in flight to cover HBM latency), then masks by index and
+// accumulates in float64.  Samples at or beyond lengths[b] contribute exact zeros.
+template <bool PAIRWISE, int ITERS>
 __global__ void __launch_bounds__(CR_THREADS)
 snr_moments_kernel(const float* __restrict__ x, const float* __restrict__ y,
                    const int64_t* __restrict__ lengths, int64_t n_rows, int64_t length,
-                   int64_t xsb, int64_t xsr, int64_t ysb, int64_t ysr, int pairwise,
-                   float eps, int chunks, float* __restrict__ out_db,
+                   int64_t xsb, int64_t xsr, int64_t ysb, int64_t ysr,
+                   float eps, float out_sign, int chunks, float* __restrict__ out_db,
                    double* __restrict__ moments, double* __restrict__ partial,
                    unsigned int* __restrict__ ticket) {
     const int64_t pair = blockIdx.x;
     const int chunk = blockIdx.y;
     int64_t b, xr, yr;
-    if (pairwise) {                      // pair = (b, target i, estimate j)
+    if (PAIRWISE) {                      // pair = (b, target i, estimate j)
         b = pair / (n_rows * n_rows);
         int64_t ij = pair % (n_rows * n_rows);
         yr = ij / n_rows;
@@ -69,27 +97,25 @@ snr_moments_kernel(const float* __restrict__ x, const float* __restrict__ y,
 
     Moments m;
     m.zero();
-    const int64_t begin = (int64_t)chunk * CR_CHUNK;
-    int64_t end = begin + CR_CHUNK;
-    if (end > valid) end = valid;
-    const bool vec = ((((uintptr_t)xp) | ((uintptr_t)yp)) & 15) == 0;
-    if (vec) {
-        // begin is a multiple of 4 and both rows are 16-byte aligned
-        for (int64_t i = begin + 4 * (int64_t)threadIdx.x; i < end; i += 4 * CR_THREADS) {
-            if (i + 4 <= end) {
-                float4 a = __ldg(reinterpret_cast<const float4*>(xp + i));
-                float4 c = __ldg(reinterpret_cast<const float4*>(yp + i));
-                m.add(a.x, c.x);
-                m.add(a.y, c.y);
-                m.add(a.z, c.z);
-                m.add(a.w, c.w);
-            } else {
-                for (int64_t j = i; j < end; ++j) m.add(__ldg(xp + j), __ldg(yp + j));
-            }
+    const bool vx = (((uintptr_t)xp) & 15) == 0, vy = (((uintptr_t)yp) & 15) == 0;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int64_t begin = ((int64_t)chunk * ITERS + it) * CR_BLOCK;
+        if (begin >= valid) break;
+        float4 a[CR_UNROLL], c[CR_UNROLL];
+#pragma unroll
+        for (int u = 0; u < CR_UNROLL; ++u) {
+            const int64_t i = begin + 4 * (int64_t)(u * CR_THREADS + threadIdx.x);
+            a[u] = load4(xp, i, valid, vx);
+            c[u] = load4(yp, i, valid, vy);
         }
-    } else {
-        for (int64_t i = begin + threadIdx.x; i < end; i += CR_THREADS)
-            m.add(__ldg(xp + i), __ldg(yp + i));
+#pragma unroll
+        for (int u = 0; u < CR_UNROLL; ++u) {
+            m.add<PAIRWISE>(a[u].x, c[u].x);
+            m.add<PAIRWISE>(a[u].y, c[u].y);
+            m.add<PAIRWISE>(a[u].z, c[u].z);
+            m.add<PAIRWISE>(a[u].w, c[u].w);
+        }
     }
 
     __shared__ double red[CR_THREADS / 32][CR_MOMENTS];
@@ -129,7 +155,7 @@ snr_moments_kernel(const float* __restrict__ x, const float* __restrict__ y,
         ticket[pair] = 0;                // leave the workspace zeroed for the next call
         const double e = (double)eps;
         double ratio;
-        if (pairwise) {
+        if (PAIRWISE) {
             // zero-mean over the valid length (criterion.py:48-49), closed form
             const double L = (double)lengths[b];   // the reference divides by lengths[b]
             const double sx = red[0][0], sy = red[0][1], sxy = red[0][2];
@@ -147,7 +173,7 @@ snr_moments_kernel(const float* __restrict__ x, const float* __restrict__ y,
         } else {
             ratio = red[0][4] / (red[0][5] + e);           // criterion.py:99
         }
-        out_db[pair] = (float)(10.0 * log10(ratio + e));   // criterion.py:61,100
+        out_db[pair] = out_sign * (float)(10.0 * log10(ratio + e));   // criterion.py:61,100
     }
 }
 
@@ -186,8 +212,18 @@ __global__ void apply_mask_kernel(const float* __restrict__ x, const int64_t* __
 
 }  // namespace
 
+// samples per CTA = ITERS * 4096; ITERS from BRV_CR_ITERS (1, 2 or 4; tuning knob)
+static int cr_iters() {
+    static int iters = 0;
+    if (!iters) {
+        const char* e = getenv("BRV_CR_ITERS");
+        int v = e ? atoi(e) : 2;
+        iters = (v == 1 || v == 2 || v == 4) ? v : 2;
+    }
+    return iters;
+}
 static int chunks_for(int64_t length) {
-    int64_t c = brv_ceil_div(length, CR_CHUNK);
+    int64_t c = brv_ceil_div(length, (int64_t)CR_BLOCK * cr_iters());
     return (int)(c < 1 ? 1 : c);
 }
 
@@ -200,8 +236,9 @@ extern "C" size_t brv_snr_workspace_bytes(int64_t n_pairs, int64_t length) {
 extern "C" int brv_snr_forward(const float* x, const float* y, const int64_t* lengths,
                                int64_t n_batch, int64_t n_rows, int64_t length,
                                int64_t xsb, int64_t xsr, int64_t ysb, int64_t ysr,
-                               int pairwise, float eps, float* out_db, double* moments,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+                               int pairwise, float eps, float out_sign, float* out_db,
+                               double* moments, void* workspace, size_t workspace_bytes,
+                               void* stream) {
     BRV_REQUIRE(x && y && lengths && out_db && moments && workspace, "null pointer argument");
     BRV_REQUIRE(n_batch >= 0 && n_rows >= 1 && length >= 0, "bad criterion shape");
     const int64_t n_pairs = pairwise ? n_batch * n_rows * n_rows : n_batch * n_rows;
@@ -216,9 +253,19 @@ extern "C" int brv_snr_forward(const float* x, const float* y, const int64_t* le
     size_t off = ((size_t)n_pairs * sizeof(unsigned int) + 255) & ~(size_t)255;
     double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + off);
     dim3 grid((unsigned)n_pairs, (unsigned)chunks);
-    snr_moments_kernel<<<grid, CR_THREADS, 0, (cudaStream_t)stream>>>(
-        x, y, lengths, n_rows, length, xsb, xsr, ysb, ysr, pairwise, eps, chunks, out_db,
-        moments, partial, ticket);
+#define BRV_LAUNCH_SNR(PW_, IT_)                                                              \
+    snr_moments_kernel<PW_, IT_><<<grid, CR_THREADS, 0, (cudaStream_t)stream>>>(                \
+        x, y, lengths, n_rows, length, xsb, xsr, ysb, ysr, eps, out_sign, chunks, out_db,       \
+        moments, partial, ticket)
+    switch (cr_iters() * 2 + (pairwise ? 1 : 0)) {
+        case 2: BRV_LAUNCH_SNR(false, 1); break;
+        case 3: BRV_LAUNCH_SNR(true, 1); break;
+        case 4: BRV_LAUNCH_SNR(false, 2); break;
+        case 5: BRV_LAUNCH_SNR(true, 2); break;
+        case 8: BRV_LAUNCH_SNR(false, 4); break;
+        default: BRV_LAUNCH_SNR(true, 4); break;
+    }
+#undef BRV_LAUNCH_SNR
     BRV_LAUNCH_CHECK("snr_moments_kernel");
     return BRV_OK;
 }

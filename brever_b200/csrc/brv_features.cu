@@ -14,7 +14,6 @@
 
 namespace {
 
-constexpr int FT_TILE = 64;     // output frames (pre-decimation) per CTA
 constexpr int FT_THREADS = 256;
 constexpr int FT_MAX_STACK = 32;
 
@@ -24,78 +23,135 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// dynamic smem: power[warps][n_bins] | energy[(FT_TILE + stacks)][n_mel + 1]
+// One CTA = `tile` output frames (pre-decimation) of one batch item, plus the `stacks`
+// frames of left context the stacker reaches back to.
+//   phase 1  all warps: |X|^2, channel mean -> power[staged][n_bins]   (coalesced 8-byte loads,
+//            four independent loads in flight per thread)
+//   phase 2  one thread per (frame, mel band): CSR row (values / columns staged in shared
+//            memory once per CTA) dotted with the frame's power row
+//   phase 3  optional pdf normalisation, log / cubic root
+//   phase 4  stack + decimate + (x - mean) / std, frames contiguous in the output
+// dynamic smem: vals[nnz] | cols[nnz] | rowptr[n_mel + 1] | power[staged][ldP] | energy[staged][n_mel + 1]
 __global__ void __launch_bounds__(FT_THREADS)
 fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_t sf,
                     int64_t st, int C, int n_bins, int64_t n_frames,
                     const float* __restrict__ mel_vals, const int32_t* __restrict__ mel_cols,
-                    const int32_t* __restrict__ mel_rowptr, int n_mel, int normalize,
+                    const int32_t* __restrict__ mel_rowptr, int n_mel, int nnz, int normalize,
                     int compression, float eps, int stacks, int decimation,
                     const float* __restrict__ mean, const float* __restrict__ stdv,
-                    float* __restrict__ out, int64_t out_frames, int tiles_per_item) {
+                    float* __restrict__ out, int64_t out_frames, int tile, int tiles_per_item) {
     extern __shared__ float smem[];
     const int warps = FT_THREADS / 32;
-    float* power = smem;                                   // [warps][n_bins]
-    float* energy = smem + (size_t)warps * n_bins;         // [FT_TILE+stacks][n_mel+1]
+    const int staged = tile + stacks;
+    const int ldP = n_bins | 1;                            // odd pitch: frames hit distinct banks
     const int ldE = n_mel + 1;
+    float* vals = smem;
+    int32_t* cols = reinterpret_cast<int32_t*>(smem + nnz);
+    int32_t* rowptr = cols + nnz;
+    float* power = reinterpret_cast<float*>(rowptr + n_mel + 1);
+    float* energy = power + (size_t)staged * ldP;
 
     const int64_t b = blockIdx.x / tiles_per_item;
-    const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_item) * FT_TILE;
+    const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_item) * tile;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int64_t first = t0 - stacks;                     // first frame staged (may be < 0)
-    const int staged = FT_TILE + stacks;
     const float inv_c = 1.f / (float)C;
 
-    for (int s = warp; s < staged; s += warps) {
-        int64_t t = first + s;
-        if (t < 0 || t >= n_frames) continue;              // t < 0 is never read: the
-                                                           // stacker clamps to frame 0 (ffnn.py:126)
-        float* pw = power + (size_t)warp * n_bins;
-        const float2* base = X + b * sb + t * st;
-        for (int f = lane; f < n_bins; f += 32) {
-            float acc = 0.f;
-            for (int c = 0; c < C; ++c) {
-                float2 v = __ldg(base + (int64_t)c * sc + (int64_t)f * sf);
-                acc = fmaf(v.x, v.x, acc);
-                acc = fmaf(v.y, v.y, acc);
+    for (int j = threadIdx.x; j < nnz; j += FT_THREADS) {
+        vals[j] = __ldg(mel_vals + j);
+        cols[j] = __ldg(mel_cols + j);
+    }
+    for (int j = threadIdx.x; j <= n_mel; j += FT_THREADS) rowptr[j] = __ldg(mel_rowptr + j);
+
+    // ---- phase 1: power spectrum, channel mean (features.py:186-188) ----
+    const float2* xb = X + b * sb;
+    if (sf <= st) {
+        // bins contiguous (frame-major spectrogram, what STFT.forward returns): lanes along bins
+        for (int s = warp; s < staged; s += warps) {
+            const int64_t t = first + s;
+            if (t < 0 || t >= n_frames) continue;          // t < 0 is never read: the stacker
+                                                           // clamps to frame 0 (ffnn.py:126)
+            const float2* base = xb + t * st;
+            float* pw = power + (size_t)s * ldP;
+            for (int f0 = 0; f0 < n_bins; f0 += 128) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int c = 0; c < C; ++c) {
+                    float2 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int f = f0 + u * 32 + lane;
+                        v[u] = f < n_bins ? __ldg(base + (int64_t)c * sc + (int64_t)f * sf)
+                                          : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[u] = fmaf(v[u].y, v[u].y, fmaf(v[u].x, v[u].x, acc[u]));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int f = f0 + u * 32 + lane;
+                    if (f < n_bins) pw[f] = acc[u] * inv_c;
+                }
             }
-            pw[f] = acc * inv_c;
         }
-        __syncwarp();
-        float part = 0.f;
-        for (int m = lane; m < n_mel; m += 32) {
-            float e = 0.f;
-            for (int j = mel_rowptr[m]; j < mel_rowptr[m + 1]; ++j)
-                e = fmaf(__ldg(mel_vals + j), pw[__ldg(mel_cols + j)], e);
-            energy[s * ldE + m] = e;
-            part += e;
+    } else {
+        // frames contiguous (bin-major spectrogram): lanes along frames
+        for (int f = warp; f < n_bins; f += warps) {
+            for (int s = lane; s < staged; s += 32) {
+                const int64_t t = first + s;
+                if (t < 0 || t >= n_frames) continue;
+                float acc = 0.f;
+                for (int c = 0; c < C; ++c) {
+                    const float2 v = __ldg(xb + (int64_t)c * sc + (int64_t)f * sf + t * st);
+                    acc = fmaf(v.y, v.y, fmaf(v.x, v.x, acc));
+                }
+                power[(size_t)s * ldP + f] = acc * inv_c;
+            }
         }
-        if (normalize) {                                    // features.py:192-193
-            float total = warp_sum(part) + eps;
-            __syncwarp();
-            for (int m = lane; m < n_mel; m += 32) energy[s * ldE + m] /= total;
-        }
-        __syncwarp();
-        for (int m = lane; m < n_mel; m += 32) {
-            float e = energy[s * ldE + m];
-            if (compression == 1) e = logf(e + eps);        // features.py:195-196
-            else if (compression == 2) e = cbrtf(e);        // features.py:197-198
-            energy[s * ldE + m] = e;
-        }
-        __syncwarp();
     }
     __syncthreads();
 
-    // out[b, k*n_mel + m, t/dec] = (E[m, max(t - k, 0)] - mean) / std
+    // ---- phase 2: banded mel projection (stft.py:189-190) ----
+    for (int idx = threadIdx.x; idx < staged * n_mel; idx += FT_THREADS) {
+        const int s = idx / n_mel, m = idx - s * n_mel;
+        const int64_t t = first + s;
+        if (t < 0 || t >= n_frames) continue;
+        const float* pw = power + (size_t)s * ldP;
+        float e = 0.f;
+        for (int j = rowptr[m]; j < rowptr[m + 1]; ++j) e = fmaf(vals[j], pw[cols[j]], e);
+        energy[s * ldE + m] = e;
+    }
+    __syncthreads();
+
+    // ---- phase 3: pdf normalisation (features.py:192-193), compression (:195-198) ----
+    if (normalize) {
+        for (int s = warp; s < staged; s += warps) {
+            float part = 0.f;
+            for (int m = lane; m < n_mel; m += 32) part += energy[s * ldE + m];
+            const float total = warp_sum(part) + eps;
+            for (int m = lane; m < n_mel; m += 32) energy[s * ldE + m] /= total;
+        }
+        __syncthreads();
+    }
+    if (compression) {
+        for (int idx = threadIdx.x; idx < staged * n_mel; idx += FT_THREADS) {
+            const int s = idx / n_mel, m = idx - s * n_mel;
+            float e = energy[s * ldE + m];
+            e = compression == 1 ? logf(e + eps) : cbrtf(e);
+            energy[s * ldE + m] = e;
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 4: out[b, k*n_mel + m, t/dec] = (E[m, max(t - k, 0)] - mean) / std ----
     const int rows = n_mel * (stacks + 1);
     const int64_t o0 = brv_ceil_div(t0, decimation);       // first output frame of this tile
-    int64_t t_end = t0 + FT_TILE < n_frames ? t0 + FT_TILE : n_frames;
+    int64_t t_end = t0 + tile < n_frames ? t0 + tile : n_frames;
     const int64_t o1 = brv_ceil_div(t_end, decimation);
     const int width = (int)(o1 - o0);
     if (width <= 0) return;
     for (int idx = threadIdx.x; idx < rows * width; idx += FT_THREADS) {
-        int r = idx / width, w = idx % width;
-        int k = r / n_mel, m = r % n_mel;
+        int r = idx / width, w = idx - r * width;
+        int k = r / n_mel, m = r - k * n_mel;
         int64_t t = (o0 + w) * decimation;
         int64_t src = t - k;
         if (src < 0) src = 0;
@@ -179,7 +235,7 @@ __global__ void cumulative_normalize_kernel(const float* __restrict__ x, int64_t
 extern "C" int brv_fbe_features(const void* X, int64_t sb, int64_t sc, int64_t sf, int64_t st,
                                 int64_t n_batch, int n_channels, int n_bins, int64_t n_frames,
                                 const float* mel_vals, const int32_t* mel_cols,
-                                const int32_t* mel_rowptr, int n_mel, int normalize,
+                                const int32_t* mel_rowptr, int n_mel, int nnz, int normalize,
                                 int compression, float eps, int stacks, int decimation,
                                 const float* mean, const float* stdv, float* out, void* stream) {
     BRV_REQUIRE(X && mel_vals && mel_cols && mel_rowptr && out, "null pointer argument");
@@ -189,17 +245,26 @@ extern "C" int brv_fbe_features(const void* X, int64_t sb, int64_t sc, int64_t s
     BRV_REQUIRE(decimation >= 1, "decimation must be >= 1");
     if (n_batch == 0 || n_frames == 0) return BRV_OK;
     const int64_t out_frames = brv_ceil_div(n_frames, decimation);
-    const int tiles = (int)brv_ceil_div(n_frames, FT_TILE);
+    // frames per CTA: the largest tile that still fills the machine (>= 4 CTAs per SM)
+    int sm_count = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    int tile = 64;
+    while (tile > 8 && n_batch * brv_ceil_div(n_frames, tile) < 4LL * sm_count) tile /= 2;
+    const int tiles = (int)brv_ceil_div(n_frames, tile);
     const int64_t grid = n_batch * tiles;
     BRV_REQUIRE(grid < (1LL << 31), "too many feature tiles");
-    size_t smem = ((size_t)(FT_THREADS / 32) * n_bins + (size_t)(FT_TILE + stacks) * (n_mel + 1)) * sizeof(float);
+    BRV_REQUIRE(nnz >= 0 && nnz <= n_mel * n_bins, "bad CSR row pointer");
+    const int staged = tile + stacks;
+    size_t smem = ((size_t)2 * nnz + n_mel + 1 + (size_t)staged * (n_bins | 1) +
+                   (size_t)staged * (n_mel + 1)) * sizeof(float);
     BRV_REQUIRE(smem <= 200 * 1024, "feature tile does not fit shared memory (%zu bytes)", smem);
     if (smem > 48 * 1024)
         BRV_CUDA(cudaFuncSetAttribute(fbe_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     fbe_features_kernel<<<(unsigned)grid, FT_THREADS, smem, (cudaStream_t)stream>>>(
         (const float2*)X, sb, sc, sf, st, n_channels, n_bins, n_frames, mel_vals, mel_cols,
-        mel_rowptr, n_mel, normalize, compression, eps, stacks, decimation, mean, stdv, out,
-        out_frames, tiles);
+        mel_rowptr, n_mel, nnz, normalize, compression, eps, stacks, decimation, mean, stdv, out,
+        out_frames, tile, tiles);
     BRV_LAUNCH_CHECK("fbe_features_kernel");
     return BRV_OK;
 }

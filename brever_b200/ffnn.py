@@ -41,7 +41,7 @@ def _stack_raw(data, stacks, decimation=1, mean=None, std=None):
     mean_t, std_t = _stats(mean, rows, x.device), _stats(std, rows, x.device)
     for start in range(0, batch, 65535):
         chunk = x[start:start + 65535]
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             _lib.check(_lib.lib().brv_stack_normalize(
                 _lib.ptr(chunk), chunk.shape[0], nf, frames, int(stacks),
                 int(decimation), _lib.ptr(mean_t), _lib.ptr(std_t),
@@ -95,7 +95,7 @@ class CumulativeNormalizer(nn.Module):
         src = x.float().contiguous()
         out = torch.empty_like(src)
         if src.numel():
-            with torch.cuda.device(src.device):
+            with _lib.on_device(src.device):
                 _lib.check(_lib.lib().brv_cumulative_normalize(
                     _lib.ptr(src), src.numel() // src.shape[-1], src.shape[-1],
                     float(self.eps), _lib.ptr(out), _lib.stream_ptr(src.device)))

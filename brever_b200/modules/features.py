@@ -121,11 +121,11 @@ class FeatureExtractor:
                 raise RuntimeError(f'statistics must have {rows} entries')
             return t.contiguous()
         mean_t, std_t = stat(mean), stat(std)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             _lib.check(_lib.lib().brv_fbe_features(
                 _lib.ptr(x), x.stride(0), x.stride(1), x.stride(2), x.stride(3),
                 batch, channels, bins, frames, _lib.ptr(vals), _lib.ptr(cols),
-                _lib.ptr(rowptr), n_mel, int(normalize),
+                _lib.ptr(rowptr), n_mel, int(vals.numel()), int(normalize),
                 _COMPRESSION[compression], float(eps), int(stacks),
                 int(decimation), _lib.ptr(mean_t), _lib.ptr(std_t),
                 _lib.ptr(out), _lib.stream_ptr(x.device)))

@@ -159,7 +159,7 @@ class STFT:
         out = torch.empty((n_sig, frames, self.n_bins), dtype=torch.complex64,
                           device=x2d.device)
         if n_sig:
-            with torch.cuda.device(x2d.device):
+            with _lib.on_device(x2d.device):
                 _lib.check(_lib.lib().brv_stft_forward(
                     self._plan(x2d.device), _lib.ptr(x2d), n_sig, samples,
                     x2d.stride(0) if n_sig > 1 else samples, _lib.ptr(out),
@@ -172,7 +172,7 @@ class STFT:
         gx = torch.empty((n_sig, samples), dtype=torch.float32, device=grad.device)
         if n_sig:
             lib = _lib.lib()
-            with torch.cuda.device(grad.device):
+            with _lib.on_device(grad.device):
                 plan = self._plan(grad.device)
                 nbytes = lib.brv_stft_workspace_bytes(plan, n_sig, frames)
                 ws = _lib.workspace(nbytes, grad.device)
@@ -191,7 +191,7 @@ class STFT:
         out_len = self.hop_length * (frames - 1) + self.n_fft - 2 * (self.n_fft // 2)
         y = torch.empty((n_sig, out_len), dtype=torch.float32, device=spec3d.device)
         lib = _lib.lib()
-        with torch.cuda.device(spec3d.device):
+        with _lib.on_device(spec3d.device):
             plan = self._plan(spec3d.device)
             nbytes = lib.brv_stft_workspace_bytes(plan, n_sig, frames)
             ws = _lib.workspace(nbytes, spec3d.device)
@@ -208,7 +208,7 @@ class STFT:
                          device=grad.device)
         if n_sig:
             lib = _lib.lib()
-            with torch.cuda.device(grad.device):
+            with _lib.on_device(grad.device):
                 plan = self._plan(grad.device)
                 nbytes = lib.brv_stft_workspace_bytes(plan, n_sig, frames)
                 ws = _lib.workspace(nbytes, grad.device)
@@ -370,7 +370,7 @@ class MelFilterbank:
         # grid.z carries the batch: chunk to the CUDA limit
         for start in range(0, x3.shape[0], 65535):
             chunk = x3[start:start + 65535]
-            with torch.cuda.device(x.device):
+            with _lib.on_device(x.device):
                 _lib.check(_lib.lib().brv_mel_apply(
                     _lib.ptr(chunk), chunk.stride(0), chunk.stride(1),
                     chunk.stride(2), chunk.shape[0], n_in, frames,

@@ -146,15 +146,16 @@ int brv_mel_apply(const float* x, int64_t stride_batch, int64_t stride_row,
  *   out[b, k*n_mel + m, t'] = (E[m, max(t'*dec - k, 0)] - mean) / std,
  *                              k = 0..stacks (mean/std nullable).
  * X : complex64 (B, C, F, T) with element strides (complex units).
+ * mel_vals / mel_cols : mel_nnz CSR entries; mel_rowptr : n_mel + 1 offsets.
  * out : (B, n_mel*(stacks+1), ceil(T/dec)) float32 contiguous.               */
 int brv_fbe_features(const void* X, int64_t stride_b, int64_t stride_c,
                      int64_t stride_f, int64_t stride_t, int64_t n_batch,
                      int n_channels, int n_bins, int64_t n_frames,
                      const float* mel_vals, const int32_t* mel_cols,
-                     const int32_t* mel_rowptr, int n_mel, int normalize,
-                     int compression, float eps, int stacks, int decimation,
-                     const float* mean, const float* std, float* out,
-                     void* stream);
+                     const int32_t* mel_rowptr, int n_mel, int mel_nnz,
+                     int normalize, int compression, float eps, int stacks,
+                     int decimation, const float* mean, const float* std,
+                     float* out, void* stream);
 
 /* FFNN.stack + decimate + StaticNormalizer on an existing feature tensor
  * (ffnn.py:122-135,186-187): x (B, nf, T) contiguous -> (B, nf*(stacks+1), T'). */
@@ -175,8 +176,10 @@ int brv_cumulative_normalize(const float* x, int64_t n_rows, int64_t n_frames,
  *       out_db[b, i, j] = SI-SNR of estimate j against target i (zero-mean over
  *       the valid length).  The S! permutation max stays in the Python mirror.
  * Row r of batch b starts at b*stride_batch + r*stride_row (elements).
+ * out_sign : multiplies the dB value (-1 gives the loss directly).
  * moments : (n_pairs, 6) float64 = [sum x, sum y, sum xy, sum x^2, sum y^2,
- *           sum (y-x)^2] over the valid length, kept for the backward pass.
+ *           sum (y-x)^2] over the valid length, kept for the backward pass
+ *           (pairwise: the first five, [5] = 0; otherwise [4] and [5], rest 0).
  * workspace : brv_snr_workspace_bytes(n_pairs, length) bytes whose leading
  *           4*n_pairs bytes (rounded up to 256) must be ZERO on entry; the
  *           kernel leaves them zeroed again, so one cached buffer serves
@@ -185,8 +188,8 @@ int brv_snr_forward(const float* x, const float* y, const int64_t* lengths,
                     int64_t n_batch, int64_t n_rows, int64_t length,
                     int64_t x_stride_batch, int64_t x_stride_row,
                     int64_t y_stride_batch, int64_t y_stride_row, int pairwise,
-                    float eps, float* out_db, double* moments, void* workspace,
-                    size_t workspace_bytes, void* stream);
+                    float eps, float out_sign, float* out_db, double* moments,
+                    void* workspace, size_t workspace_bytes, void* stream);
 size_t brv_snr_workspace_bytes(int64_t n_pairs, int64_t length);
 
 /* Gradient w.r.t. the estimate as an affine masked map per estimate row:
