@@ -22,11 +22,25 @@ int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t 
                    int64_t n_sig, int64_t n_frames, int64_t out_len, float* y, cudaStream_t st);
 
 static int g_force_generic = -1;
-static int g_tc_variant = 0;   // 0: folded kernels where supported, 1: dense contraction only
+extern int g_brv_fold_variant;
+// 0: folded kernels where supported (forward kernel picked by tile count), 1: dense contraction
+// only, 2 / 3: folded kernels with the forward forced to one tile per CTA / persistent two-pass
+static int g_tc_variant = -1;
+
+static int tc_variant() {
+    if (g_tc_variant < 0) {
+        const char* e = getenv("BRV_TC_VARIANT");
+        const int v = e ? atoi(e) : 0;
+        g_tc_variant = (v >= 1 && v <= 3) ? v : 0;
+        g_brv_fold_variant = g_tc_variant >= 2 ? g_tc_variant : 0;
+    }
+    return g_tc_variant;
+}
 
 extern "C" int brv_set_tc_variant(int variant) {
-    int prev = g_tc_variant;
-    g_tc_variant = variant == 1 ? 1 : 0;
+    int prev = tc_variant();
+    g_tc_variant = (variant >= 1 && variant <= 3) ? variant : 0;
+    g_brv_fold_variant = g_tc_variant >= 2 ? g_tc_variant : 0;
     return prev;
 }
 
@@ -55,7 +69,7 @@ extern "C" int brv_stft_forward(const brv_stft_plan* p, const float* x, int64_t 
     int rc = brv_stft_geometry(p, samples, &n_frames, nullptr, nullptr);
     if (rc != BRV_OK) return rc;
     if (n_signals == 0) return BRV_OK;
-    if (!force_generic() && g_tc_variant == 0 && brv_fold_supported(p))
+    if (!force_generic() && tc_variant() != 1 && brv_fold_supported(p))
         return brv_fold_stft_forward(p, x, n_signals, samples, x_stride, (float2*)out, n_frames,
                                      (cudaStream_t)stream);
     if (!force_generic() && brv_tc_supported(p))
@@ -95,7 +109,7 @@ extern "C" int brv_istft_forward(const brv_stft_plan* p, const void* X, int64_t 
     if (rc != BRV_OK) return rc;
     if (n_signals == 0 || out_len == 0) return BRV_OK;
     BRV_REQUIRE(y, "output pointer is null");
-    if (!force_generic() && g_tc_variant == 0 && brv_fold_inverse_supported(p))
+    if (!force_generic() && tc_variant() != 1 && brv_fold_inverse_supported(p))
         return brv_fold_istft(p, (const float2*)X, ss, sb, sf, n_signals, n_frames, out_len, y,
                               (cudaStream_t)stream);   // fused overlap-add: no workspace
     BRV_REQUIRE(workspace && workspace_bytes >= brv_stft_workspace_bytes(p, n_signals, n_frames),

@@ -76,6 +76,7 @@ struct FoldFwdParams {
     int n_fft, hop, n_bins, q;
     int rows;                    // frames per tile (<= 128, span fits SPAN_MAX)
     int tiles_per_signal;
+    int64_t total_tiles;         // n_signals * tiles_per_signal (persistent kernel)
     int tmem_cols;
     float wq, w3q;               // w[Q] / norm, w[3Q] / norm
     float wmax;                  // max |w| / norm
@@ -371,6 +372,399 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
 }
 
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N_PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
+}
+
+// =====================================================================================
+// Pipelined persistent forward (default).  Same arithmetic as stft_fold_kernel, but the
+// four sub-GEMMs are grouped by bin parity into two passes with their own halves of
+// TMEM, so that every phase overlaps another one:
+//
+//   pass A  even bins  ee -> Re X[2m]    oe -> Im X[2m]      TMEM columns [0, 2Q)
+//   pass B  odd bins   eo -> Re X[2m+1]  oo -> Im X[2m+1]    TMEM columns [2Q, 4Q)
+//
+//   warp 0       TMA producer: basis k-chunks of the current pass (2-stage ring)
+//   warp 1       TMEM owner + MMA issuer; waits for the epilogue to hand a half back
+//   warps 4-7    epilogue: drain one half (TMEM -> registers -> per-warp transpose ->
+//                complex64 stores of that parity's bins) while the tensor core and the
+//                builders work on the other half / the next tile
+//   warps 8-15   builders: stage the tile's sample span (the next tile's span is
+//                prefetched into L2 a tile ahead), window, fold, scale, split
+//
+// One CTA per SM walks the tile list, so barrier setup, TMEM allocation and the tensor
+// map fetch are paid once per SM and a tile's stores drain under the next tile's loads.
+constexpr int F2_BUILDERS = 16;                                   // builder warps
+constexpr int F2_BUILDER_THREADS = F2_BUILDERS * 32;
+constexpr int F2_ROWS_PER_WARP = TILE_M / F2_BUILDERS;            // 8
+constexpr int F2_THREADS = 256 + F2_BUILDER_THREADS;
+constexpr int F2_EPI_WARP0 = 4;
+constexpr int F2_EPI_WARPS = 4;
+constexpr int F2_BUILD_WARP0 = 8;
+constexpr int F2_EPI_PITCH = 34;                                   // floats: 16 complex + pad
+constexpr int F2_OFF_SPAN = SMEM_STAGES;
+constexpr int F2_OFF_WTAB = F2_OFF_SPAN + SMEM_SPAN;
+constexpr int F2_OFF_ROWINFO = F2_OFF_WTAB + SMEM_WTAB;             // 2 slots x 128 float4
+constexpr int F2_OFF_BMAX = F2_OFF_ROWINFO + 2 * TILE_M * 16;
+constexpr int F2_OFF_EPI = F2_OFF_BMAX + 2112;
+constexpr int F2_SMEM_EPI = F2_EPI_WARPS * 32 * F2_EPI_PITCH * 4;
+constexpr int F2_SMEM_BYTES = 1024 + F2_OFF_EPI + F2_SMEM_EPI;
+static_assert(F2_SMEM_BYTES <= 227 * 1024, "forward kernel shared memory");
+
+template <bool COMPRESS>
+__global__ void __launch_bounds__(F2_THREADS, 1)
+stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tmem_full[2];     // MMA -> epilogue, per pass
+    __shared__ __align__(8) uint64_t tmem_empty[2];    // epilogue -> MMA, per pass
+    __shared__ __align__(8) uint64_t ri_full[2];       // builders -> epilogue (row info slot)
+    __shared__ __align__(8) uint64_t ri_empty[2];      // epilogue -> builders
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    uint8_t* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* span = reinterpret_cast<float*>(stages + F2_OFF_SPAN);
+    float4* wtab = reinterpret_cast<float4*>(stages + F2_OFF_WTAB);
+    float4* rowinfo2 = reinterpret_cast<float4*>(stages + F2_OFF_ROWINFO);
+    uint32_t* bmax = reinterpret_cast<uint32_t*>(stages + F2_OFF_BMAX);
+    float* epi = reinterpret_cast<float*>(stages + F2_OFF_EPI);
+
+    const int N = p.n_fft, H = p.hop, Q = p.q, Hf = N / 2;
+    const int n_kc = Q / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1 + F2_BUILDERS);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], F2_EPI_WARPS);
+            mbar_init(&ri_full[b], F2_BUILDERS);
+            mbar_init(&ri_empty[b], F2_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    for (int j = threadIdx.x; j < Q; j += F2_THREADS) wtab[j] = __ldg(p.wtab + j);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer ====================================
+        if (elect_one()) {
+            int g = 0;
+            for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x)
+                for (int pass = 0; pass < 2; ++pass)
+                    for (int kc = 0; kc < n_kc; ++kc, ++g) {
+                        const int s = g % STAGES;
+                        const uint32_t ph = (g / STAGES) & 1;
+                        mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
+                        uint8_t* sb = stages + (size_t)s * STAGE_BYTES + STAGE_A;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)      // j = 0: cos-type sub, 1: sin-type
+#pragma unroll
+                            for (int pl = 0; pl < 2; ++pl)
+                                tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
+                                            &full_bar[s], kc * BK, (pl * 4 + 2 * j + pass) * Q);
+                    }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer ======================================
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_f16(TILE_M, Q);
+            int g = 0, n = 0;
+            for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n)
+                for (int pass = 0; pass < 2; ++pass) {
+                    mbar_wait_relaxed(&tmem_empty[pass], (uint32_t)((n & 1) ^ 1));
+                    tcgen05_fence_after();
+                    for (int kc = 0; kc < n_kc; ++kc, ++g) {
+                        const int s = g % STAGES;
+                        const uint32_t ph = (g / STAGES) & 1;
+                        mbar_wait_relaxed(&full_bar[s], ph, 32);
+                        tcgen05_fence_after();
+                        const uint32_t a0 = smem_u32(stages + (size_t)s * STAGE_BYTES);
+                        const uint32_t b0 = a0 + STAGE_A;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint32_t d = tmem_base + (uint32_t)((pass * 2 + j) * Q);
+#pragma unroll
+                            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                                const uint32_t off = ks * UMMA_K * 2;
+                                const uint64_t dah = umma_desc_sw64(a0 + (j * 2) * SUB_TILE + off);
+                                const uint64_t dal = umma_desc_sw64(a0 + (j * 2 + 1) * SUB_TILE + off);
+                                const uint64_t dbh = umma_desc_sw64(b0 + (j * 2) * SUB_TILE + off);
+                                const uint64_t dbl = umma_desc_sw64(b0 + (j * 2 + 1) * SUB_TILE + off);
+                                umma_f16(d, dah, dbh, idesc, (kc | ks) != 0);
+                                umma_f16(d, dal, dbh, idesc, 1);
+                                umma_f16(d, dah, dbl, idesc, 1);
+                            }
+                        }
+                        umma_commit(&empty_bar[s]);
+                    }
+                    umma_commit(&tmem_full[pass]);
+                }
+        }
+    } else if (warp >= F2_EPI_WARP0 && warp < F2_EPI_WARP0 + F2_EPI_WARPS) {
+        // ===================== epilogue ========================================
+        const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        float* stg = epi + (size_t)q * 32 * F2_EPI_PITCH;
+        const int pitch = 2 * p.n_bins;
+        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int sub_row = lane >> 4, cl = lane & 15;
+        int n = 0;
+        for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
+            const int slot = n & 1;
+            const int64_t sig = tile_id / p.tiles_per_signal;
+            const int64_t t0 = (int64_t)(tile_id % p.tiles_per_signal) * p.rows;
+            const int rows_eff = (int)min((int64_t)p.rows, p.n_frames - t0);
+            const int rows_w = min(32, rows_eff - q * 32);
+            const bool live = row < rows_eff;
+            mbar_wait_relaxed(&ri_full[slot], (uint32_t)((n >> 1) & 1));
+            const float4 ri = rowinfo2[slot * TILE_M + row];   // scale, nyquist sum, ee[Q], oo[Q]
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ri_empty[slot]);
+            // without compression scale_factor folds into the per-row factors
+            const float ps = COMPRESS ? 1.f : p.post_scale;
+            const float g0 = live ? ps * p.basis_scale_inv / ri.x : 0.f;
+            const float eeq = live ? ps * ri.z : 0.f, ooq = live ? ps * ri.w : 0.f;
+            float* obase = p.out + (sig * p.n_frames + t0 + q * 32) * (int64_t)pitch;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                mbar_wait_relaxed(&tmem_full[pass], (uint32_t)(n & 1));
+                tcgen05_fence_after();
+                const float rq = pass == 0 ? eeq : 0.f;    // rank-1 term of Re (even bins)
+                const float iq = pass == 1 ? -ooq : 0.f;   // rank-1 term of Im (odd bins)
+                const uint32_t tp = tq + (uint32_t)(pass * 2 * Q);
+#pragma unroll 1
+                for (int c = 0; c < Q / 16; ++c) {
+                    const int m0 = 16 * c;
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16_nowait(tp + (uint32_t)m0, r0);
+                    tmem_ld16_nowait(tp + (uint32_t)(Q + m0), r1);
+                    tmem_ld_wait();
+                    if (c == Q / 16 - 1) {                 // last read of this half: hand it back
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[pass]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float re = fmaf(__uint_as_float(r0[j]), g0, (j & 1) ? -rq : rq);   // m0 is even
+                        float im = fmaf(__uint_as_float(r1[j]), g0, (j & 1) ? -iq : iq);
+                        if (COMPRESS) {
+                            compress(re, im, p.post_expo);
+                            re *= p.post_scale;
+                            im *= p.post_scale;
+                        }
+                        *reinterpret_cast<float2*>(stg + lane * F2_EPI_PITCH + 2 * j) =
+                            make_float2(re, im);
+                    }
+                    __syncwarp();
+                    // bins 2 (m0 + cl) + pass of rows sub_row, sub_row + 2, ...
+                    float* ocol = obase + 2 * (2 * (m0 + cl) + pass) + (int64_t)sub_row * pitch;
+                    const float* srow = stg + sub_row * F2_EPI_PITCH + 2 * cl;
+#pragma unroll 4
+                    for (int rr = sub_row; rr < rows_w; rr += 2) {
+                        *reinterpret_cast<float2*>(ocol) = *reinterpret_cast<const float2*>(srow);
+                        ocol += 2 * (int64_t)pitch;
+                        srow += 2 * F2_EPI_PITCH;
+                    }
+                    __syncwarp();
+                }
+                if (pass == 0 && live) {                   // Nyquist bin: purely real
+                    float v = ri.y + ri.z;                 // Q is even: (-1)^Q = +1
+                    if (COMPRESS) v = compress_real(v, p.post_expo);
+                    *reinterpret_cast<float2*>(obase + (int64_t)lane * pitch + 2 * Hf) =
+                        make_float2(v * p.post_scale, 0.f);
+                }
+            }
+        }
+    } else if (warp >= F2_BUILD_WARP0) {
+        // ===================== builders ========================================
+        const int bw = warp - F2_BUILD_WARP0;      // 0..15
+        const int bt = bw * 32 + lane;             // 0..511
+        const int half = lane >> 4;                // which of the warp's two rows per pass
+        const int pr = lane & 15;                  // n pair inside the 32-wide k-chunk
+        const uint32_t chunk = (uint32_t)(pr >> 2);
+        int g = 0, n = 0;
+        for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
+            const int slot = n & 1;
+            float4* rowinfo = rowinfo2 + slot * TILE_M;
+            const int64_t sig = tile_id / p.tiles_per_signal;
+            const int64_t t0 = (int64_t)(tile_id % p.tiles_per_signal) * p.rows;
+            const int rows_eff = (int)min((int64_t)p.rows, p.n_frames - t0);
+            const float* xs = p.x + sig * p.x_stride;
+            const int64_t span0 = t0 * H - Hf;         // first sample of the span (may be < 0)
+            const int span_len = (rows_eff - 1) * H + N;
+            const int span_pad = (span_len + 31) & ~31;
+            if (n > 0) named_bar_sync(1, F2_BUILDER_THREADS);   // previous tile's span fully read
+
+            // ---- stage the sample span + per-32-sample maxima ------------------------
+            // aligned rows: every thread fires all of its 16-byte cp.async copies at once
+            // (zero-filled outside [0, samples)), so one memory latency covers the whole span
+            const bool vec = ((((uintptr_t)xs) & 15) == 0) && ((span0 & 3) == 0);
+            if (vec) {
+                for (int i = bt * 4; i < span_pad; i += F2_BUILDER_THREADS * 4) {
+                    const int64_t idx = span0 + i;
+                    const int64_t nb = (p.samples - idx) * 4;           // valid bytes from idx on
+                    const uint32_t src_bytes = idx < 0 ? 0u : (uint32_t)(nb < 0 ? 0 : (nb > 16 ? 16 : nb));
+                    const float* src = src_bytes ? xs + idx : xs;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(span + i)),
+                                 "l"(src), "r"(src_bytes)
+                                 : "memory");
+                }
+                cp_async_commit();
+            } else {
+                for (int i = bt * 4; i < span_pad; i += F2_BUILDER_THREADS * 4) {
+                    const int64_t idx = span0 + i;
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx >= 0 && idx < p.samples) f.x = __ldg(xs + idx);
+                    if (idx + 1 >= 0 && idx + 1 < p.samples) f.y = __ldg(xs + idx + 1);
+                    if (idx + 2 >= 0 && idx + 2 < p.samples) f.z = __ldg(xs + idx + 2);
+                    if (idx + 3 >= 0 && idx + 3 < p.samples) f.w = __ldg(xs + idx + 3);
+                    *reinterpret_cast<float4*>(span + i) = f;
+                }
+            }
+            // ---- pull the NEXT tile's span into L2 while this tile is built -----------
+            {
+                const int64_t nt = tile_id + gridDim.x;
+                if (nt < p.total_tiles) {
+                    const int64_t nsig = nt / p.tiles_per_signal;
+                    const int64_t nt0 = (int64_t)(nt % p.tiles_per_signal) * p.rows;
+                    const int nrows = (int)min((int64_t)p.rows, p.n_frames - nt0);
+                    int64_t lo = nt0 * H - Hf, hi = lo + (int64_t)(nrows - 1) * H + N;
+                    if (lo < 0) lo = 0;
+                    if (hi > p.samples) hi = p.samples;
+                    const float* nx = p.x + nsig * p.x_stride;
+                    for (int64_t i = lo + (int64_t)bt * 32; i < hi; i += F2_BUILDER_THREADS * 32)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+                }
+            }
+            cp_async_wait<0>();
+            for (int i0 = bw * 128; i0 < span_pad; i0 += F2_BUILDER_THREADS * 4) {   // own copies only
+                const int i = i0 + lane * 4;
+                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < span_pad) f = *reinterpret_cast<const float4*>(span + i);
+                // fmaxf drops NaNs; an inf is removed by the slow path
+                float m = fmaxf(fmaxf(fabsf(f.x), fabsf(f.y)), fmaxf(fabsf(f.z), fabsf(f.w)));
+                if (!(m <= 3.0e38f))
+                    m = fmaxf(fmaxf(finite_abs(f.x), finite_abs(f.y)),
+                              fmaxf(finite_abs(f.z), finite_abs(f.w)));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                if ((lane & 7) == 0 && i < span_pad) bmax[i >> 5] = __float_as_uint(m);
+            }
+            named_bar_sync(1, F2_BUILDER_THREADS);
+
+            // ---- per-row scale, rank-1 terms ------------------------------------------
+            mbar_wait(&ri_empty[slot], (uint32_t)(((n >> 1) & 1) ^ 1));
+            if (bt < TILE_M) {
+                float4 ri = make_float4(1.f, 0.f, 0.f, 0.f);
+                if (bt < rows_eff) {
+                    const int b0 = (bt * H) >> 5, b1 = (bt * H + N - 1) >> 5;
+                    uint32_t mx = 0u;
+                    for (int b = b0; b <= b1; ++b) mx = max(mx, bmax[b]);
+                    ri.x = row_scale(4.f * p.wmax * __uint_as_float(mx));
+                    const float xq = span[bt * H + Q] * p.wq, x3q = span[bt * H + 3 * Q] * p.w3q;
+                    ri.z = xq + x3q;                   // ee[Q]
+                    ri.w = xq - x3q;                   // oo[Q]
+                }
+                rowinfo[bt] = ri;
+            }
+            named_bar_sync(1, F2_BUILDER_THREADS);
+
+            constexpr int RI = F2_ROWS_PER_WARP / 2;      // row pairs per warp
+            float rscale[RI];
+#pragma unroll
+            for (int i = 0; i < RI; ++i) {
+                const int row = bw * F2_ROWS_PER_WARP + 2 * i + half;
+                rscale[i] = row < rows_eff ? rowinfo[row].x : 0.f;
+            }
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                float nyq[RI];
+#pragma unroll
+                for (int i = 0; i < RI; ++i) nyq[i] = 0.f;
+                for (int kc = 0; kc < n_kc; ++kc, ++g) {
+                    const int n0 = kc * BK + 2 * pr;
+                    const float4 w0 = wtab[n0], w1 = wtab[n0 + 1];
+                    const int s = g % STAGES;
+                    const uint32_t ph = (g / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = stages + (size_t)s * STAGE_BYTES;
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) {
+                        const int row = bw * F2_ROWS_PER_WARP + 2 * i + half;
+                        if (row >= rows_eff) continue;
+                        const float* fr = span + row * H;
+                        const float a0 = fr[n0] * w0.x, a1 = fr[n0 + 1] * w1.x;
+                        const float b0 = fr[Hf - n0] * w0.y, b1 = fr[Hf - n0 - 1] * w1.y;
+                        const float c0 = fr[Hf + n0] * w0.z, c1 = fr[Hf + n0 + 1] * w1.z;
+                        const float d0 = n0 ? fr[N - n0] * w0.w : 0.f, d1 = fr[N - n0 - 1] * w1.w;
+                        const float s0 = a0 + d0, r0 = b0 + c0, s1 = a1 + d1, r1 = b1 + c1;
+                        const float sd0 = a0 - d0, rd0 = b0 - c0, sd1 = a1 - d1, rd1 = b1 - c1;
+                        float u0, u1, v0, v1;
+                        if (pass == 0) {
+                            u0 = s0 + r0; u1 = s1 + r1;            // ee
+                            v0 = sd0 - rd0; v1 = sd1 - rd1;        // oe
+                            nyq[i] += u0 - u1;                     // (-1)^n ee[n], n0 even
+                        } else {
+                            u0 = s0 - r0; u1 = s1 - r1;            // eo
+                            v0 = sd0 + rd0; v1 = sd1 + rd1;        // oo
+                        }
+                        const float sc = rscale[i];
+                        uint8_t* dst = sa + row * (BK * 2) +
+                                       ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
+                        split_store(dst, dst + SUB_TILE, u0 * sc, u1 * sc);
+                        split_store(dst + 2 * SUB_TILE, dst + 3 * SUB_TILE, v0 * sc, v1 * sc);
+                    }
+                    if (pass == 0 && kc == n_kc - 1) {
+                        // Nyquist sums must be visible before the epilogue can be released
+#pragma unroll
+                        for (int i = 0; i < RI; ++i) {
+                            float v = nyq[i];
+                            v += __shfl_xor_sync(0xffffffffu, v, 8);
+                            v += __shfl_xor_sync(0xffffffffu, v, 4);
+                            v += __shfl_xor_sync(0xffffffffu, v, 2);
+                            v += __shfl_xor_sync(0xffffffffu, v, 1);
+                            const int row = bw * F2_ROWS_PER_WARP + 2 * i + half;
+                            if (pr == 0 && row < rows_eff) rowinfo[row].y = v;
+                        }
+                    }
+                    fence_proxy_async();                           // generic -> async proxy
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&full_bar[s]);
+                        if (pass == 0 && kc == n_kc - 1) mbar_arrive(&ri_full[slot]);
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
 // =====================================================================================
 // Folded inverse: STFT.backward (brever/modules/stft.py:101-138) = per-frame real
 // inverse DFT, window, overlap-add, / overlap-added w^2, centre trim — one persistent
@@ -473,18 +867,6 @@ __device__ __forceinline__ float rot(float v, int lane, int s) {
 __device__ __forceinline__ uint32_t absbits_max(uint32_t m, float2 v) {
     return max(m, max(__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu));
 }
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() {
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int N_PENDING>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
-}
-
 // HQ = hop / Q (1, 2 or 4); FRAMES_FAST: lanes run along frames when loading the
 // spectrogram (bin-major or arbitrary strides), else along bins (frame-major input);
 // DECOMP: |X|^(1/c - 1) decompression in the loaders (keeps powf out of the common path).
@@ -541,12 +923,12 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
             int g = 0;
             int n = 0;
             for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
-                if (n > 0) mbar_wait(&region_free, (uint32_t)((n - 1) & 1));
+                if (n > 0) mbar_wait_relaxed(&region_free, (uint32_t)((n - 1) & 1));
                 for (int it = 0; it < n_it; ++it, ++g) {
                     const int s = g % STAGES;
                     const uint32_t ph = (g / STAGES) & 1;
                     const int kc = it >> 1, pair = it & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
                     uint8_t* sb = stages + (size_t)s * STAGE_BYTES + STAGE_A;
 #pragma unroll
@@ -568,7 +950,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                     const int s = g % STAGES;
                     const uint32_t ph = (g / STAGES) & 1;
                     const int kc = it >> 1, pair = it & 1;
-                    mbar_wait(&full_bar[s], ph);
+                    mbar_wait_relaxed(&full_bar[s], ph, 32);
                     tcgen05_fence_after();
                     const uint32_t a0 = smem_u32(stages + (size_t)s * STAGE_BYTES);
                     const uint32_t b0 = a0 + STAGE_A;
@@ -599,7 +981,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
         int n = 0;
         for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
             const int slot = n & 1;
-            mbar_wait(&scale_empty[slot], (uint32_t)(((n >> 1) & 1) ^ 1));
+            mbar_wait_relaxed(&scale_empty[slot], (uint32_t)(((n >> 1) & 1) ^ 1));
             float4* ri = rowinfo2 + slot * TILE_M;
             const int64_t sig = tile_id / p.tiles_per_signal;
             const int64_t t0 = (int64_t)(tile_id % p.tiles_per_signal) * p.adv;
@@ -1122,6 +1504,8 @@ void free_fold(FoldPlan* fp) {
 
 }  // namespace
 
+int g_brv_fold_variant = 0;   // 0: by tile count, 2: one tile per CTA, 3: persistent two-pass (brv_set_tc_variant)
+
 bool brv_fold_supported(const brv_stft_plan* p) { return p->fold != nullptr; }
 
 int brv_fold_plan_init(brv_stft_plan* p) {
@@ -1160,6 +1544,16 @@ int brv_fold_plan_init(brv_stft_plan* p) {
         cudaFuncSetAttribute(stft_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SMEM_BYTES) != cudaSuccess)
         rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(stft_fold_kernel)");
+    if (rc == BRV_OK &&
+        (cudaFuncSetAttribute(stft_fold2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              F2_SMEM_BYTES) != cudaSuccess ||
+         cudaFuncSetAttribute(stft_fold2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              F2_SMEM_BYTES) != cudaSuccess))
+        rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(stft_fold2_kernel)");
+    if (rc == BRV_OK &&
+        cudaDeviceGetAttribute(&fp->sm_count, cudaDevAttrMultiProcessorCount, p->device) !=
+            cudaSuccess)
+        rc = brv_fail_cuda(cudaGetLastError(), "cudaDeviceGetAttribute(SM count)");
     // inverse: trigonometric basis with the Hermitian weights (c_0 = 1, else 2); the
     // window, sqrt(sum w^2) and 1/N live in the permuted window table
     if (rc == BRV_OK)
@@ -1261,8 +1655,25 @@ int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig,
     prm.post_expo = (float)(p->compression - 1.0);
     const int64_t grid = n_sig * prm.tiles_per_signal;
     BRV_REQUIRE(grid < (1LL << 31), "too many tiles (%lld)", (long long)grid);
-    stft_fold_kernel<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(fp->fwd.map, prm);
-    BRV_LAUNCH_CHECK("stft_fold_kernel");
+    prm.total_tiles = grid;
+    // Both kernels are bound by shared-memory bandwidth per tile (operand build + MMA operand
+    // reads + epilogue transpose).  The persistent two-pass kernel overlaps the phases of
+    // consecutive tiles and wins once every SM has a few tiles to pipeline (cfg5: 760 -> 620 us);
+    // with one or two tiles per SM its fill / drain latency loses to one CTA per tile
+    // (cfg2: 46 vs 60 us).  Variant 2 / 3 force one or the other for A/B runs.
+    const bool one_per_cta = g_brv_fold_variant == 2 ||
+                             (g_brv_fold_variant != 3 && grid < 3LL * fp->sm_count);
+    if (one_per_cta) {
+        stft_fold_kernel<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(fp->fwd.map, prm);
+        BRV_LAUNCH_CHECK("stft_fold_kernel");
+        return BRV_OK;
+    }
+    const unsigned ctas = (unsigned)(grid < fp->sm_count ? grid : fp->sm_count);
+    if (p->compression != 1.0)
+        stft_fold2_kernel<true><<<ctas, F2_THREADS, F2_SMEM_BYTES, st>>>(fp->fwd.map, prm);
+    else
+        stft_fold2_kernel<false><<<ctas, F2_THREADS, F2_SMEM_BYTES, st>>>(fp->fwd.map, prm);
+    BRV_LAUNCH_CHECK("stft_fold2_kernel");
     return BRV_OK;
 }
 

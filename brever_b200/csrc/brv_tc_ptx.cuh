@@ -42,6 +42,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+// Wait used by the roles that are NOT on the critical path of the CUDA cores (TMA producer,
+// MMA issuer, epilogue / scout warps waiting for work): backs off with nanosleep so the
+// polling does not take issue slots from the warps that do the arithmetic.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 64) {
+    const uint32_t addr = smem_u32(bar);
+    long long start = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(ns);
+        if ((spins & 1023) == 1023) {                        // never hang the device
+            if (start == 0) start = clock64();
+            else if (clock64() - start > 4000000000LL) __trap();
+        }
+    }
+}
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

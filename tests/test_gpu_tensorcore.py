@@ -26,6 +26,20 @@ class generic_path:
         _lib.lib().brv_set_force_generic(self.prev)
 
 
+class tc_variant:
+    """0: default kernels, 1: dense contraction only, 2 / 3: folded forward forced to one tile
+    per CTA / to the persistent two-pass kernel."""
+
+    def __init__(self, variant):
+        self.variant = variant
+
+    def __enter__(self):
+        self.prev = _lib.lib().brv_set_tc_variant(self.variant)
+
+    def __exit__(self, *a):
+        _lib.lib().brv_set_tc_variant(self.prev)
+
+
 CASES = [
     dict(frame_length=512, hop_length=128),
     dict(frame_length=512, hop_length=256),
@@ -61,6 +75,35 @@ def test_tensorcore_forward_matches_generic_and_oracle(kw, samples, capsys):
         assert e_gen[0] < 1e-4, (kw, i, e_gen)
     with capsys.disabled():
         print(f'\n[tc-accuracy] {kw} S={samples}: max-rel {worst:.2e}')
+
+
+@pytest.mark.parametrize('kw', [dict(frame_length=512, hop_length=128),
+                                dict(frame_length=512, hop_length=256),
+                                dict(frame_length=256, hop_length=128, normalized=False),
+                                dict(frame_length=128, hop_length=32),
+                                dict(frame_length=384, hop_length=96, compression_factor=0.5,
+                                     scale_factor=0.15)])
+@pytest.mark.parametrize('shape', [(1, 100), (3, 4097), (400, 20000), (37, 64000)])
+def test_pipelined_forward_matches_single_tile_kernel_and_oracle(kw, shape):
+    """The persistent two-pass forward (several tiles per CTA, TMEM halves handed back
+    and forth) against the one-tile-per-CTA kernel and the float64 oracle."""
+    x = randn(shape, 5)
+    x[::3] *= 1e-3
+    x[1::3] *= 200.0
+    stft = brv.STFT(**kw)
+    with tc_variant(3):
+        new = stft(x.to(DEV))
+        again = stft(x.to(DEV))
+    with tc_variant(2):
+        old = stft(x.to(DEV))
+    assert new.shape == old.shape and new.stride() == old.stride()
+    assert torch.equal(new, again)                     # deterministic
+    for i in range(0, shape[0], max(1, shape[0] // 7)):
+        e = rel_err(cpu(new[i]), cpu(old[i]))
+        assert e[0] < 2e-6, (kw, shape, i, e)
+        ref = O.stft(x[i].numpy(), **kw)
+        e = rel_err(cpu(new[i]), ref)
+        assert e[0] < 1e-4 and e[1] < 1e-4, (kw, shape, i, e)
 
 
 def test_tensorcore_is_actually_used():
