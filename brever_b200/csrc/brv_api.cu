@@ -21,6 +21,9 @@ bool brv_fold_inverse_supported(const brv_stft_plan* p);
 int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t sb, int64_t sf,
                    int64_t n_sig, int64_t n_frames, int64_t out_len, float* y, cudaStream_t st);
 
+int brv_fold_istft_grad(const brv_stft_plan* p, const float* gy, int64_t n_sig, int64_t n_frames,
+                        int64_t out_len, float2* gX, cudaStream_t st);
+
 static int g_force_generic = -1;
 extern int g_brv_fold_variant;
 // 0: folded kernels where supported (forward kernel picked by tile count), 1: dense contraction
@@ -135,6 +138,15 @@ extern "C" int brv_istft_forward_grad(const brv_stft_plan* p, const float* gy, i
         return brv_fail(BRV_ERR_UNSUPPORTED,
                         "gradient of the decompressing iSTFT (compression_factor != 1) is not "
                         "implemented: the reference only runs it under no_grad");
+    if (n_signals == 0) return BRV_OK;
+    if (!force_generic() && tc_variant() != 1 && brv_fold_supported(p) && p->n_bins == p->n_bins_inv) {
+        int64_t out_len = 0;
+        int rc = brv_istft_geometry(p, n_frames, &out_len);
+        if (rc != BRV_OK) return rc;
+        if (out_len > 0)
+            return brv_fold_istft_grad(p, gy, n_signals, n_frames, out_len, (float2*)gX,
+                                       (cudaStream_t)stream);
+    }
     BRV_REQUIRE(workspace && workspace_bytes >= brv_stft_workspace_bytes(p, n_signals, n_frames),
                 "workspace too small");
     return brv_simt_istft_grad(p, gy, n_signals, n_frames, (float2*)gX, (float*)workspace,

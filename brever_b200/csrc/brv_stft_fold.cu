@@ -82,8 +82,25 @@ struct FoldFwdParams {
     float wmax;                  // max |w| / norm
     float basis_scale_inv;
     float post_scale, post_expo;
+    // gradient of the inverse transform (brv_fold_istft_grad): the input is multiplied by
+    // in_mul[sample] (1 / overlap-added w^2) while it is staged, and the DC and Nyquist bins,
+    // which carry Hermitian weight 1 instead of 2, are multiplied by edge_scale = 1/2
+    const float* in_mul;
+    float edge_scale;
 };
 
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) {
+    return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+// table[idx .. idx+3] with 1 outside [0, n) (positions there hold zero-padding anyway)
+__device__ __forceinline__ float4 load4_clamped(const float* table, int64_t idx, int64_t n) {
+    float4 v = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (idx >= 0 && idx < n) v.x = __ldg(table + idx);
+    if (idx + 1 >= 0 && idx + 1 < n) v.y = __ldg(table + idx + 1);
+    if (idx + 2 >= 0 && idx + 2 < n) v.z = __ldg(table + idx + 2);
+    if (idx + 3 >= 0 && idx + 3 < n) v.w = __ldg(table + idx + 3);
+    return v;
+}
 __device__ __forceinline__ void split_store(uint8_t* hi_ptr, uint8_t* lo_ptr, float v0, float v1) {
     const __half2 h = __floats2half2_rn(v0, v1);
     const float2 hf = __half22float2(h);
@@ -205,11 +222,14 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
                 if (i < span_pad) {
                     if (vec && idx >= 0 && idx + 4 <= p.samples) {
                         f[u] = __ldg(reinterpret_cast<const float4*>(xs + idx));
+                        if (p.in_mul)
+                            f[u] = mul4(f[u], __ldg(reinterpret_cast<const float4*>(p.in_mul + idx)));
                     } else {
                         if (idx >= 0 && idx < p.samples) f[u].x = __ldg(xs + idx);
                         if (idx + 1 >= 0 && idx + 1 < p.samples) f[u].y = __ldg(xs + idx + 1);
                         if (idx + 2 >= 0 && idx + 2 < p.samples) f[u].z = __ldg(xs + idx + 2);
                         if (idx + 3 >= 0 && idx + 3 < p.samples) f[u].w = __ldg(xs + idx + 3);
+                        if (p.in_mul) f[u] = mul4(f[u], load4_clamped(p.in_mul, idx, p.samples));
                     }
                 }
             }
@@ -336,6 +356,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
             for (int j = 0; j < 16; ++j) {
                 const float sg = (j & 1) ? -1.f : 1.f;        // m0 is even
                 float re_e = __uint_as_float(r0[j]) * g0 + sg * eeq;
+                if (j == 0 && m0 == 0) re_e *= p.edge_scale;       // DC bin (its Im is exactly 0)
                 float re_o = __uint_as_float(r1[j]) * g0;
                 float im_e = __uint_as_float(r2[j]) * g0;
                 float im_o = __uint_as_float(r3[j]) * g0 - sg * ooq;
@@ -357,7 +378,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
             __syncwarp();
         }
         if (hsel == 1 && live) {                   // Nyquist bin: purely real
-            float v = ny;
+            float v = ny * p.edge_scale;
             if (p.post_expo != 0.f) v = compress_real(v, p.post_expo);
             *reinterpret_cast<float2*>(obase + (int64_t)lane * pitch + 2 * Hf) =
                 make_float2(v * p.post_scale, 0.f);
@@ -566,6 +587,7 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
                     for (int j = 0; j < 16; ++j) {
                         float re = fmaf(__uint_as_float(r0[j]), g0, (j & 1) ? -rq : rq);   // m0 is even
                         float im = fmaf(__uint_as_float(r1[j]), g0, (j & 1) ? -iq : iq);
+                        if (j == 0 && c == 0 && pass == 0) re *= p.edge_scale;   // DC bin
                         if (COMPRESS) {
                             compress(re, im, p.post_expo);
                             re *= p.post_scale;
@@ -587,7 +609,7 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
                     __syncwarp();
                 }
                 if (pass == 0 && live) {                   // Nyquist bin: purely real
-                    float v = ri.y + ri.z;                 // Q is even: (-1)^Q = +1
+                    float v = (ri.y + ri.z) * p.edge_scale;   // Q is even: (-1)^Q = +1
                     if (COMPRESS) v = compress_real(v, p.post_expo);
                     *reinterpret_cast<float2*>(obase + (int64_t)lane * pitch + 2 * Hf) =
                         make_float2(v * p.post_scale, 0.f);
@@ -659,7 +681,17 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
             for (int i0 = bw * 128; i0 < span_pad; i0 += F2_BUILDER_THREADS * 4) {   // own copies only
                 const int i = i0 + lane * 4;
                 float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < span_pad) f = *reinterpret_cast<const float4*>(span + i);
+                if (i < span_pad) {
+                    f = *reinterpret_cast<const float4*>(span + i);
+                    if (p.in_mul) {
+                        const int64_t idx = span0 + i;
+                        if (vec && idx >= 0 && idx + 4 <= p.samples)
+                            f = mul4(f, __ldg(reinterpret_cast<const float4*>(p.in_mul + idx)));
+                        else
+                            f = mul4(f, load4_clamped(p.in_mul, idx, p.samples));
+                        *reinterpret_cast<float4*>(span + i) = f;
+                    }
+                }
                 // fmaxf drops NaNs; an inf is removed by the slow path
                 float m = fmaxf(fmaxf(fabsf(f.x), fabsf(f.y)), fmaxf(fabsf(f.z), fabsf(f.w)));
                 if (!(m <= 3.0e38f))
@@ -1423,6 +1455,8 @@ struct FoldPlan {
     FoldBasis fwd, inv;
     float4* wtab = nullptr;      // Q permuted, normalised window entries
     float4* wtab_inv = nullptr;  // the same permutation of w * sqrt(sum w^2) / N
+    float4* wtab_grad = nullptr; // forward-convention table of 2 w sqrt(sum w^2) / N (iSTFT gradient)
+    float wq_g = 0.f, w3q_g = 0.f, wmax_g = 0.f;
     float wq = 0.f, w3q = 0.f, wmax = 0.f;
     float wq_inv = 0.f, w3q_inv = 0.f;
     int q = 0, tmem_cols = 0;
@@ -1497,6 +1531,7 @@ void free_fold(FoldPlan* fp) {
     cudaFree(fp->inv.data);
     cudaFree(fp->wtab);
     cudaFree(fp->wtab_inv);
+    cudaFree(fp->wtab_grad);
     cudaFree(fp->env_per);
     for (auto& kv : fp->inv_env) cudaFree(kv.second);
     delete fp;
@@ -1539,6 +1574,27 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             cudaMemcpy(fp->wtab, wt.data(), Q * sizeof(float4), cudaMemcpyHostToDevice) !=
                 cudaSuccess)
             rc = brv_fail_cuda(cudaGetLastError(), "folded window table");
+    }
+    if (rc == BRV_OK) {
+        // gradient of the inverse transform = this forward kernel on gy / envelope with the
+        // inverse's window scaling and Hermitian weights (2, folded in here; DC / Nyquist get 1/2)
+        const double gs = 2.0 * p->norm / N;
+        std::vector<float4> wt(Q);
+        double wmax = 0;
+        for (int n = 0; n < N; ++n) wmax = fmax(wmax, fabs(p->window[n] * gs));
+        for (int n = 0; n < Q; ++n) {
+            wt[n].x = (float)(p->window[n] * gs);
+            wt[n].y = (float)(p->window[Hf - n] * gs);
+            wt[n].z = n ? (float)(p->window[Hf + n] * gs) : 0.f;
+            wt[n].w = n ? (float)(p->window[N - n] * gs) : 0.f;
+        }
+        fp->wq_g = (float)(p->window[Q] * gs);
+        fp->w3q_g = (float)(p->window[3 * Q] * gs);
+        fp->wmax_g = (float)wmax;
+        if (cudaMalloc((void**)&fp->wtab_grad, Q * sizeof(float4)) != cudaSuccess ||
+            cudaMemcpy(fp->wtab_grad, wt.data(), Q * sizeof(float4), cudaMemcpyHostToDevice) !=
+                cudaSuccess)
+            rc = brv_fail_cuda(cudaGetLastError(), "folded gradient window table");
     }
     if (rc == BRV_OK &&
         cudaFuncSetAttribute(stft_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1627,16 +1683,10 @@ void brv_fold_plan_free(brv_stft_plan* p) {
     p->fold = nullptr;
 }
 
-int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
-                          int64_t x_stride, float2* out, int64_t n_frames, cudaStream_t st) {
+static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool compress,
+                               int64_t n_sig, int64_t n_frames, cudaStream_t st) {
     const FoldPlan* fp = (const FoldPlan*)p->fold;
-    FoldFwdParams prm = {};
-    prm.x = x;
-    prm.x_stride = x_stride;
-    prm.samples = samples;
-    prm.out = reinterpret_cast<float*>(out);
     prm.n_frames = n_frames;
-    prm.wtab = fp->wtab;
     prm.n_fft = p->n_fft;
     prm.hop = p->hop;
     prm.n_bins = p->n_bins;
@@ -1647,12 +1697,7 @@ int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig,
     prm.rows = rows;
     prm.tiles_per_signal = (int)brv_ceil_div(n_frames, rows);
     prm.tmem_cols = fp->tmem_cols;
-    prm.wq = fp->wq;
-    prm.w3q = fp->w3q;
-    prm.wmax = fp->wmax;
     prm.basis_scale_inv = fp->fwd.scale_inv;
-    prm.post_scale = (float)p->scale;
-    prm.post_expo = (float)(p->compression - 1.0);
     const int64_t grid = n_sig * prm.tiles_per_signal;
     BRV_REQUIRE(grid < (1LL << 31), "too many tiles (%lld)", (long long)grid);
     prm.total_tiles = grid;
@@ -1669,7 +1714,7 @@ int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig,
         return BRV_OK;
     }
     const unsigned ctas = (unsigned)(grid < fp->sm_count ? grid : fp->sm_count);
-    if (p->compression != 1.0)
+    if (compress)
         stft_fold2_kernel<true><<<ctas, F2_THREADS, F2_SMEM_BYTES, st>>>(fp->fwd.map, prm);
     else
         stft_fold2_kernel<false><<<ctas, F2_THREADS, F2_SMEM_BYTES, st>>>(fp->fwd.map, prm);
@@ -1677,6 +1722,24 @@ int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig,
     return BRV_OK;
 }
 
+int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
+                          int64_t x_stride, float2* out, int64_t n_frames, cudaStream_t st) {
+    const FoldPlan* fp = (const FoldPlan*)p->fold;
+    FoldFwdParams prm = {};
+    prm.x = x;
+    prm.x_stride = x_stride;
+    prm.samples = samples;
+    prm.out = reinterpret_cast<float*>(out);
+    prm.wtab = fp->wtab;
+    prm.wq = fp->wq;
+    prm.w3q = fp->w3q;
+    prm.wmax = fp->wmax;
+    prm.post_scale = (float)p->scale;
+    prm.post_expo = (float)(p->compression - 1.0);
+    prm.in_mul = nullptr;
+    prm.edge_scale = 1.f;
+    return fold_forward_launch(p, prm, p->compression != 1.0, n_sig, n_frames, st);
+}
 
 bool brv_fold_inverse_supported(const brv_stft_plan* p) {
     return p->fold != nullptr && ((const FoldPlan*)p->fold)->hq != 0;
@@ -1775,4 +1838,26 @@ int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t 
 #undef BRV_LAUNCH_INV
     BRV_LAUNCH_CHECK("istft_fold_kernel");
     return BRV_OK;
+}
+
+// Gradient of STFT.backward w.r.t. its spectrogram input (SURVEY 8a'): the forward kernel
+// on gy / envelope, window * sqrt(sum w^2) / N, Hermitian weights (1, 2, ..., 2, 1), 1 / scale.
+int brv_fold_istft_grad(const brv_stft_plan* p, const float* gy, int64_t n_sig, int64_t n_frames,
+                        int64_t out_len, float2* gX, cudaStream_t st) {
+    const FoldPlan* fp = (const FoldPlan*)p->fold;
+    FoldFwdParams prm = {};
+    int rc = fold_inv_envelope(p, n_frames, out_len, &prm.in_mul);
+    if (rc != BRV_OK) return rc;
+    prm.x = gy;
+    prm.x_stride = out_len;
+    prm.samples = out_len;
+    prm.out = reinterpret_cast<float*>(gX);
+    prm.wtab = fp->wtab_grad;
+    prm.wq = fp->wq_g;
+    prm.w3q = fp->w3q_g;
+    prm.wmax = fp->wmax_g;
+    prm.post_scale = (float)(1.0 / p->scale);
+    prm.post_expo = 0.f;
+    prm.edge_scale = 0.5f;
+    return fold_forward_launch(p, prm, false, n_sig, n_frames, st);
 }

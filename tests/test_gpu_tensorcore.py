@@ -8,7 +8,7 @@ import brever_b200 as brv
 from brever_b200 import _lib
 from oracle import tf_oracle as O
 
-from _util import assert_parity, golden, randn, rel_err, synthetic_mixture
+from _util import assert_parity, crandn, golden, randn, rel_err, synthetic_mixture
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -104,6 +104,47 @@ def test_pipelined_forward_matches_single_tile_kernel_and_oracle(kw, shape):
         ref = O.stft(x[i].numpy(), **kw)
         e = rel_err(cpu(new[i]), ref)
         assert e[0] < 1e-4 and e[1] < 1e-4, (kw, shape, i, e)
+
+
+@pytest.mark.parametrize('kw', [dict(frame_length=512, hop_length=128),
+                                dict(frame_length=512, hop_length=256, scale_factor=0.3),
+                                dict(frame_length=256, hop_length=128, normalized=False),
+                                dict(frame_length=400, hop_length=128, n_fft=512)])
+@pytest.mark.parametrize('shape', [(2, 3), (3, 130), (160, 157), (64, 501)])
+@pytest.mark.parametrize('variant', [2, 3])
+def test_tensorcore_istft_gradient(kw, shape, variant):
+    """d STFT.backward / dX on the folded tcgen05 forward kernel (gy / envelope staged as the
+    signal, Hermitian bin weights) against the generic float64-accumulating path and, on a
+    few signals, torch autograd through the reference's own library calls."""
+    from oracle import torch_port as P
+    n_sig, frames = shape
+    stft = brv.STFT(**kw)
+    spec = crandn((n_sig, stft.n_bins, frames), 31)
+    v = randn((n_sig, stft.hop_length * (frames - 1)), 32)
+    v[::2] *= 1e-3
+    lib = _lib.lib()
+
+    def grad():
+        sg = spec.clone().to(DEV).requires_grad_(True)
+        n0 = lib.brv_launch_count()
+        (stft.backward(sg) * v.to(DEV)).sum().backward()
+        return sg.grad, lib.brv_launch_count() - n0
+
+    with tc_variant(variant):
+        g_tc, launches = grad()
+    assert launches == 2                      # one inverse kernel + one gradient kernel
+    with generic_path():
+        g_gen, _ = grad()
+    assert g_tc.shape == g_gen.shape == spec.shape
+    for i in range(0, n_sig, max(1, n_sig // 5)):
+        e = rel_err(cpu(g_tc[i]), cpu(g_gen[i]))
+        assert e[0] < 2e-5 and e[1] < 2e-5, (kw, shape, i, e)
+    assert float(g_tc[:, 0].imag.abs().max()) == 0       # DC / Nyquist carry no imaginary gradient
+    assert float(g_tc[:, -1].imag.abs().max()) == 0
+    win = torch.from_numpy(O.get_window('hann', kw['frame_length']))
+    sr = spec[:2].clone().requires_grad_(True)
+    (P.istft(sr, win, **kw) * v[:2]).sum().backward()
+    assert_parity(cpu(g_tc[:2]), sr.grad.numpy(), 1e-4, 'd istft / dX')
 
 
 def test_tensorcore_is_actually_used():
