@@ -24,6 +24,10 @@ int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t 
 int brv_fold_istft_grad(const brv_stft_plan* p, const float* gy, int64_t n_sig, int64_t n_frames,
                         int64_t out_len, float2* gX, cudaStream_t st);
 
+int brv_fold_stft_grad(const brv_stft_plan* p, const float2* gX, int64_t ss, int64_t sb, int64_t sf,
+                       int64_t n_sig, int64_t n_frames, int64_t samples, float* gx,
+                       cudaStream_t st);
+
 static int g_force_generic = -1;
 extern int g_brv_fold_variant;
 // 0: folded kernels where supported (forward kernel picked by tile count), 1: dense contraction
@@ -94,6 +98,11 @@ extern "C" int brv_stft_forward_grad(const brv_stft_plan* p, const void* gX, int
     int64_t n_frames = 0;
     int rc = brv_stft_geometry(p, samples, &n_frames, nullptr, nullptr);
     if (rc != BRV_OK) return rc;
+    if (n_signals == 0 || samples == 0) return BRV_OK;
+    if (!force_generic() && tc_variant() != 1 && brv_fold_inverse_supported(p) &&
+        p->n_bins == p->n_bins_inv)
+        return brv_fold_stft_grad(p, (const float2*)gX, ss, sb, sf, n_signals, n_frames, samples,
+                                  gx, (cudaStream_t)stream);
     BRV_REQUIRE(workspace && workspace_bytes >= brv_stft_workspace_bytes(p, n_signals, n_frames),
                 "workspace too small");
     return brv_simt_spec_to_signal(p, (const float2*)gX, ss, sb, sf, n_signals, n_frames, samples,

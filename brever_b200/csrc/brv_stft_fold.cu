@@ -869,6 +869,9 @@ struct FoldInvParams {
     int tmem_cols;
     float wq, w3q;               // w[Q] * norm / N, w[3Q] * norm / N
     float basis_scale_inv;
+    // gradient of the forward transform (brv_fold_stft_grad): no envelope (inv_env == nullptr),
+    // all bins weigh 1: the window table carries 1/2 and the DC / Nyquist inputs edge_gain = 2
+    float edge_gain;
 };
 
 template <bool DECOMP>
@@ -1068,7 +1071,8 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                 }
                 float ny = 0.f;
                 if (live)
-                    ny = prep_bin<DECOMP>(__ldg(col + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x;
+                    ny = prep_bin<DECOMP>(__ldg(col + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x *
+                         p.edge_gain;
                 ri[st] = make_float4(row_scale(m), 0.f, 0.f, ny);
             } else {
                 // chunk = 8 frames; warp sw owns rows sw and sw + 4 of every chunk (bins contiguous),
@@ -1126,7 +1130,8 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                                     m = __uint_as_float(mb) * fabsf(p.pre_scale);
                                 }
                                 if (lane == 0)
-                                    ny = prep_bin<DECOMP>(src[r * RING_ROW + Hf], p.pre_scale, p.pre_expo).x;
+                                    ny = prep_bin<DECOMP>(src[r * RING_ROW + Hf], p.pre_scale, p.pre_expo).x *
+                                         p.edge_gain;
                             }
 #pragma unroll
                             for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -1151,7 +1156,8 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
         constexpr int R = 4 / HQ;                  // frames overlapping one hop block
         float env_reg[8];                          // 1 / envelope of interior hop blocks
 #pragma unroll
-        for (int j = 0; j < 8; ++j) env_reg[j] = lane + 32 * j < H ? __ldg(p.env_per + lane + 32 * j) : 0.f;
+        for (int j = 0; j < 8; ++j)
+            env_reg[j] = !p.inv_env ? 1.f : (lane + 32 * j < H ? __ldg(p.env_per + lane + 32 * j) : 0.f);
 
         int g = 0, n = 0;
         for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
@@ -1180,7 +1186,10 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                         for (int e = 0; e < 32; ++e) c[e] = __ldg(xr + (int64_t)(bin0 + e) * p.sb);
 #pragma unroll
                         for (int e = 0; e < 32; ++e) c[e] = prep_bin<DECOMP>(c[e], p.pre_scale, p.pre_expo);
-                        if (bin0 == 0) c[0].y = 0.f;   // Im X[0] is ignored by the c2r inverse
+                        if (bin0 == 0) {
+                            c[0].y = 0.f;              // Im X[0] is ignored by the c2r inverse
+                            c[0].x *= p.edge_gain;
+                        }
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
                             pacc += c[2 * j].x - c[2 * j + 2].x;          // (-1)^m Re X[2m]
@@ -1260,7 +1269,10 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             c[i][e] = prep_bin<DECOMP>(c[i][e], p.pre_scale, p.pre_expo);
-                        if (m0 == 0) c[i][0].y = 0.f;  // Im X[0] is ignored by the c2r inverse
+                        if (m0 == 0) {
+                            c[i][0].y = 0.f;           // Im X[0] is ignored by the c2r inverse
+                            c[i][0].x *= p.edge_gain;
+                        }
                         pacc[i] += c[i][0].x - c[i][2].x;
                         racc[i] += c[i][1].y - c[i][3].y;
                         if (m0 == 0) pacc[i] -= 0.5f * c[i][0].x;
@@ -1425,7 +1437,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                         if (off < H && i >= 0 && i < p.out_len) {
                             float v = src[off];
                             if (sp) v += sp[off];
-                            ys[i] = v * (interior ? env_reg[j] : __ldg(p.inv_env + i));
+                            ys[i] = v * ((interior || !p.inv_env) ? env_reg[j] : __ldg(p.inv_env + i));
                         }
                     }
                 }
@@ -1457,6 +1469,8 @@ struct FoldPlan {
     float4* wtab_inv = nullptr;  // the same permutation of w * sqrt(sum w^2) / N
     float4* wtab_grad = nullptr; // forward-convention table of 2 w sqrt(sum w^2) / N (iSTFT gradient)
     float wq_g = 0.f, w3q_g = 0.f, wmax_g = 0.f;
+    float4* wtab_fgrad = nullptr;   // inverse-convention table of w / (2 sqrt(sum w^2)) (STFT gradient)
+    float wq_fg = 0.f, w3q_fg = 0.f;
     float wq = 0.f, w3q = 0.f, wmax = 0.f;
     float wq_inv = 0.f, w3q_inv = 0.f;
     int q = 0, tmem_cols = 0;
@@ -1532,6 +1546,7 @@ void free_fold(FoldPlan* fp) {
     cudaFree(fp->wtab);
     cudaFree(fp->wtab_inv);
     cudaFree(fp->wtab_grad);
+    cudaFree(fp->wtab_fgrad);
     cudaFree(fp->env_per);
     for (auto& kv : fp->inv_env) cudaFree(kv.second);
     delete fp;
@@ -1631,6 +1646,21 @@ int brv_fold_plan_init(brv_stft_plan* p) {
         }
         fp->wq_inv = (float)(p->window[Q] * gw);
         fp->w3q_inv = (float)(p->window[3 * Q] * gw);
+        // gradient of the forward transform: window / norm, and 1/2 against the basis' weight 2
+        const double fg = 0.5 / p->norm;
+        std::vector<float4> wf(Q);
+        for (int n = 0; n < Q; ++n) {
+            wf[n].x = (float)(p->window[n] * fg);
+            wf[n].y = (float)(p->window[Hf - n] * fg);
+            wf[n].z = (float)(p->window[Hf + n] * fg);
+            wf[n].w = n ? (float)(p->window[N - n] * fg) : 0.f;
+        }
+        fp->wq_fg = (float)(p->window[Q] * fg);
+        fp->w3q_fg = (float)(p->window[3 * Q] * fg);
+        if (cudaMalloc((void**)&fp->wtab_fgrad, Q * sizeof(float4)) != cudaSuccess ||
+            cudaMemcpy(fp->wtab_fgrad, wf.data(), Q * sizeof(float4), cudaMemcpyHostToDevice) !=
+                cudaSuccess)
+            rc = brv_fail_cuda(cudaGetLastError(), "folded forward-gradient window table");
         if (cudaMalloc((void**)&fp->wtab_inv, Q * sizeof(float4)) != cudaSuccess ||
             cudaMemcpy(fp->wtab_inv, wt.data(), Q * sizeof(float4), cudaMemcpyHostToDevice) !=
                 cudaSuccess)
@@ -1787,21 +1817,10 @@ static int fold_inv_envelope(const brv_stft_plan* p, int64_t n_frames, int64_t o
     return BRV_OK;
 }
 
-int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t sb, int64_t sf,
-                   int64_t n_sig, int64_t n_frames, int64_t out_len, float* y, cudaStream_t st) {
+static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool decomp,
+                               int64_t n_sig, int64_t n_frames, int64_t out_len, cudaStream_t st) {
     const FoldPlan* fp = (const FoldPlan*)p->fold;
-    FoldInvParams prm = {};
-    int rc = fold_inv_envelope(p, n_frames, out_len, &prm.inv_env);
-    if (rc != BRV_OK) return rc;
-    prm.spec = X;
-    prm.ss = ss;
-    prm.sb = sb;
-    prm.sf = sf;
-    prm.pre_scale = (float)(1.0 / p->scale);
-    prm.pre_expo = (float)(1.0 / p->compression - 1.0);
-    prm.y = y;
     prm.out_len = out_len;
-    prm.wtab = fp->wtab_inv;
     prm.n_frames = n_frames;
     prm.n_fft = p->n_fft;
     prm.hop = p->hop;
@@ -1812,14 +1831,11 @@ int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t 
     prm.tiles_per_signal =
         prm.n_blocks <= TILE_M ? 1 : 1 + (int)brv_ceil_div(prm.n_blocks - TILE_M, prm.adv);
     prm.tmem_cols = fp->tmem_cols;
-    prm.wq = fp->wq_inv;
-    prm.w3q = fp->w3q_inv;
     prm.basis_scale_inv = fp->inv.scale_inv;
     prm.env_per = fp->env_per;
     prm.total_tiles = n_sig * prm.tiles_per_signal;
     const unsigned grid = (unsigned)(prm.total_tiles < fp->sm_count ? prm.total_tiles : fp->sm_count);
-    const bool frames_fast = sb != 1;
-    const bool decomp = p->compression != 1.0;
+    const bool frames_fast = prm.sb != 1;
 #define BRV_LAUNCH_INV(HQ_, FF_)                                                                  \
     do {                                                                                          \
         if (decomp)                                                                               \
@@ -1838,6 +1854,49 @@ int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t 
 #undef BRV_LAUNCH_INV
     BRV_LAUNCH_CHECK("istft_fold_kernel");
     return BRV_OK;
+}
+
+int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t sb, int64_t sf,
+                   int64_t n_sig, int64_t n_frames, int64_t out_len, float* y, cudaStream_t st) {
+    const FoldPlan* fp = (const FoldPlan*)p->fold;
+    FoldInvParams prm = {};
+    int rc = fold_inv_envelope(p, n_frames, out_len, &prm.inv_env);
+    if (rc != BRV_OK) return rc;
+    prm.spec = X;
+    prm.ss = ss;
+    prm.sb = sb;
+    prm.sf = sf;
+    prm.pre_scale = (float)(1.0 / p->scale);
+    prm.pre_expo = (float)(1.0 / p->compression - 1.0);
+    prm.y = y;
+    prm.wtab = fp->wtab_inv;
+    prm.wq = fp->wq_inv;
+    prm.w3q = fp->w3q_inv;
+    prm.edge_gain = 1.f;
+    return fold_inverse_launch(p, prm, p->compression != 1.0, n_sig, n_frames, out_len, st);
+}
+
+// Gradient of STFT.forward w.r.t. the waveform (SURVEY 8a', compression_factor == 1): the
+// inverse kernel with every bin weighing 1, window * scale / sqrt(sum w^2), no envelope, and
+// the overlap-added frames cut to the `samples` the forward transform was given.
+int brv_fold_stft_grad(const brv_stft_plan* p, const float2* gX, int64_t ss, int64_t sb, int64_t sf,
+                       int64_t n_sig, int64_t n_frames, int64_t samples, float* gx,
+                       cudaStream_t st) {
+    const FoldPlan* fp = (const FoldPlan*)p->fold;
+    FoldInvParams prm = {};
+    prm.inv_env = nullptr;
+    prm.spec = gX;
+    prm.ss = ss;
+    prm.sb = sb;
+    prm.sf = sf;
+    prm.pre_scale = (float)p->scale;
+    prm.pre_expo = 0.f;
+    prm.y = gx;
+    prm.wtab = fp->wtab_fgrad;
+    prm.wq = fp->wq_fg;
+    prm.w3q = fp->w3q_fg;
+    prm.edge_gain = 2.f;
+    return fold_inverse_launch(p, prm, false, n_sig, n_frames, samples, st);
 }
 
 // Gradient of STFT.backward w.r.t. its spectrogram input (SURVEY 8a'): the forward kernel

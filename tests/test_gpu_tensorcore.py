@@ -147,6 +147,43 @@ def test_tensorcore_istft_gradient(kw, shape, variant):
     assert_parity(cpu(g_tc[:2]), sr.grad.numpy(), 1e-4, 'd istft / dX')
 
 
+@pytest.mark.parametrize('kw', [dict(frame_length=512, hop_length=128),
+                                dict(frame_length=512, hop_length=256, scale_factor=0.3),
+                                dict(frame_length=256, hop_length=128, normalized=False),
+                                dict(frame_length=400, hop_length=128, n_fft=512)])
+@pytest.mark.parametrize('shape', [(2, 100), (3, 4097), (160, 20000), (64, 64000)])
+def test_tensorcore_stft_gradient(kw, shape):
+    """d STFT.forward / dx on the folded tcgen05 inverse kernel (all bins weigh 1, no
+    envelope, cut to the input length) against the generic path and reference autograd."""
+    from oracle import torch_port as P
+    n_sig, samples = shape
+    stft = brv.STFT(**kw)
+    frames = stft.n_frames(samples)
+    x = randn(shape, 41)
+    wt = crandn((n_sig, stft.n_bins, frames), 42)
+    wt[::2] *= 1e-2
+    lib = _lib.lib()
+
+    def grad():
+        xg = x.clone().to(DEV).requires_grad_(True)
+        n0 = lib.brv_launch_count()
+        (stft(xg) * wt.to(DEV).conj()).real.sum().backward()
+        return xg.grad, lib.brv_launch_count() - n0
+
+    g_tc, launches = grad()
+    assert launches == 2                      # one forward kernel + one gradient kernel
+    with generic_path():
+        g_gen, _ = grad()
+    assert g_tc.shape == g_gen.shape == x.shape
+    for i in range(0, n_sig, max(1, n_sig // 5)):
+        e = rel_err(cpu(g_tc[i]), cpu(g_gen[i]))
+        assert e[0] < 2e-5 and e[1] < 2e-5, (kw, shape, i, e)
+    win = torch.from_numpy(O.get_window('hann', kw['frame_length']))
+    xr = x[:2].clone().requires_grad_(True)
+    (P.stft(xr, win, **kw) * wt[:2].conj()).real.sum().backward()
+    assert_parity(cpu(g_tc[:2]), xr.grad.numpy(), 1e-4, 'd stft / dx')
+
+
 def test_tensorcore_is_actually_used():
     """The default path must launch the tcgen05 kernel (count launches)."""
     lib = _lib.lib()
