@@ -9,11 +9,12 @@ backed by hand-written CUDA kernels behind a C ABI (include/brever_b200.h).
 CUDA tensors only; there is no CPU fallback.
 """
 from . import criterion, ffnn, modules
-from .criterion import CriterionRegistry, apply_mask, init_criterion, sisnr, snr
+from .criterion import (CriterionRegistry, MultiResYuLoss, apply_mask, init_criterion, mse,
+                        sisnr, snr)
 from .modules import STFT, FeatureExtractor, MelFilterbank
 from .registry import Registry
 
 __version__ = '0.1.0'
 __all__ = ['STFT', 'MelFilterbank', 'FeatureExtractor', 'CriterionRegistry',
-           'init_criterion', 'sisnr', 'snr', 'apply_mask', 'Registry',
+           'init_criterion', 'sisnr', 'snr', 'mse', 'MultiResYuLoss', 'apply_mask', 'Registry',
            'criterion', 'ffnn', 'modules']

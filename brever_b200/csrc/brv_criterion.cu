@@ -177,6 +177,146 @@ snr_moments_kernel(const float* __restrict__ x, const float* __restrict__ y,
     }
 }
 
+// ---- L1 reductions for MultiResYuLoss (criterion.py:135-226) and the plain masked MSE ----
+// One scalar per row: partial sums per chunk, fixed-order final sum by the last CTA of the row
+// (same ticket scheme as above, so results are deterministic).
+__device__ __forceinline__ void finish_row_sum(double v, int64_t row, int chunk, int chunks,
+                                               double* __restrict__ partial,
+                                               unsigned int* __restrict__ ticket, double post,
+                                               float* __restrict__ out) {
+    __shared__ double red1[CR_THREADS / 32];
+    __shared__ bool last1;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    v = warp_sum_d(v);
+    if (lane == 0) red1[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < CR_THREADS / 32; ++w) t += red1[w];
+        partial[row * chunks + chunk] = t;
+        __threadfence();
+        const unsigned int prev = atomicAdd(ticket + row, 1u);
+        last1 = (prev == (unsigned int)chunks - 1);
+    }
+    __syncthreads();
+    if (!last1 || threadIdx.x != 0) return;
+    __threadfence();
+    double t = 0;
+    for (int c = 0; c < chunks; ++c) t += __ldcg(partial + row * chunks + c);
+    ticket[row] = 0;
+    out[row] = (float)(t * post);
+}
+
+// out[row] = sum_{n < lengths[b]} | s[row] * x[n] - y[n] |      (time-domain term, :207-209)
+__global__ void __launch_bounds__(CR_THREADS)
+l1_rows_kernel(const float* __restrict__ x, const float* __restrict__ y,
+               const int64_t* __restrict__ lengths, const float* __restrict__ scale,
+               int64_t n_rows, int64_t length, int64_t xsb, int64_t xsr, int64_t ysb, int64_t ysr,
+               int chunks, float* __restrict__ out, double* __restrict__ partial,
+               unsigned int* __restrict__ ticket) {
+    const int64_t row = blockIdx.x;
+    const int chunk = blockIdx.y;
+    const int64_t b = row / n_rows, r = row % n_rows;
+    int64_t valid = lengths[b];
+    if (valid > length) valid = length;
+    if (valid < 0) valid = 0;
+    const float* xp = x + b * xsb + r * xsr;
+    const float* yp = y + b * ysb + r * ysr;
+    const float s = scale ? __ldg(scale + row) : 1.f;
+    const bool vx = (((uintptr_t)xp) & 15) == 0, vy = (((uintptr_t)yp) & 15) == 0;
+    double acc = 0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int64_t begin = ((int64_t)chunk * 2 + it) * CR_BLOCK;
+        if (begin >= valid) break;
+        float4 a[CR_UNROLL], c[CR_UNROLL];
+#pragma unroll
+        for (int u = 0; u < CR_UNROLL; ++u) {
+            const int64_t i = begin + 4 * (int64_t)(u * CR_THREADS + threadIdx.x);
+            a[u] = load4(xp, i, valid, vx);
+            c[u] = load4(yp, i, valid, vy);
+        }
+#pragma unroll
+        for (int u = 0; u < CR_UNROLL; ++u) {
+            const float t = (fabsf(s * a[u].x - c[u].x) + fabsf(s * a[u].y - c[u].y)) +
+                            (fabsf(s * a[u].z - c[u].z) + fabsf(s * a[u].w - c[u].w));
+            acc += (double)t;
+        }
+    }
+    finish_row_sum(acc, row, chunk, chunks, partial, ticket, 1.0, out);
+}
+
+constexpr int MAG_BLOCK = 8 * CR_THREADS;     // complex bins per CTA
+// out[sig] = sum over the (contiguous) spectrogram of | |X| - |Y| |        (spectral term, :213-216)
+__global__ void __launch_bounds__(CR_THREADS)
+mag_l1_kernel(const float2* __restrict__ X, const float2* __restrict__ Y, int64_t n_elems,
+              int chunks, float* __restrict__ out, double* __restrict__ partial,
+              unsigned int* __restrict__ ticket) {
+    const int64_t sig = blockIdx.x;
+    const int chunk = blockIdx.y;
+    const float2* xp = X + sig * n_elems;
+    const float2* yp = Y + sig * n_elems;
+    const int64_t begin = (int64_t)chunk * MAG_BLOCK;
+    double acc = 0;
+    float2 a[8], c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int64_t i = begin + u * CR_THREADS + threadIdx.x;
+        a[u] = i < n_elems ? __ldcs(xp + i) : make_float2(0.f, 0.f);
+        c[u] = i < n_elems ? __ldcs(yp + i) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) {
+        const float t0 = fabsf(hypotf(a[u].x, a[u].y) - hypotf(c[u].x, c[u].y));
+        const float t1 = fabsf(hypotf(a[u + 1].x, a[u + 1].y) - hypotf(c[u + 1].x, c[u + 1].y));
+        acc += (double)(t0 + t1);
+    }
+    finish_row_sum(acc, sig, chunk, chunks, partial, ticket, 1.0, out);
+}
+
+// gX = coef[sig] * sign(|X| - |Y|) * X / |X|   (torch's complex gradient of the spectral term)
+__global__ void mag_l1_grad_kernel(const float2* __restrict__ X, const float2* __restrict__ Y,
+                                   const float* __restrict__ coef, int64_t n_elems,
+                                   float2* __restrict__ gX) {
+    const int64_t sig = blockIdx.y;
+    const float cf = coef[sig];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 a = __ldcs(X + sig * n_elems + i), c = __ldcs(Y + sig * n_elems + i);
+        const float ma = hypotf(a.x, a.y), mc = hypotf(c.x, c.y);
+        float2 g = make_float2(0.f, 0.f);
+        if (ma > 0.f && ma != mc) {
+            const float k = (ma > mc ? cf : -cf) / ma;
+            g = make_float2(k * a.x, k * a.y);
+        }
+        gX[sig * n_elems + i] = g;
+    }
+}
+
+// gx[row, n] = coef[row] * sign(s x - y) for n < lengths[b], else 0
+__global__ void l1_rows_grad_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                    const int64_t* __restrict__ lengths,
+                                    const float* __restrict__ scale, const float* __restrict__ coef,
+                                    int64_t n_rows, int64_t length, int64_t xsb, int64_t xsr,
+                                    int64_t ysb, int64_t ysr, float* __restrict__ gx) {
+    const int64_t row = blockIdx.y;
+    const int64_t b = row / n_rows, r = row % n_rows;
+    int64_t valid = lengths[b];
+    if (valid > length) valid = length;
+    const float s = scale ? scale[row] : 1.f, cf = coef[row];
+    const float* xp = x + b * xsb + r * xsr;
+    const float* yp = y + b * ysb + r * ysr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < length;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (i < valid) {
+            const float d = s * __ldg(xp + i) - __ldg(yp + i);
+            v = d > 0.f ? cf : (d < 0.f ? -cf : 0.f);
+        }
+        gx[row * length + i] = v;
+    }
+}
+
 __global__ void masked_affine_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                      const int64_t* __restrict__ lengths, int64_t n_rows,
                                      int64_t length, int64_t xsb, int64_t xsr, int64_t ysb,
@@ -297,5 +437,89 @@ extern "C" int brv_apply_mask(const float* x, const int64_t* lengths, int64_t n_
     apply_mask_kernel<<<dim3(blocks, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
         x, lengths, inner, length, out);
     BRV_LAUNCH_CHECK("apply_mask_kernel");
+    return BRV_OK;
+}
+
+// ---- L1 terms of MultiResYuLoss ---------------------------------------------------------
+static int l1_chunks(int64_t n, int64_t per_cta) {
+    int64_t c = brv_ceil_div(n, per_cta);
+    return (int)(c < 1 ? 1 : c);
+}
+
+extern "C" size_t brv_l1_workspace_bytes(int64_t n_rows_total, int64_t length) {
+    if (n_rows_total <= 0) return 256;
+    size_t tickets = ((size_t)n_rows_total * sizeof(unsigned int) + 255) & ~(size_t)255;
+    return tickets + (size_t)n_rows_total * l1_chunks(length, MAG_BLOCK) * sizeof(double);
+}
+
+static void l1_split_ws(void* workspace, int64_t rows, unsigned int** ticket, double** partial) {
+    *ticket = reinterpret_cast<unsigned int*>(workspace);
+    size_t off = ((size_t)rows * sizeof(unsigned int) + 255) & ~(size_t)255;
+    *partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + off);
+}
+
+extern "C" int brv_l1_forward(const float* x, const float* y, const int64_t* lengths,
+                              const float* scale, int64_t n_batch, int64_t n_rows, int64_t length,
+                              int64_t xsb, int64_t xsr, int64_t ysb, int64_t ysr, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    BRV_REQUIRE(x && y && lengths && out && workspace, "null pointer argument");
+    const int64_t rows = n_batch * n_rows;
+    if (rows == 0) return BRV_OK;
+    BRV_REQUIRE(workspace_bytes >= brv_l1_workspace_bytes(rows, length), "L1 workspace too small");
+    const int chunks = l1_chunks(length, 2 * CR_BLOCK);
+    BRV_REQUIRE(rows <= 2147483647LL && chunks < 65536, "L1 problem too large");
+    unsigned int* ticket;
+    double* partial;
+    l1_split_ws(workspace, rows, &ticket, &partial);
+    l1_rows_kernel<<<dim3((unsigned)rows, (unsigned)chunks), CR_THREADS, 0, (cudaStream_t)stream>>>(
+        x, y, lengths, scale, n_rows, length, xsb, xsr, ysb, ysr, chunks, out, partial, ticket);
+    BRV_LAUNCH_CHECK("l1_rows_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_l1_backward(const float* x, const float* y, const int64_t* lengths,
+                               const float* scale, const float* coef, int64_t n_batch,
+                               int64_t n_rows, int64_t length, int64_t xsb, int64_t xsr,
+                               int64_t ysb, int64_t ysr, float* gx, void* stream) {
+    BRV_REQUIRE(x && y && lengths && coef && gx, "null pointer argument");
+    const int64_t rows = n_batch * n_rows;
+    if (rows == 0 || length == 0) return BRV_OK;
+    BRV_REQUIRE(rows < 65536, "more than 65535 rows per call");
+    unsigned blocks = (unsigned)brv_ceil_div(length, 256 * 8);
+    l1_rows_grad_kernel<<<dim3(blocks, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
+        x, y, lengths, scale, coef, n_rows, length, xsb, xsr, ysb, ysr, gx);
+    BRV_LAUNCH_CHECK("l1_rows_grad_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_mag_l1_forward(const void* X, const void* Y, int64_t n_signals, int64_t n_elems,
+                                  float* out, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+    BRV_REQUIRE(X && Y && out && workspace, "null pointer argument");
+    if (n_signals == 0) return BRV_OK;
+    BRV_REQUIRE(workspace_bytes >= brv_l1_workspace_bytes(n_signals, n_elems),
+                "L1 workspace too small");
+    const int chunks = l1_chunks(n_elems, MAG_BLOCK);
+    BRV_REQUIRE(n_signals <= 2147483647LL && chunks < 65536, "L1 problem too large");
+    unsigned int* ticket;
+    double* partial;
+    l1_split_ws(workspace, n_signals, &ticket, &partial);
+    mag_l1_kernel<<<dim3((unsigned)n_signals, (unsigned)chunks), CR_THREADS, 0,
+                    (cudaStream_t)stream>>>((const float2*)X, (const float2*)Y, n_elems, chunks,
+                                            out, partial, ticket);
+    BRV_LAUNCH_CHECK("mag_l1_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_mag_l1_backward(const void* X, const void* Y, const float* coef,
+                                   int64_t n_signals, int64_t n_elems, void* gX, void* stream) {
+    BRV_REQUIRE(X && Y && coef && gX, "null pointer argument");
+    if (n_signals == 0 || n_elems == 0) return BRV_OK;
+    BRV_REQUIRE(n_signals < 65536, "more than 65535 signals per call");
+    unsigned blocks = (unsigned)brv_ceil_div(n_elems, 256 * 8);
+    if (blocks > 4096) blocks = 4096;
+    mag_l1_grad_kernel<<<dim3(blocks, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(
+        (const float2*)X, (const float2*)Y, coef, n_elems, (float2*)gX);
+    BRV_LAUNCH_CHECK("mag_l1_grad_kernel");
     return BRV_OK;
 }

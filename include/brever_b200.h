@@ -203,6 +203,31 @@ int brv_masked_affine(const float* x, const float* y, const int64_t* lengths,
                       const float* ca, const float* cb, const float* c0,
                       const int32_t* ymap, float* gx, void* stream);
 
+/* ---- L1 terms of MultiResYuLoss (criterion.py:135-226) ------------------------------
+ * brv_l1_forward : out[b, r] = sum_{n < lengths[b]} | scale[b,r] * x[b,r,n] - y[b,r,n] |
+ *                  (time-domain term, :207-209; scale nullable = 1).
+ * brv_l1_backward: gx[b,r,n] = coef[b,r] * sign(scale x - y) under the length mask.
+ * brv_mag_l1_forward : out[s] = sum over a contiguous complex64 spectrogram of n_elems bins
+ *                  of | |X| - |Y| |  (spectral term, :213-216), X = STFT(estimate), Y = STFT(target).
+ * brv_mag_l1_backward: gX = coef[s] * sign(|X| - |Y|) * X / |X| (torch's complex gradient).
+ * workspace : brv_l1_workspace_bytes(rows, length) bytes, leading tickets zero on entry and
+ *             left zeroed (same contract as brv_snr_forward).                              */
+size_t brv_l1_workspace_bytes(int64_t n_rows_total, int64_t length);
+int brv_l1_forward(const float* x, const float* y, const int64_t* lengths,
+                   const float* scale, int64_t n_batch, int64_t n_rows, int64_t length,
+                   int64_t x_stride_batch, int64_t x_stride_row, int64_t y_stride_batch,
+                   int64_t y_stride_row, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int brv_l1_backward(const float* x, const float* y, const int64_t* lengths,
+                    const float* scale, const float* coef, int64_t n_batch,
+                    int64_t n_rows, int64_t length, int64_t x_stride_batch,
+                    int64_t x_stride_row, int64_t y_stride_batch, int64_t y_stride_row,
+                    float* gx, void* stream);
+int brv_mag_l1_forward(const void* X, const void* Y, int64_t n_signals, int64_t n_elems,
+                       float* out, void* workspace, size_t workspace_bytes, void* stream);
+int brv_mag_l1_backward(const void* X, const void* Y, const float* coef,
+                        int64_t n_signals, int64_t n_elems, void* gX, void* stream);
+
 /* apply_mask (criterion.py:229-234) for callers that need the masked tensors
  * themselves: out[b, ..., n] = n < lengths[b] ? x[b, ..., n] : 0.            */
 int brv_apply_mask(const float* x, const int64_t* lengths, int64_t n_batch,

@@ -133,3 +133,34 @@ def sisnr(x, y, lengths):
         2, perms.unsqueeze(2), 1)
     best = torch.einsum('bij,pij->bp', db, one_hot).amax(1)
     return -(best / n_src)
+
+
+def mse(x, y, lengths, weight=None):
+    """criterion.py:125-132 (out of place)."""
+    x, y = mask_pair(x, y, lengths)
+    loss = (x - y).abs().pow(2).sum(-1)
+    loss = loss / lengths.view(-1, *[1] * (x.ndim - 2))
+    if weight is not None:
+        loss = loss * weight.view(-1, *[1] * (x.ndim - 2))
+    return loss.mean(tuple(range(1, x.ndim - 1)))
+
+
+def multiresyu(x, y, lengths, frame_lengths=(512,), hop_lengths=None,
+               time_domain_weight=0.5, spectral_weight=0.5, scale_invariant=False):
+    """criterion.py:164-226: boxcar, unnormalised STFT magnitudes + L1 in time."""
+    if hop_lengths is None:
+        hop_lengths = [n // 2 for n in frame_lengths]
+    x, y = mask_pair(x, y, lengths)
+    if scale_invariant:
+        scaling = (x * y).sum(-1, keepdim=True) / (x.pow(2).sum(-1, keepdim=True) + EPS32)
+    else:
+        scaling = 1
+    out = time_domain_weight * (scaling * x - y).abs().sum(-1)
+    for n, hop in zip(frame_lengths, hop_lengths):
+        win = torch.ones(n, dtype=torch.float64)
+        kw = dict(frame_length=n, hop_length=hop, normalized=False)
+        y_mag = stft(y, win, **kw).abs()
+        x_mag = stft(scaling * x, win, **kw).abs()
+        out = out + spectral_weight * (x_mag - y_mag).abs().sum((-2, -1)) / len(frame_lengths)
+    out = out / lengths.view(-1, *[1] * (x.ndim - 2))
+    return out.mean(tuple(range(1, x.ndim - 1)))

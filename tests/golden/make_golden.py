@@ -61,7 +61,7 @@ def crandn(shape, seed):
 
 def main():
     sys.path.insert(0, REF)
-    from brever.criterion import sisnr, snr
+    from brever.criterion import MultiResYuLoss, mse, sisnr, snr
     from brever.modules import STFT, FeatureExtractor, MelFilterbank
 
     torch.set_num_threads(1)
@@ -219,6 +219,34 @@ def main():
         assert torch.equal(port.detach(), sisnr(est, ref, lengths))
         port.sum().backward()
         out['crit_sisnr_grad'] = e.grad.numpy()
+
+    # ---- mse (criterion.py:104-132) and multiresyu (criterion.py:135-226)
+    weight = torch.tensor([1.0, 0.5, 2.0, 0.25, 1.5])
+    out['crit_mse_weight'] = weight.numpy()
+    out['crit_mse'] = mse(est, ref, lengths).numpy()
+    out['crit_mse_w'] = mse(est, ref, lengths, weight=weight).numpy()
+    out['crit_mse_2d'] = mse(est[:, 0], ref[:, 0], lengths).numpy()
+    cest = torch.complex(est[..., :1000], est[..., 1000:])
+    cref = torch.complex(ref[..., :1000], ref[..., 1000:])
+    clen = lengths.clamp(max=1000)
+    out['crit_mse_complex'] = mse(cest, cref, clen, weight=weight).numpy()
+    e = est.clone().requires_grad_(True)
+    mse(e, ref, lengths, weight=weight).sum().backward()
+    out['crit_mse_grad'] = e.grad.numpy()
+    ce = cest.clone().requires_grad_(True)
+    mse(ce, cref, clen).sum().backward()
+    out['crit_mse_complex_grad'] = ce.grad.numpy()
+    for name, kw in (('def', {}),
+                     ('multi', dict(frame_lengths=[512, 256], hop_lengths=[128, 128],
+                                    time_domain_weight=0.3, spectral_weight=0.7)),
+                     ('si', dict(scale_invariant=True))):
+        crit = MultiResYuLoss(**kw)
+        out[f'crit_mry_{name}'] = crit(est, ref, lengths).numpy()
+        out[f'crit_mry_{name}_2d'] = crit(est[:, 0], ref[:, 0], lengths).numpy()
+        if name != 'si':
+            e = est.clone().requires_grad_(True)
+            (crit(e, ref, lengths) * weight).sum().backward()
+            out[f'crit_mry_{name}_grad'] = e.grad.numpy()
 
     np.savez_compressed(os.path.join(HERE, 'reference_vectors.npz'), **out)
     total = sum(v.nbytes for v in out.values())

@@ -446,6 +446,77 @@ def test_batched_equals_single_reference_sizes(name):
     assert np.allclose(cpu(batched), ref.numpy(), rtol=0, atol=5e-5)
 
 
+def test_mse_against_reference():
+    """criterion.py:104-132: values, weights, the 2-D mean(()) quirk, complex inputs, gradients."""
+    g = golden()
+    est, ref, lengths = _crit_inputs()
+    weight = torch.tensor(g['crit_mse_weight'])
+    e, r = est.to(DEV), ref.to(DEV)
+    assert np.allclose(cpu(brv.mse(e, r, lengths)), g['crit_mse'], rtol=2e-6)
+    assert np.allclose(cpu(brv.mse(e, r, lengths, weight=weight.to(DEV))), g['crit_mse_w'], rtol=2e-6)
+    out = brv.mse(e[:, 0], r[:, 0], lengths)
+    assert out.ndim == 0 and abs(float(out) - float(g['crit_mse_2d'])) < 1e-5
+    cest = torch.complex(est[..., :1000], est[..., 1000:])
+    cref = torch.complex(ref[..., :1000], ref[..., 1000:])
+    clen = lengths.clamp(max=1000)
+    out = brv.mse(cest.to(DEV), cref.to(DEV), clen, weight=weight.to(DEV))
+    assert out.dtype == torch.float32
+    assert np.allclose(cpu(out), g['crit_mse_complex'], rtol=2e-6)
+    eg = est.clone().to(DEV).requires_grad_(True)
+    brv.mse(eg, r, lengths, weight=weight.to(DEV)).sum().backward()
+    assert_parity(cpu(eg.grad), g['crit_mse_grad'], 1e-5)
+    assert float(eg.grad[3, :, 801:].abs().max()) == 0           # masked tail
+    cg = cest.clone().to(DEV).requires_grad_(True)
+    brv.mse(cg, cref.to(DEV), clen).sum().backward()
+    assert_parity(cpu(cg.grad), g['crit_mse_complex_grad'], 1e-5)
+    assert brv.init_criterion('mse') is brv.mse
+
+
+MRY_KW = {'def': {}, 'multi': dict(frame_lengths=[512, 256], hop_lengths=[128, 128],
+                                   time_domain_weight=0.3, spectral_weight=0.7),
+          'si': dict(scale_invariant=True)}
+
+
+@pytest.mark.parametrize('name', ['def', 'multi', 'si'])
+def test_multiresyu_against_reference(name):
+    """criterion.py:135-226 (TF-GridNet's default criterion): values, 2-D quirk, gradients
+    through the fused L1 reductions and the tcgen05 STFT gradient kernel."""
+    g = golden()
+    est, ref, lengths = _crit_inputs()
+    crit = brv.init_criterion('multiresyu', **MRY_KW[name])
+    e, r = est.to(DEV), ref.to(DEV)
+    assert np.allclose(cpu(crit(e, r, lengths)), g[f'crit_mry_{name}'], rtol=2e-5)
+    out = crit(e[:, 0], r[:, 0], lengths)
+    assert out.ndim == 0 and abs(float(out) - float(g[f'crit_mry_{name}_2d'])) < 2e-4
+    eg = est.clone().to(DEV).requires_grad_(True)
+    if name == 'si':
+        with pytest.raises(NotImplementedError):
+            crit(eg, r, lengths)
+        return
+    weight = torch.tensor(g['crit_mse_weight']).to(DEV)
+    (crit(eg, r, lengths) * weight).sum().backward()
+    assert_parity(cpu(eg.grad), g[f'crit_mry_{name}_grad'], 1e-4)
+    assert float(eg.grad[3, :, 801:].abs().max()) == 0
+
+
+@pytest.mark.parametrize('name', ['mse', 'multiresyu'])
+def test_batched_equals_single_next_criteria(name):
+    """tests/test_losses.py:13-57 for the two remaining registry entries."""
+    torch.manual_seed(0)
+    B, S, lo, hi = 8, 4, 16000, 32000
+    lengths = torch.randint(lo, hi, (B,))
+    batched_out = torch.randn(B, S, hi)                          # padding NOT zero
+    batched_tgt = torch.randn(B, S, hi)
+    crit = brv.init_criterion(name)
+    batched = crit(batched_out.to(DEV), batched_tgt.to(DEV), lengths)
+    single = torch.stack([
+        crit(batched_out[i:i + 1, :, :n].to(DEV), batched_tgt[i:i + 1, :, :n].to(DEV),
+             torch.tensor([n]))[0] for i, n in enumerate(lengths)])
+    assert torch.allclose(batched, single, rtol=1e-5)
+    port = P.mse if name == 'mse' else P.multiresyu
+    assert np.allclose(cpu(batched), port(batched_out, batched_tgt, lengths).numpy(), rtol=2e-5)
+
+
 def test_sisnr_baseline_size_and_pit():
     """cfg3 shape: (256, 1, 64000) and the PIT S=2 variant with swapped sources."""
     mix, fg = synthetic_mixture((256, 1, 64000), 1003)

@@ -262,3 +262,29 @@ def test_batched_equals_single():
         single = np.array([fn(x[i:i + 1, :, :n], y[i:i + 1, :, :n], [n])[0]
                            for i, n in enumerate(lengths)])
         assert np.allclose(batched, single, rtol=0, atol=1e-10)
+
+
+def test_mse_and_multiresyu_port_against_reference():
+    """oracle/torch_port.py restatements of criterion.py:104-226 against the reference's own
+    outputs (values and autograd)."""
+    g = golden()
+    est, ref, lengths = _crit_inputs()
+    weight = torch.tensor(g['crit_mse_weight'])
+    assert np.allclose(P.mse(est, ref, lengths).numpy(), g['crit_mse'], atol=1e-6)
+    assert np.allclose(P.mse(est, ref, lengths, weight).numpy(), g['crit_mse_w'], atol=1e-6)
+    assert np.allclose(P.mse(est[:, 0], ref[:, 0], lengths).numpy(), g['crit_mse_2d'], atol=1e-6)
+    cest = torch.complex(est[..., :1000], est[..., 1000:])
+    cref = torch.complex(ref[..., :1000], ref[..., 1000:])
+    assert np.allclose(P.mse(cest, cref, lengths.clamp(max=1000), weight).numpy(),
+                       g['crit_mse_complex'], atol=1e-6)
+    kws = {'def': {}, 'multi': dict(frame_lengths=[512, 256], hop_lengths=[128, 128],
+                                    time_domain_weight=0.3, spectral_weight=0.7),
+           'si': dict(scale_invariant=True)}
+    for name, kw in kws.items():
+        assert np.allclose(P.multiresyu(est, ref, lengths, **kw).numpy(), g[f'crit_mry_{name}'],
+                           rtol=1e-5)
+        assert np.allclose(P.multiresyu(est[:, 0], ref[:, 0], lengths, **kw).numpy(),
+                           g[f'crit_mry_{name}_2d'], rtol=1e-5)
+    e = est.clone().requires_grad_(True)
+    (P.multiresyu(e, ref, lengths) * weight).sum().backward()
+    assert_parity(e.grad.numpy(), g['crit_mry_def_grad'], 1e-5)
