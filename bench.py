@@ -397,6 +397,11 @@ def run_ours(args, rank, world, device):
         roofline = dict(bound='hbm', kernel=dominant, achieved=round(achieved, 1),
                         peak=peaks['hbm'], unit='GB/s', frac=round(achieved / peaks['hbm'], 4),
                         traffic=None, peak_source=peaks['source'])
+    try:    # DRAM traffic of the dominant kernel from the committed ncu capture, if there is one
+        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+            roofline['traffic'] = json.load(f).get(args.workload, {}).get(dominant)
+    except (OSError, ValueError):
+        pass
     roofline['stage_ms'] = {k: round(v, 4) for k, v in stage_ms.items()}
     roofline['stage_hbm_frac'] = {
         k: round(work[k]['bytes'] / (v * 1e-3) / 1e9 / peaks['hbm'], 4) for k, v in stage_ms.items()}
