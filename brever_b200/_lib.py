@@ -57,6 +57,9 @@ PROTOTYPES = {
                                  _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr,
                                  _ptr, _ptr]),
     'brv_apply_mask': (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr]),
+    'brv_criterion_backward': (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _f32, _ptr, _int,
+                                      _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _ptr,
+                                      _ptr]),
     'brv_l1_workspace_bytes': (_sz, [_i64, _i64]),
     'brv_l1_forward': (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64,
                               _i64, _i64, _ptr, _ptr, _sz, _ptr]),

@@ -94,6 +94,22 @@ def _masked_affine(x3, y3, lengths, ca, cb, c0, ymap=None):
     return gx
 
 
+def _criterion_backward(x3, y3, lengths, mom, grad, gscale, pairwise, ymap=None):
+    """One launch: coefficients from the saved moments + masked affine map."""
+    batch, rows, length = x3.shape
+    gx = torch.empty((batch, rows, length), dtype=torch.float32, device=x3.device)
+    if gx.numel():
+        g = grad.float().reshape(-1).contiguous()
+        stride = 0 if g.numel() == 1 else 1
+        with _lib.on_device(x3.device):
+            _lib.check(_lib.lib().brv_criterion_backward(
+                _lib.ptr(x3), _lib.ptr(y3), _lib.ptr(lengths), _lib.ptr(mom), _lib.ptr(g),
+                stride, float(gscale), _lib.ptr(ymap), int(pairwise), batch, rows, length,
+                x3.stride(0), x3.stride(1), y3.stride(0), y3.stride(1), float(eps),
+                _lib.ptr(gx), _lib.stream_ptr(x3.device)))
+    return gx
+
+
 class _SnrFunction(torch.autograd.Function):
     """-(mean over rows of 10 log10(sum y^2 / (sum (y-x)^2 + eps) + eps))."""
 
@@ -112,17 +128,9 @@ class _SnrFunction(torch.autograd.Function):
     def backward(ctx, grad):
         x3, y3, lengths, mom = ctx.saved_tensors
         batch, rows, _ = x3.shape
-        p, d = mom[:, 4], mom[:, 5]
-        r = p / (d + eps)
-        # d(dB)/dx_n = K * 2P / ((r+eps)(D+eps)^2) * (y_n - x_n)
-        coef = _K * 2 * p / ((r + eps) * (d + eps) ** 2)
-        if len(ctx.shape) == 2:
-            g = grad.reshape(1).expand(batch) / batch
-        else:
-            g = grad.reshape(batch) / rows
-        cb = (-(g.double().repeat_interleave(rows)) * coef).float()
-        gx = _masked_affine(x3, y3, lengths, (-cb).contiguous(), cb.contiguous(),
-                            torch.zeros_like(cb))
+        # loss = -mean dB: a 2-D input averages over the batch too (the mean(()) quirk)
+        gscale = 1.0 / batch if len(ctx.shape) == 2 else 1.0 / rows
+        gx = _criterion_backward(x3, y3, lengths, mom, grad, gscale, False)
         return gx.view(ctx.shape).to(ctx.dtype), None, None
 
 
@@ -154,41 +162,18 @@ class _SiSnrFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
-        if len(ctx.saved_tensors) == 4:
+        if len(ctx.saved_tensors) == 4:          # one source: no permutation
             x3, y3, lengths, mom = ctx.saved_tensors
-            perm = torch.zeros((x3.shape[0], 1), dtype=torch.int64, device=x3.device)
-        else:
-            x3, y3, lengths, mom, perm = ctx.saved_tensors
+            gx = _criterion_backward(x3, y3, lengths, mom, grad, 1.0, True)
+            return gx.view(ctx.shape).to(ctx.dtype), None, None
+        x3, y3, lengths, mom, perm = ctx.saved_tensors
         batch, n_src, _ = x3.shape
         dev = x3.device
-        # moments of the matched pairs: pair index = (b*S + i)*S + perm[b, i]
-        tgt = torch.arange(n_src, device=dev).expand(batch, n_src)
-        pair = (torch.arange(batch, device=dev)[:, None] * n_src + tgt) * n_src + perm
-        m = mom[pair.reshape(-1)]                  # (B*S, 6) ordered by (b, target i)
-        sx, sy, sxy, sxx, syy = m[:, 0], m[:, 1], m[:, 2], m[:, 3], m[:, 4]
-        L = lengths.double().repeat_interleave(n_src)
-        n = torch.minimum(L, torch.full_like(L, float(x3.shape[-1])))
-        mx, my = sx / L, sy / L
-        dot = sxy - mx * sy - my * sx + n * mx * my
-        ea = sxx - 2 * mx * sx + n * mx * mx
-        eb = syy - 2 * my * sy + n * my * my
-        t = dot * dot / eb
-        e = (ea - t).clamp_min(0)
-        r = t / (e + eps)
-        common = _K / ((r + eps) * (e + eps) ** 2)
-        alpha = common * (e + eps + t) * (2 * dot / eb)   # multiplies b = y - my
-        beta = -2 * t * common                            # multiplies a = x - mx
-        g = (-grad.double() / n_src).repeat_interleave(n_src)
-        ca_t, cb_t = g * beta, g * alpha
-        c0_t = g * (-alpha * my - beta * mx)
-        # scatter from (b, target i) order to estimate rows j = perm[b, i]
-        row = (torch.arange(batch, device=dev)[:, None] * n_src + perm).reshape(-1)
-        ca = torch.empty_like(ca_t).index_copy_(0, row, ca_t).float()
-        cb = torch.empty_like(cb_t).index_copy_(0, row, cb_t).float()
-        c0 = torch.empty_like(c0_t).index_copy_(0, row, c0_t).float()
-        ymap = torch.empty(batch * n_src, dtype=torch.int32, device=dev)
-        ymap.index_copy_(0, row, tgt.reshape(-1).to(torch.int32))
-        gx = _masked_affine(x3, y3, lengths, ca, cb, c0, ymap)
+        # estimate row j = perm[b, i] is matched with target i: ymap[b, j] = i
+        ymap = torch.empty((batch, n_src), dtype=torch.int64, device=dev)
+        ymap.scatter_(1, perm, torch.arange(n_src, device=dev).expand(batch, n_src))
+        gx = _criterion_backward(x3, y3, lengths, mom, grad, 1.0 / n_src, True,
+                                 ymap.to(torch.int32).contiguous())
         return gx.view(ctx.shape).to(ctx.dtype), None, None
 
 

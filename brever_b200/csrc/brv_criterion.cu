@@ -340,6 +340,85 @@ __global__ void masked_affine_kernel(const float* __restrict__ x, const float* _
     }
 }
 
+// Criterion gradient with the per-row coefficients evaluated in the kernel from the saved
+// float64 moments (one launch instead of ~25 small tensor ops, SURVEY 8a' closed forms):
+//   mode 0 (snr):   gx = g coef (x - y),  coef = K 2P / ((r + eps)(D + eps)^2), r = P / (D + eps)
+//   mode 1 (sisnr): gx = g (beta (x - mx) + alpha (y - my)) for the matched (target, estimate) pair
+// g = -gout[b] * gscale for sisnr (loss = -dB), +gout[b] * gscale * ... see the host wrapper.
+__global__ void __launch_bounds__(256)
+criterion_grad_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                      const int64_t* __restrict__ lengths, const double* __restrict__ moments,
+                      const float* __restrict__ gout, int64_t gout_stride, float gscale,
+                      const int32_t* __restrict__ ymap, int mode, int64_t n_rows, int64_t length,
+                      int64_t xsb, int64_t xsr, int64_t ysb, int64_t ysr, float eps,
+                      float* __restrict__ gx) {
+    const int64_t row = blockIdx.y;               // b * n_rows + r (estimate row)
+    const int64_t b = row / n_rows, r = row % n_rows;
+    const int64_t yr = ymap ? ymap[row] : r;
+    int64_t valid = lengths[b];
+    if (valid > length) valid = length;
+    if (valid < 0) valid = 0;
+    __shared__ float coef[3];
+    if (threadIdx.x == 0) {
+        const double K = 4.342944819032518;       // 10 / ln 10
+        const double e = (double)eps;
+        const double g = (double)gout[b * gout_stride] * (double)gscale;
+        if (mode == 0) {
+            const double* m = moments + row * CR_MOMENTS;
+            const double p = m[4], d = m[5];
+            const double ratio = p / (d + e);
+            const double c = g * K * 2.0 * p / ((ratio + e) * (d + e) * (d + e));
+            coef[0] = (float)c;
+            coef[1] = (float)(-c);
+            coef[2] = 0.f;
+        } else {
+            const double* m = moments + ((b * n_rows + yr) * n_rows + r) * CR_MOMENTS;
+            const double sx = m[0], sy = m[1], sxy = m[2], sxx = m[3], syy = m[4];
+            const double L = (double)lengths[b], n = (double)valid;
+            const double mx = sx / L, my = sy / L;
+            const double dot = sxy - mx * sy - my * sx + n * mx * my;
+            const double ea = sxx - 2 * mx * sx + n * mx * mx;
+            const double eb = syy - 2 * my * sy + n * my * my;
+            const double t = dot * dot / eb;
+            double en = ea - t;
+            if (en < 0) en = 0;
+            const double ratio = t / (en + e);
+            const double common = K / ((ratio + e) * (en + e) * (en + e));
+            const double alpha = common * (en + e + t) * (2 * dot / eb);   // multiplies (y - my)
+            const double beta = -2 * t * common;                            // multiplies (x - mx)
+            coef[0] = (float)(-g * beta);
+            coef[1] = (float)(-g * alpha);
+            coef[2] = (float)(-g * (-alpha * my - beta * mx));
+        }
+    }
+    __syncthreads();
+    const float ca = coef[0], cb = coef[1], c0 = coef[2];
+    const float* xp = x + b * xsb + r * xsr;
+    const float* yp = y + b * ysb + yr * ysr;
+    float* gp = gx + row * length;
+    const bool vec = (((((uintptr_t)xp) | ((uintptr_t)yp) | ((uintptr_t)gp)) & 15) == 0);
+    const int64_t base = (int64_t)blockIdx.x * 2048 * 4;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int64_t i = base + 4 * (int64_t)(u * 256 + threadIdx.x);
+        if (i >= length) break;
+        if (vec && i + 4 <= length) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < valid) {
+                const float4 a = load4(xp, i, valid, true), c = load4(yp, i, valid, true);
+                o.x = fmaf(ca, a.x, fmaf(cb, c.x, c0));
+                o.y = i + 1 < valid ? fmaf(ca, a.y, fmaf(cb, c.y, c0)) : 0.f;
+                o.z = i + 2 < valid ? fmaf(ca, a.z, fmaf(cb, c.z, c0)) : 0.f;
+                o.w = i + 3 < valid ? fmaf(ca, a.w, fmaf(cb, c.w, c0)) : 0.f;
+            }
+            *reinterpret_cast<float4*>(gp + i) = o;
+        } else {
+            for (int64_t j = i; j < i + 4 && j < length; ++j)
+                gp[j] = j < valid ? fmaf(ca, __ldg(xp + j), fmaf(cb, __ldg(yp + j), c0)) : 0.f;
+        }
+    }
+}
+
 __global__ void apply_mask_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengths,
                                   int64_t inner, int64_t length, float* __restrict__ out) {
     const int64_t row = blockIdx.y;
@@ -521,5 +600,23 @@ extern "C" int brv_mag_l1_backward(const void* X, const void* Y, const float* co
     mag_l1_grad_kernel<<<dim3(blocks, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(
         (const float2*)X, (const float2*)Y, coef, n_elems, (float2*)gX);
     BRV_LAUNCH_CHECK("mag_l1_grad_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_criterion_backward(const float* x, const float* y, const int64_t* lengths,
+                                      const double* moments, const float* gout,
+                                      int64_t gout_stride, float gscale, const int32_t* ymap,
+                                      int pairwise, int64_t n_batch, int64_t n_rows,
+                                      int64_t length, int64_t xsb, int64_t xsr, int64_t ysb,
+                                      int64_t ysr, float eps, float* gx, void* stream) {
+    BRV_REQUIRE(x && y && lengths && moments && gout && gx, "null pointer argument");
+    const int64_t rows = n_batch * n_rows;
+    if (rows == 0 || length == 0) return BRV_OK;
+    BRV_REQUIRE(rows < 65536, "more than 65535 rows per call");
+    const unsigned blocks = (unsigned)brv_ceil_div(length, 2048 * 4);
+    criterion_grad_kernel<<<dim3(blocks, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
+        x, y, lengths, moments, gout, gout_stride, gscale, ymap, pairwise ? 1 : 0, n_rows, length,
+        xsb, xsr, ysb, ysr, eps, gx);
+    BRV_LAUNCH_CHECK("criterion_grad_kernel");
     return BRV_OK;
 }

@@ -228,6 +228,22 @@ int brv_mag_l1_forward(const void* X, const void* Y, int64_t n_signals, int64_t 
 int brv_mag_l1_backward(const void* X, const void* Y, const float* coef,
                         int64_t n_signals, int64_t n_elems, void* gX, void* stream);
 
+/* Gradient of the snr / sisnr loss w.r.t. the estimate in one launch: the per-row
+ * coefficients of the closed forms (SURVEY.md 8a') are evaluated in the kernel from the
+ * float64 `moments` brv_snr_forward saved.
+ *   gout : upstream gradient of the (negated) loss, read at gout[b * gout_stride]
+ *          (stride 0 broadcasts one scalar); gscale multiplies it (1 / rows for the row mean).
+ *   pairwise == 0 (snr): estimate row r pairs with target row r.
+ *   pairwise == 1 (sisnr): estimate row r pairs with target row ymap[b, r] (nullable =
+ *          identity), moments indexed [(b, target, estimate)].                       */
+int brv_criterion_backward(const float* x, const float* y, const int64_t* lengths,
+                           const double* moments, const float* gout,
+                           int64_t gout_stride, float gscale, const int32_t* ymap,
+                           int pairwise, int64_t n_batch, int64_t n_rows,
+                           int64_t length, int64_t x_stride_batch, int64_t x_stride_row,
+                           int64_t y_stride_batch, int64_t y_stride_row, float eps,
+                           float* gx, void* stream);
+
 /* apply_mask (criterion.py:229-234) for callers that need the masked tensors
  * themselves: out[b, ..., n] = n < lengths[b] ? x[b, ..., n] : 0.            */
 int brv_apply_mask(const float* x, const int64_t* lengths, int64_t n_batch,
