@@ -18,6 +18,7 @@ bool brv_fold_supported(const brv_stft_plan* p);
 int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
                           int64_t x_stride, float2* out, int64_t n_frames, cudaStream_t st);
 bool brv_fold_inverse_supported(const brv_stft_plan* p);
+bool brv_fold_grad_supported(const brv_stft_plan* p);
 int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t sb, int64_t sf,
                    int64_t n_sig, int64_t n_frames, int64_t out_len, float* y, cudaStream_t st);
 
@@ -100,7 +101,7 @@ extern "C" int brv_stft_forward_grad(const brv_stft_plan* p, const void* gX, int
     if (rc != BRV_OK) return rc;
     if (n_signals == 0 || samples == 0) return BRV_OK;
     if (!force_generic() && tc_variant() != 1 && brv_fold_inverse_supported(p) &&
-        p->n_bins == p->n_bins_inv)
+        brv_fold_grad_supported(p) && p->n_bins == p->n_bins_inv)
         return brv_fold_stft_grad(p, (const float2*)gX, ss, sb, sf, n_signals, n_frames, samples,
                                   gx, (cudaStream_t)stream);
     BRV_REQUIRE(workspace && workspace_bytes >= brv_stft_workspace_bytes(p, n_signals, n_frames),
@@ -148,7 +149,7 @@ extern "C" int brv_istft_forward_grad(const brv_stft_plan* p, const float* gy, i
                         "gradient of the decompressing iSTFT (compression_factor != 1) is not "
                         "implemented: the reference only runs it under no_grad");
     if (n_signals == 0) return BRV_OK;
-    if (!force_generic() && tc_variant() != 1 && brv_fold_supported(p) && p->n_bins == p->n_bins_inv) {
+    if (!force_generic() && tc_variant() != 1 && brv_fold_grad_supported(p) && p->n_bins == p->n_bins_inv) {
         int64_t out_len = 0;
         int rc = brv_istft_geometry(p, n_frames, &out_len);
         if (rc != BRV_OK) return rc;

@@ -1,7 +1,8 @@
 // Symmetry-folded tensor-core STFT for sm_100a (tcgen05 + TMEM + TMA), fp32-grade.
 //
 // STFT.forward (brever/modules/stft.py:59-89) for one-sided transforms with
-// n_fft in {128, 256, 384, 512}.  A real DFT of length N = 4Q splits, by the
+// n_fft in {128, 256, 384, 512} and {126, 254, 382, 510} (N = 4Q - 2: the same fold with
+// N/2 odd — SGMSE's 510-point transform; see FoldFwdParams::odd).  A real DFT of length N = 4Q splits, by the
 // even/odd symmetries of cos and sin about n = N/2 and n = N/4 (two radix-2
 // decimation-in-frequency steps done on the *input* side), into four independent
 // Q x Q contractions:
@@ -87,6 +88,11 @@ struct FoldFwdParams {
     // which carry Hermitian weight 1 instead of 2, are multiplied by edge_scale = 1/2
     const float* in_mul;
     float edge_scale;
+    // n_fft = 4Q - 2 (N/2 odd, e.g. 510): same four contractions over n = 0..Q-1, but there is
+    // no self-paired n = Q column and no separate Nyquist bin (k = N/2 is the last odd bin)
+    int odd;
+    // the staged span starts `shift` samples early so that it is 16-byte aligned in HBM
+    int shift;
 };
 
 __device__ __forceinline__ float4 mul4(float4 a, float4 b) {
@@ -201,8 +207,9 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
         const int bw = warp - 2;                   // 0..7
         const int bt = bw * 32 + lane;             // 0..255
         const float* xs = p.x + sig * p.x_stride;
-        const int64_t span0 = t0 * H - Hf;         // first sample of the span (may be < 0)
-        const int span_len = (rows_eff - 1) * H + N;
+        const int shift = p.shift;
+        const int64_t span0 = t0 * H - Hf - shift; // first sample of the span (may be < 0)
+        const int span_len = (rows_eff - 1) * H + N + shift;
         const int span_pad = (span_len + 31) & ~31;
 
         for (int j = bt; j < Q; j += BUILDER_THREADS) wtab[j] = __ldg(p.wtab + j);
@@ -249,7 +256,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
 
         // ---- per-row power-of-two scale from a bound on the folded magnitudes ----
         if (bt < rows_eff) {
-            const int b0 = (bt * H) >> 5, b1 = (bt * H + N - 1) >> 5;
+            const int b0 = (bt * H + shift) >> 5, b1 = (bt * H + shift + N - 1) >> 5;
             uint32_t mx = 0u;
             for (int b = b0; b <= b1; ++b) mx = max(mx, bmax[b]);
             rowinfo[bt].x = row_scale(4.f * p.wmax * __uint_as_float(mx));
@@ -282,7 +289,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
                 for (int i = 0; i < 8; ++i) {
                     const int row = bw * 16 + 2 * i + half;
                     if (row >= rows_eff) continue;
-                    const float* fr = span + row * H;
+                    const float* fr = span + shift + row * H;
                     const float a0 = fr[n0] * w0.x, a1 = fr[n0 + 1] * w1.x;
                     const float b0 = fr[Hf - n0] * w0.y, b1 = fr[Hf - n0 - 1] * w1.y;
                     const float c0 = fr[Hf + n0] * w0.z, c1 = fr[Hf + n0 + 1] * w1.z;
@@ -330,7 +337,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
         if (live) {
             const float2 ri = rowinfo[row];
             g0 = p.basis_scale_inv / ri.x;
-            const float xq = span[row * H + Q] * p.wq, x3q = span[row * H + 3 * Q] * p.w3q;
+            const float xq = span[shift + row * H + Q] * p.wq, x3q = span[shift + row * H + 3 * Q] * p.w3q;
             eeq = xq + x3q;
             ooq = xq - x3q;
             ny = ri.y + eeq;                       // Q is even: (-1)^Q = +1
@@ -377,7 +384,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
             }
             __syncwarp();
         }
-        if (hsel == 1 && live) {                   // Nyquist bin: purely real
+        if (hsel == 1 && live && !p.odd) {         // Nyquist bin: purely real
             float v = ny * p.edge_scale;
             if (p.post_expo != 0.f) v = compress_real(v, p.post_expo);
             *reinterpret_cast<float2*>(obase + (int64_t)lane * pitch + 2 * Hf) =
@@ -608,7 +615,7 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
                     }
                     __syncwarp();
                 }
-                if (pass == 0 && live) {                   // Nyquist bin: purely real
+                if (pass == 0 && live && !p.odd) {         // Nyquist bin: purely real
                     float v = (ri.y + ri.z) * p.edge_scale;   // Q is even: (-1)^Q = +1
                     if (COMPRESS) v = compress_real(v, p.post_expo);
                     *reinterpret_cast<float2*>(obase + (int64_t)lane * pitch + 2 * Hf) =
@@ -631,8 +638,9 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
             const int64_t t0 = (int64_t)(tile_id % p.tiles_per_signal) * p.rows;
             const int rows_eff = (int)min((int64_t)p.rows, p.n_frames - t0);
             const float* xs = p.x + sig * p.x_stride;
-            const int64_t span0 = t0 * H - Hf;         // first sample of the span (may be < 0)
-            const int span_len = (rows_eff - 1) * H + N;
+            const int shift = p.shift;
+            const int64_t span0 = t0 * H - Hf - shift; // first sample of the span (may be < 0)
+            const int span_len = (rows_eff - 1) * H + N + shift;
             const int span_pad = (span_len + 31) & ~31;
             if (n > 0) named_bar_sync(1, F2_BUILDER_THREADS);   // previous tile's span fully read
 
@@ -709,11 +717,12 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
             if (bt < TILE_M) {
                 float4 ri = make_float4(1.f, 0.f, 0.f, 0.f);
                 if (bt < rows_eff) {
-                    const int b0 = (bt * H) >> 5, b1 = (bt * H + N - 1) >> 5;
+                    const int b0 = (bt * H + shift) >> 5, b1 = (bt * H + shift + N - 1) >> 5;
                     uint32_t mx = 0u;
                     for (int b = b0; b <= b1; ++b) mx = max(mx, bmax[b]);
                     ri.x = row_scale(4.f * p.wmax * __uint_as_float(mx));
-                    const float xq = span[bt * H + Q] * p.wq, x3q = span[bt * H + 3 * Q] * p.w3q;
+                    const float xq = span[shift + bt * H + Q] * p.wq,
+                                x3q = span[shift + bt * H + 3 * Q] * p.w3q;
                     ri.z = xq + x3q;                   // ee[Q]
                     ri.w = xq - x3q;                   // oo[Q]
                 }
@@ -744,7 +753,7 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
                     for (int i = 0; i < RI; ++i) {
                         const int row = bw * F2_ROWS_PER_WARP + 2 * i + half;
                         if (row >= rows_eff) continue;
-                        const float* fr = span + row * H;
+                        const float* fr = span + shift + row * H;
                         const float a0 = fr[n0] * w0.x, a1 = fr[n0 + 1] * w1.x;
                         const float b0 = fr[Hf - n0] * w0.y, b1 = fr[Hf - n0 - 1] * w1.y;
                         const float c0 = fr[Hf + n0] * w0.z, c1 = fr[Hf + n0 + 1] * w1.z;
@@ -905,7 +914,12 @@ __device__ __forceinline__ uint32_t absbits_max(uint32_t m, float2 v) {
 // HQ = hop / Q (1, 2 or 4); FRAMES_FAST: lanes run along frames when loading the
 // spectrogram (bin-major or arbitrary strides), else along bins (frame-major input);
 // DECOMP: |X|^(1/c - 1) decompression in the loaders (keeps powf out of the common path).
-template <int HQ, bool FRAMES_FAST, bool DECOMP>
+// ODD: n_fft = 4Q - 2 with hop = Q (SGMSE's 510 / 128).  Same contractions over n = 0..Q-1, no
+// Nyquist term and no n = Q column; the four formulas land on positions n, N/2 - n, N/2 + n,
+// N - n with N/2 = 2Q - 1, so hop block s (positions sQ .. sQ + Q - 1) at offset o takes
+//   s = 0: f[n = o]            s = 1: f[N/2 - (Q-1-o)]
+//   s = 2: f[N/2 + (o+1)]  (o = Q-1: f[N - (Q-1)])      s = 3: f[N - (Q-2-o)]  (o >= Q-2: nothing)
+template <int HQ, bool FRAMES_FAST, bool DECOMP, bool ODD = false>
 __global__ void __launch_bounds__(INV_THREADS, 1)
 istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -1025,7 +1039,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
             if (FRAMES_FAST) {
                 // thread = frame; chunk = 16 bins x 128 frames; a thread scans only what it
                 // copied itself: cp.async group waits are the only synchronisation
-                const int nch = Hf / 16;
+                const int nch = Q / 8;                 // 2Q bins besides the Nyquist bin
                 const bool live = st < rows_eff;
                 const float2* col = xs + (t0 + (live ? st : 0)) * p.sf;
                 float m = 0.f;
@@ -1070,7 +1084,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                     }
                 }
                 float ny = 0.f;
-                if (live)
+                if (live && !ODD)
                     ny = prep_bin<DECOMP>(__ldg(col + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x *
                          p.edge_gain;
                 ri[st] = make_float4(row_scale(m), 0.f, 0.f, ny);
@@ -1129,7 +1143,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                                     }
                                     m = __uint_as_float(mb) * fabsf(p.pre_scale);
                                 }
-                                if (lane == 0)
+                                if (lane == 0 && !ODD)
                                     ny = prep_bin<DECOMP>(src[r * RING_ROW + Hf], p.pre_scale, p.pre_expo).x *
                                          p.edge_gain;
                             }
@@ -1190,6 +1204,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                             c[0].y = 0.f;              // Im X[0] is ignored by the c2r inverse
                             c[0].x *= p.edge_gain;
                         }
+                        if (ODD && bin0 + 32 == 2 * Q) c[31].y = 0.f;   // so is Im X[N/2]
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
                             pacc += c[2 * j].x - c[2 * j + 2].x;          // (-1)^m Re X[2m]
@@ -1273,6 +1288,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                             c[i][0].y = 0.f;           // Im X[0] is ignored by the c2r inverse
                             c[i][0].x *= p.edge_gain;
                         }
+                        if (ODD && m0 == Q - 2) c[i][3].y = 0.f;      // so is Im X[N/2]
                         pacc[i] += c[i][0].x - c[i][2].x;
                         racc[i] += c[i][1].y - c[i][3].y;
                         if (m0 == 0) pacc[i] -= 0.5f * c[i][0].x;
@@ -1352,10 +1368,15 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
 #pragma unroll 1
                 for (int c0 = o_begin; c0 < o_end; c0 += 8) {
                     uint32_t A[4][8], B[4][8];
+                    uint32_t XA[4] = {0u, 0u, 0u, 0u}, XB[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         tmem_ld8_nowait(tq + (uint32_t)(a * Q + c0), A[a]);
                         tmem_ld8_nowait(tq + (uint32_t)(a * Q + Q - c0 - 8), B[a]);
+                        if (ODD && c0 + 8 < Q) {       // one column of look-ahead on either side
+                            tmem_ld1_nowait(tq + (uint32_t)(a * Q + c0 + 8), &XA[a]);
+                            tmem_ld1_nowait(tq + (uint32_t)(a * Q + Q - c0 - 9), &XB[a]);
+                        }
                     }
                     tmem_ld_wait();
 #pragma unroll
@@ -1368,7 +1389,28 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                         float seg0 = (((ce + co) - (se + so)) * g0 + sg) * wa.x;
                         float seg2 = (((ce - co) - (se - so)) * g0 + sg) * wa.z;
                         float seg1, seg3;
-                        if (o == 0) {
+                        if (ODD) {
+                            // column Q-1-o -> position N/2 - n
+                            const float ce1 = __uint_as_float(B[0][7 - i]), co1 = __uint_as_float(B[1][7 - i]);
+                            const float se1 = __uint_as_float(B[2][7 - i]), so1 = __uint_as_float(B[3][7 - i]);
+                            seg1 = ((ce1 - co1) + (se1 - so1)) * g0 * wtab[Q - 1 - o].y;
+                            if (o == Q - 1) {          // position N - (Q-1): column Q-1 = A[.][7]
+                                seg2 = ((ce + co) + (se + so)) * g0 * wa.w;
+                                seg3 = 0.f;
+                            } else {
+                                const float ce2 = __uint_as_float(i < 7 ? A[0][(i + 1) & 7] : XA[0]);
+                                const float co2 = __uint_as_float(i < 7 ? A[1][(i + 1) & 7] : XA[1]);
+                                const float se2 = __uint_as_float(i < 7 ? A[2][(i + 1) & 7] : XA[2]);
+                                const float so2 = __uint_as_float(i < 7 ? A[3][(i + 1) & 7] : XA[3]);
+                                seg2 = ((ce2 - co2) - (se2 - so2)) * g0 * wtab[o + 1].z;
+                                // column Q-2-o -> position N - n (column 0 carries weight 0)
+                                const float ce3 = __uint_as_float(i < 7 ? B[0][(6 - i) & 7] : XB[0]);
+                                const float co3 = __uint_as_float(i < 7 ? B[1][(6 - i) & 7] : XB[1]);
+                                const float se3 = __uint_as_float(i < 7 ? B[2][(6 - i) & 7] : XB[2]);
+                                const float so3 = __uint_as_float(i < 7 ? B[3][(6 - i) & 7] : XB[3]);
+                                seg3 = ((ce3 + co3) + (se3 + so3)) * g0 * wtab[Q - 2 - o].w;
+                            }
+                        } else if (o == 0) {
                             seg1 = fq;
                             seg3 = f3q;
                         } else {
@@ -1474,6 +1516,7 @@ struct FoldPlan {
     float wq = 0.f, w3q = 0.f, wmax = 0.f;
     float wq_inv = 0.f, w3q_inv = 0.f;
     int q = 0, tmem_cols = 0;
+    int odd = 0;                 // n_fft = 4Q - 2 (see FoldFwdParams::odd)
     int hq = 0;                  // hop / Q when the fused overlap-add applies (1, 2, 4), else 0
     float* env_per = nullptr;    // hop: 1 / overlap-added w^2 for interior hop blocks
     int sm_count = 0;
@@ -1558,14 +1601,23 @@ int g_brv_fold_variant = 0;   // 0: by tile count, 2: one tile per CTA, 3: persi
 
 bool brv_fold_supported(const brv_stft_plan* p) { return p->fold != nullptr; }
 
+// the gradient entry points reuse the kernels with edge-bin weights that the n_fft = 4Q - 2
+// layout (k = N/2 inside the odd bins) does not carry: those plans differentiate on the generic path
+bool brv_fold_grad_supported(const brv_stft_plan* p) {
+    return p->fold != nullptr && !((const FoldPlan*)p->fold)->odd;
+}
+
 int brv_fold_plan_init(brv_stft_plan* p) {
     const int N = p->n_fft;
-    if (!p->onesided || N % 128 != 0 || N > 512) return BRV_OK;
+    // N = 4Q, or N = 4Q - 2 (SGMSE's 510): Q a multiple of the 32-wide k-chunk
+    const bool odd = N % 4 == 2 && (N + 2) % 128 == 0;
+    if (!p->onesided || !(N % 128 == 0 || odd) || N > 512) return BRV_OK;
     if (!encode_tiled()) return BRV_OK;
-    const int Q = N / 4, Hf = N / 2;
+    const int Q = (N + 2) / 4, Hf = N / 2;
     FoldPlan* fp = new FoldPlan();
     fp->q = Q;
-    fp->tmem_cols = N <= 128 ? 128 : (N <= 256 ? 256 : 512);
+    fp->odd = odd ? 1 : 0;
+    fp->tmem_cols = 4 * Q <= 128 ? 128 : (4 * Q <= 256 ? 256 : 512);
     int rc = build_fold_basis(&fp->fwd, Q, [&](int sub, int m, int n) {
         const long long k = (sub & 1) ? 2 * m + 1 : 2 * m;
         double c, s;
@@ -1582,8 +1634,8 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             wt[n].z = n ? (float)(p->window[Hf + n] / p->norm) : 0.f;
             wt[n].w = n ? (float)(p->window[N - n] / p->norm) : 0.f;
         }
-        fp->wq = (float)(p->window[Q] / p->norm);
-        fp->w3q = (float)(p->window[3 * Q] / p->norm);
+        fp->wq = odd ? 0.f : (float)(p->window[Q] / p->norm);
+        fp->w3q = odd ? 0.f : (float)(p->window[3 * Q] / p->norm);
         fp->wmax = (float)wmax;
         if (cudaMalloc((void**)&fp->wtab, Q * sizeof(float4)) != cudaSuccess ||
             cudaMemcpy(fp->wtab, wt.data(), Q * sizeof(float4), cudaMemcpyHostToDevice) !=
@@ -1603,8 +1655,8 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             wt[n].z = n ? (float)(p->window[Hf + n] * gs) : 0.f;
             wt[n].w = n ? (float)(p->window[N - n] * gs) : 0.f;
         }
-        fp->wq_g = (float)(p->window[Q] * gs);
-        fp->w3q_g = (float)(p->window[3 * Q] * gs);
+        fp->wq_g = odd ? 0.f : (float)(p->window[Q] * gs);
+        fp->w3q_g = odd ? 0.f : (float)(p->window[3 * Q] * gs);
         fp->wmax_g = (float)wmax;
         if (cudaMalloc((void**)&fp->wtab_grad, Q * sizeof(float4)) != cudaSuccess ||
             cudaMemcpy(fp->wtab_grad, wt.data(), Q * sizeof(float4), cudaMemcpyHostToDevice) !=
@@ -1632,7 +1684,7 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             const long long k = (sub & 1) ? 2 * m + 1 : 2 * m;
             double c, s;
             unit_root(k * n, N, &c, &s);
-            const double wk = (k == 0) ? 1.0 : 2.0;
+            const double wk = (k == 0 || 2 * k == N) ? 1.0 : 2.0;
             return wk * (sub < 2 ? c : s);
         });
     if (rc == BRV_OK) {
@@ -1644,8 +1696,8 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             wt[n].z = (float)(p->window[Hf + n] * gw);
             wt[n].w = n ? (float)(p->window[N - n] * gw) : 0.f;
         }
-        fp->wq_inv = (float)(p->window[Q] * gw);
-        fp->w3q_inv = (float)(p->window[3 * Q] * gw);
+        fp->wq_inv = odd ? 0.f : (float)(p->window[Q] * gw);
+        fp->w3q_inv = odd ? 0.f : (float)(p->window[3 * Q] * gw);
         // gradient of the forward transform: window / norm, and 1/2 against the basis' weight 2
         const double fg = 0.5 / p->norm;
         std::vector<float4> wf(Q);
@@ -1655,8 +1707,8 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             wf[n].z = (float)(p->window[Hf + n] * fg);
             wf[n].w = n ? (float)(p->window[N - n] * fg) : 0.f;
         }
-        fp->wq_fg = (float)(p->window[Q] * fg);
-        fp->w3q_fg = (float)(p->window[3 * Q] * fg);
+        fp->wq_fg = odd ? 0.f : (float)(p->window[Q] * fg);
+        fp->w3q_fg = odd ? 0.f : (float)(p->window[3 * Q] * fg);
         if (cudaMalloc((void**)&fp->wtab_fgrad, Q * sizeof(float4)) != cudaSuccess ||
             cudaMemcpy(fp->wtab_fgrad, wf.data(), Q * sizeof(float4), cudaMemcpyHostToDevice) !=
                 cudaSuccess)
@@ -1666,7 +1718,7 @@ int brv_fold_plan_init(brv_stft_plan* p) {
                 cudaSuccess)
             rc = brv_fail_cuda(cudaGetLastError(), "folded inverse window table");
         const int H = p->hop;
-        if (H == Q || H == 2 * Q || H == 4 * Q)
+        if (H == Q || (!odd && (H == 2 * Q || H == 4 * Q)))
             if ((size_t)TILE_M * (H + 1) * sizeof(float) <= (size_t)INV_REGION && H <= 256)
                 fp->hq = H / Q;
     }
@@ -1688,7 +1740,9 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             rc = brv_fail_cuda(cudaGetLastError(), "cudaDeviceGetAttribute(SM count)");
     }
     if (rc == BRV_OK) {
-        const void* kernels[12] = {
+        const void* kernels[16] = {
+            (const void*)istft_fold_kernel<1, false, false, true>, (const void*)istft_fold_kernel<1, true, false, true>,
+            (const void*)istft_fold_kernel<1, false, true, true>, (const void*)istft_fold_kernel<1, true, true, true>,
             (const void*)istft_fold_kernel<1, false, false>, (const void*)istft_fold_kernel<1, true, false>,
             (const void*)istft_fold_kernel<2, false, false>, (const void*)istft_fold_kernel<2, true, false>,
             (const void*)istft_fold_kernel<4, false, false>, (const void*)istft_fold_kernel<4, true, false>,
@@ -1721,7 +1775,10 @@ static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool c
     prm.hop = p->hop;
     prm.n_bins = p->n_bins;
     prm.q = fp->q;
-    int rows = (SPAN_MAX - p->n_fft) / p->hop + 1;
+    prm.odd = fp->odd;
+    // 16-byte aligned span when the hop allows it (n_fft / 2 = 255 would otherwise force scalar loads)
+    prm.shift = p->hop % 4 == 0 ? (4 - ((p->n_fft / 2) & 3)) & 3 : 0;
+    int rows = (SPAN_MAX - p->n_fft - prm.shift) / p->hop + 1;
     if (rows > TILE_M) rows = TILE_M;
     if (rows > n_frames) rows = (int)n_frames;
     prm.rows = rows;
@@ -1843,6 +1900,16 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
         else                                                                                      \
             istft_fold_kernel<HQ_, FF_, false><<<grid, INV_THREADS, INV_SMEM_BYTES, st>>>(fp->inv.map, prm); \
     } while (0)
+#define BRV_LAUNCH_INV_ODD(FF_)                                                                   \
+    do {                                                                                          \
+        if (decomp)                                                                               \
+            istft_fold_kernel<1, FF_, true, true><<<grid, INV_THREADS, INV_SMEM_BYTES, st>>>(fp->inv.map, prm); \
+        else                                                                                      \
+            istft_fold_kernel<1, FF_, false, true><<<grid, INV_THREADS, INV_SMEM_BYTES, st>>>(fp->inv.map, prm); \
+    } while (0)
+    if (fp->odd) {
+        if (frames_fast) BRV_LAUNCH_INV_ODD(true); else BRV_LAUNCH_INV_ODD(false);
+    } else
     switch (fp->hq * 2 + (frames_fast ? 1 : 0)) {
         case 2: BRV_LAUNCH_INV(1, false); break;
         case 3: BRV_LAUNCH_INV(1, true); break;
@@ -1852,6 +1919,7 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
         default: BRV_LAUNCH_INV(4, true); break;
     }
 #undef BRV_LAUNCH_INV
+#undef BRV_LAUNCH_INV_ODD
     BRV_LAUNCH_CHECK("istft_fold_kernel");
     return BRV_OK;
 }

@@ -145,14 +145,21 @@ __device__ __forceinline__ float finite_abs(float v) {       // |v|, or 0 for in
     return a <= 3.0e38f ? a : 0.f;
 }
 // X * |X|^expo for a complex value (expo = c - 1 or 1/c - 1); 0 stays 0
+// The two exponents SGMSE's compression_factor = 0.5 produces (c - 1 = -1/2 forward,
+// 1/c - 1 = 1 inverse) avoid powf: |X|^-1/2 = rsqrt(sqrt(|X|^2)), |X|^1 = sqrt(|X|^2).
+__device__ __forceinline__ float pow_half_expo(float m2, float expo) {
+    if (expo == -0.5f) return rsqrtf(sqrtf(m2));
+    if (expo == 1.f) return sqrtf(m2);
+    return powf(m2, 0.5f * expo);
+}
 __device__ __forceinline__ void compress(float& re, float& im, float expo) {
     const float m2 = re * re + im * im;
-    const float g = m2 > 0.f ? powf(m2, 0.5f * expo) : 0.f;
+    const float g = m2 > 0.f ? pow_half_expo(m2, expo) : 0.f;
     re *= g;
     im *= g;
 }
 __device__ __forceinline__ float compress_real(float v, float expo) {
-    return v != 0.f ? v * powf(fabsf(v), expo) : 0.f;
+    return v != 0.f ? v * pow_half_expo(v * v, expo) : 0.f;
 }
 
 

@@ -82,7 +82,13 @@ def test_tensorcore_forward_matches_generic_and_oracle(kw, samples, capsys):
                                 dict(frame_length=256, hop_length=128, normalized=False),
                                 dict(frame_length=128, hop_length=32),
                                 dict(frame_length=384, hop_length=96, compression_factor=0.5,
-                                     scale_factor=0.15)])
+                                     scale_factor=0.15),
+                                # n_fft = 4Q - 2: no Nyquist bin, no n = Q column, unaligned centre pad
+                                dict(frame_length=510, hop_length=128, normalized=False,
+                                     compression_factor=0.5, scale_factor=0.15),
+                                dict(frame_length=510, hop_length=128),
+                                dict(frame_length=254, hop_length=64, window='hamming'),
+                                dict(frame_length=200, hop_length=50, n_fft=254)])
 @pytest.mark.parametrize('shape', [(1, 100), (3, 4097), (400, 20000), (37, 64000)])
 def test_pipelined_forward_matches_single_tile_kernel_and_oracle(kw, shape):
     """The persistent two-pass forward (several tiles per CTA, TMEM halves handed back
@@ -290,6 +296,11 @@ FOLD_INV_CASES = [
     dict(frame_length=400, hop_length=128, n_fft=512),            # window shorter than n_fft
     dict(frame_length=512, hop_length=128, compression_factor=0.5, scale_factor=0.15,
          normalized=False),                                        # SGMSE-style decompression
+    dict(frame_length=510, hop_length=128, compression_factor=0.5, scale_factor=0.15,
+         normalized=False),                                        # SGMSE (cfg4): n_fft = 4Q - 2
+    dict(frame_length=510, hop_length=128),
+    dict(frame_length=254, hop_length=64, window='hamming'),
+    dict(frame_length=126, hop_length=32, normalized=False),
 ]
 
 
