@@ -46,6 +46,11 @@ PROTOTYPES = {
     'brv_fbe_features': (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _int, _int,
                                 _i64, _ptr, _ptr, _ptr, _int, _int, _int, _int,
                                 _f32, _int, _int, _ptr, _ptr, _ptr, _ptr]),
+    'brv_mel_features': (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _int, _int,
+                                _i64, _int, _ptr, _ptr, _ptr, _int, _int, _int,
+                                _int, _f32, _ptr, _int, _ptr, _ptr]),
+    'brv_ic_coherence': (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _int, _int,
+                                _i64, _f32, _f32, _ptr, _ptr]),
     'brv_stack_normalize': (_int, [_ptr, _i64, _int, _i64, _int, _int, _ptr,
                                    _ptr, _ptr, _ptr]),
     'brv_cumulative_normalize': (_int, [_ptr, _i64, _i64, _f32, _ptr, _ptr]),

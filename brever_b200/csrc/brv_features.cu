@@ -6,6 +6,11 @@
 // brever/modules/features.py:186-198 (FeatureExtractor.fbe),
 // brever/models/ffnn/ffnn.py:122-135,175-203 (stack, decimate, normalisers).
 //
+// The same kernel also produces the binaural cues (features.py:222-296: ild, ipd read both
+// channels in phase 1; ic arrives as a real per-bin coherence from ic_coherence_kernel) and
+// the DCT features (features.py:199-219: mfcc, cubicmfcc, pdfcc = DCT-II of the compressed
+// energies, coefficients 1..13, plus first / second frame differences).
+//
 // The kernel is HBM-bound: per frame it reads C*F complex bins once (8 B each)
 // and writes n_mel*(stacks+1) floats.  The mel matrix is 97 % zeros (<= 2
 // filters per bin), so it is applied as a CSR gather from a shared-memory
@@ -16,6 +21,7 @@ namespace {
 
 constexpr int FT_THREADS = 256;
 constexpr int FT_MAX_STACK = 32;
+enum { FT_MODE_POWER = 0, FT_MODE_ILD = 1, FT_MODE_IPD = 2, FT_MODE_REAL = 3 };
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -39,10 +45,12 @@ fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_
                     const int32_t* __restrict__ mel_rowptr, int n_mel, int nnz, int normalize,
                     int compression, float eps, int stacks, int decimation,
                     const float* __restrict__ mean, const float* __restrict__ stdv,
-                    float* __restrict__ out, int64_t out_frames, int tile, int tiles_per_item) {
+                    float* __restrict__ out, int64_t out_frames, int tile, int tiles_per_item,
+                    int mode, const float* __restrict__ dct_basis, int n_dct) {
     extern __shared__ float smem[];
     const int warps = FT_THREADS / 32;
-    const int staged = tile + stacks;
+    const int ctx = n_dct ? 2 : stacks;                    // frames of left context staged
+    const int staged = tile + ctx;
     const int ldP = n_bins | 1;                            // odd pitch: frames hit distinct banks
     const int ldE = n_mel + 1;
     float* vals = smem;
@@ -54,7 +62,7 @@ fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_
     const int64_t b = blockIdx.x / tiles_per_item;
     const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_item) * tile;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int64_t first = t0 - stacks;                     // first frame staged (may be < 0)
+    const int64_t first = t0 - ctx;                        // first frame staged (may be < 0)
     const float inv_c = 1.f / (float)C;
 
     for (int j = threadIdx.x; j < nnz; j += FT_THREADS) {
@@ -63,9 +71,39 @@ fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_
     }
     for (int j = threadIdx.x; j <= n_mel; j += FT_THREADS) rowptr[j] = __ldg(mel_rowptr + j);
 
-    // ---- phase 1: power spectrum, channel mean (features.py:186-188) ----
+    // ---- phase 1: per-bin quantity -> power[staged][n_bins] ----
     const float2* xb = X + b * sb;
-    if (sf <= st) {
+    if (mode == FT_MODE_REAL) {
+        // a real (frames, bins) map computed upstream (interaural coherence): strides in floats
+        const float* rb = reinterpret_cast<const float*>(X) + b * sb;
+        for (int s = warp; s < staged; s += warps) {
+            const int64_t t = first + s;
+            if (t < 0 || t >= n_frames) continue;
+            for (int f = lane; f < n_bins; f += 32)
+                power[(size_t)s * ldP + f] = __ldg(rb + t * st + (int64_t)f * sf);
+        }
+    } else if (mode != FT_MODE_POWER) {
+        // ild: 20 log10((|R| + eps) / (|L| + eps)), features.py:238-239
+        // ipd: angle(R) - angle(L), features.py:258-259          (L = channel 0, R = channel 1)
+        const bool bins_fast = sf <= st;
+        const int n_outer = bins_fast ? staged : n_bins, n_inner = bins_fast ? n_bins : staged;
+        for (int o = warp; o < n_outer; o += warps) {
+            for (int i = lane; i < n_inner; i += 32) {
+                const int s = bins_fast ? o : i, f = bins_fast ? i : o;
+                const int64_t t = first + s;
+                if (t < 0 || t >= n_frames) continue;
+                const float2 l = __ldg(xb + (int64_t)f * sf + t * st);
+                const float2 r = __ldg(xb + sc + (int64_t)f * sf + t * st);
+                float v;
+                if (mode == FT_MODE_ILD)
+                    v = 20.f * log10f((hypotf(r.x, r.y) + eps) / (hypotf(l.x, l.y) + eps));
+                else
+                    v = atan2f(r.y, r.x) - atan2f(l.y, l.x);
+                power[(size_t)s * ldP + f] = v;
+            }
+        }
+    } else if (sf <= st) {
+        // power spectrum, channel mean (features.py:186-188)
         // bins contiguous (frame-major spectrogram, what STFT.forward returns): lanes along bins
         for (int s = warp; s < staged; s += warps) {
             const int64_t t = first + s;
@@ -136,10 +174,43 @@ fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_
         for (int idx = threadIdx.x; idx < staged * n_mel; idx += FT_THREADS) {
             const int s = idx / n_mel, m = idx - s * n_mel;
             float e = energy[s * ldE + m];
-            e = compression == 1 ? logf(e + eps) : cbrtf(e);
+            e = compression == 1 ? logf(e + eps) : (compression == 2 ? cbrtf(e) : sqrtf(e));
             energy[s * ldE + m] = e;
         }
         __syncthreads();
+    }
+
+    if (n_dct) {
+        // ---- DCT-II (ortho) coefficients 1..n_dct of every staged frame, then
+        //      out[b, k] = cc[k, t], out[b, n_dct + k] = cc[k, t] - cc[k, t-1] (0 for t < 1),
+        //      out[b, 2 n_dct + k] = cc[k, t] - 2 cc[k, t-1] + cc[k, t-2] (0 for t < 2)
+        //      (scipy.fft.dct + np.diff + left zero pad, features.py:201-215) ----
+        float* cc = power;                                 // the power rows are dead by now
+        const int ldC = n_dct + 1;
+        for (int idx = threadIdx.x; idx < staged * n_dct; idx += FT_THREADS) {
+            const int s = idx / n_dct, k = idx - s * n_dct;
+            const int64_t t = first + s;
+            float acc = 0.f;
+            if (t >= 0 && t < n_frames)
+                for (int m = 0; m < n_mel; ++m)
+                    acc = fmaf(__ldg(dct_basis + k * n_mel + m), energy[s * ldE + m], acc);
+            cc[s * ldC + k] = acc;
+        }
+        __syncthreads();
+        int64_t t_end = t0 + tile < n_frames ? t0 + tile : n_frames;
+        const int width = (int)(t_end - t0);
+        for (int idx = threadIdx.x; idx < 3 * n_dct * width; idx += FT_THREADS) {
+            const int r = idx / width, w = idx - r * width;
+            const int order = r / n_dct, k = r - order * n_dct;
+            const int64_t t = t0 + w;
+            const int s = w + ctx;
+            float v = cc[s * ldC + k];
+            if (order == 1) v = t >= 1 ? v - cc[(s - 1) * ldC + k] : 0.f;
+            if (order == 2)
+                v = t >= 2 ? v - 2.f * cc[(s - 1) * ldC + k] + cc[(s - 2) * ldC + k] : 0.f;
+            out[(b * 3 * n_dct + r) * n_frames + t] = v;
+        }
+        return;
     }
 
     // ---- phase 4: out[b, k*n_mel + m, t/dec] = (E[m, max(t - k, 0)] - mean) / std ----
@@ -230,17 +301,64 @@ __global__ void cumulative_normalize_kernel(const float* __restrict__ x, int64_t
     }
 }
 
+// Interaural coherence before the mel projection (features.py:262-296): one thread per
+// (batch item, bin) walks the frames with the four recursions
+//   phi[t] = (1 - alpha) x[t] + alpha phi[t-1],  x in {|L|^2, |R|^2, Re L conj(R), Im L conj(R)}
+// (torchaudio.functional.lfilter, a = [1, -alpha], b = [1 - alpha, 0]); the filter OUTPUT is
+// clamped to [-1, 1] (lfilter's default clamp=True) and coh = |phi_lr|^2 / (phi_ll phi_rr).
+// Loads of IC_UNROLL frames are issued together; out is (B, T, F) float, bins contiguous.
+constexpr int IC_UNROLL = 8;
+__global__ void __launch_bounds__(128)
+ic_coherence_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_t sf, int64_t st,
+                    int n_bins, int64_t n_frames, float b0, float a1, float* __restrict__ out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    if (f >= n_bins) return;
+    const float2* xl = X + b * sb + (int64_t)f * sf;
+    const float2* xr = xl + sc;
+    float* o = out + b * n_frames * n_bins + f;
+    float ll = 0.f, rr = 0.f, cre = 0.f, cim = 0.f;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += IC_UNROLL) {
+        float2 l[IC_UNROLL], r[IC_UNROLL];
+#pragma unroll
+        for (int u = 0; u < IC_UNROLL; ++u) {
+            const bool ok = t0 + u < n_frames;
+            l[u] = ok ? __ldg(xl + (t0 + u) * st) : make_float2(0.f, 0.f);
+            r[u] = ok ? __ldg(xr + (t0 + u) * st) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < IC_UNROLL; ++u) {
+            if (t0 + u >= n_frames) break;
+            ll = fmaf(b0, l[u].x * l[u].x + l[u].y * l[u].y, -a1 * ll);
+            rr = fmaf(b0, r[u].x * r[u].x + r[u].y * r[u].y, -a1 * rr);
+            cre = fmaf(b0, l[u].x * r[u].x + l[u].y * r[u].y, -a1 * cre);
+            cim = fmaf(b0, l[u].y * r[u].x - l[u].x * r[u].y, -a1 * cim);
+            const float cl = fminf(fmaxf(ll, -1.f), 1.f), cr = fminf(fmaxf(rr, -1.f), 1.f);
+            const float cx = fminf(fmaxf(cre, -1.f), 1.f), cy = fminf(fmaxf(cim, -1.f), 1.f);
+            o[(t0 + u) * n_bins] = (cx * cx + cy * cy) / (cl * cr);
+        }
+    }
+}
+
 }  // namespace
 
-extern "C" int brv_fbe_features(const void* X, int64_t sb, int64_t sc, int64_t sf, int64_t st,
-                                int64_t n_batch, int n_channels, int n_bins, int64_t n_frames,
-                                const float* mel_vals, const int32_t* mel_cols,
-                                const int32_t* mel_rowptr, int n_mel, int nnz, int normalize,
-                                int compression, float eps, int stacks, int decimation,
-                                const float* mean, const float* stdv, float* out, void* stream) {
+static int launch_features(const void* X, int64_t sb, int64_t sc, int64_t sf, int64_t st,
+                           int64_t n_batch, int n_channels, int n_bins, int64_t n_frames,
+                           const float* mel_vals, const int32_t* mel_cols,
+                           const int32_t* mel_rowptr, int n_mel, int nnz, int normalize,
+                           int compression, float eps, int stacks, int decimation,
+                           const float* mean, const float* stdv, float* out, void* stream,
+                           int mode, const float* dct_basis, int n_dct) {
     BRV_REQUIRE(X && mel_vals && mel_cols && mel_rowptr && out, "null pointer argument");
     BRV_REQUIRE(n_channels >= 1 && n_bins >= 1 && n_mel >= 1, "bad feature dimensions");
-    BRV_REQUIRE(compression >= 0 && compression <= 2, "compression must be 0 (none), 1 (log) or 2 (cubic)");
+    BRV_REQUIRE(compression >= 0 && compression <= 3,
+                "compression must be 0 (none), 1 (log), 2 (cubic) or 3 (square root)");
+    BRV_REQUIRE(mode >= FT_MODE_POWER && mode <= FT_MODE_REAL, "unknown feature mode %d", mode);
+    BRV_REQUIRE((mode != FT_MODE_ILD && mode != FT_MODE_IPD) || n_channels >= 2,
+                "interaural features need two channels, got %d", n_channels);
+    BRV_REQUIRE(n_dct >= 0 && n_dct <= n_mel && (n_dct == 0 || dct_basis), "bad DCT arguments");
+    BRV_REQUIRE(n_dct == 0 || (stacks == 0 && decimation == 1 && !mean && !stdv),
+                "the DCT features are not fused with stacking / decimation / normalisation");
     BRV_REQUIRE(stacks >= 0 && stacks <= FT_MAX_STACK, "stacks must be in [0, %d]", FT_MAX_STACK);
     BRV_REQUIRE(decimation >= 1, "decimation must be >= 1");
     if (n_batch == 0 || n_frames == 0) return BRV_OK;
@@ -255,7 +373,7 @@ extern "C" int brv_fbe_features(const void* X, int64_t sb, int64_t sc, int64_t s
     const int64_t grid = n_batch * tiles;
     BRV_REQUIRE(grid < (1LL << 31), "too many feature tiles");
     BRV_REQUIRE(nnz >= 0 && nnz <= n_mel * n_bins, "bad CSR row pointer");
-    const int staged = tile + stacks;
+    const int staged = tile + (n_dct ? 2 : stacks);
     size_t smem = ((size_t)2 * nnz + n_mel + 1 + (size_t)staged * (n_bins | 1) +
                    (size_t)staged * (n_mel + 1)) * sizeof(float);
     BRV_REQUIRE(smem <= 200 * 1024, "feature tile does not fit shared memory (%zu bytes)", smem);
@@ -264,8 +382,45 @@ extern "C" int brv_fbe_features(const void* X, int64_t sb, int64_t sc, int64_t s
     fbe_features_kernel<<<(unsigned)grid, FT_THREADS, smem, (cudaStream_t)stream>>>(
         (const float2*)X, sb, sc, sf, st, n_channels, n_bins, n_frames, mel_vals, mel_cols,
         mel_rowptr, n_mel, nnz, normalize, compression, eps, stacks, decimation, mean, stdv, out,
-        out_frames, tile, tiles);
+        out_frames, tile, tiles, mode, dct_basis, n_dct);
     BRV_LAUNCH_CHECK("fbe_features_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_fbe_features(const void* X, int64_t sb, int64_t sc, int64_t sf, int64_t st,
+                                int64_t n_batch, int n_channels, int n_bins, int64_t n_frames,
+                                const float* mel_vals, const int32_t* mel_cols,
+                                const int32_t* mel_rowptr, int n_mel, int nnz, int normalize,
+                                int compression, float eps, int stacks, int decimation,
+                                const float* mean, const float* stdv, float* out, void* stream) {
+    return launch_features(X, sb, sc, sf, st, n_batch, n_channels, n_bins, n_frames, mel_vals,
+                           mel_cols, mel_rowptr, n_mel, nnz, normalize, compression, eps, stacks,
+                           decimation, mean, stdv, out, stream, FT_MODE_POWER, nullptr, 0);
+}
+
+extern "C" int brv_mel_features(const void* X, int64_t sb, int64_t sc, int64_t sf, int64_t st,
+                                int64_t n_batch, int n_channels, int n_bins, int64_t n_frames,
+                                int mode, const float* mel_vals, const int32_t* mel_cols,
+                                const int32_t* mel_rowptr, int n_mel, int nnz, int normalize,
+                                int compression, float eps, const float* dct_basis, int n_dct,
+                                float* out, void* stream) {
+    return launch_features(X, sb, sc, sf, st, n_batch, n_channels, n_bins, n_frames, mel_vals,
+                           mel_cols, mel_rowptr, n_mel, nnz, normalize, compression, eps, 0, 1,
+                           nullptr, nullptr, out, stream, mode, dct_basis, n_dct);
+}
+
+extern "C" int brv_ic_coherence(const void* X, int64_t sb, int64_t sc, int64_t sf, int64_t st,
+                                int64_t n_batch, int n_channels, int n_bins, int64_t n_frames,
+                                float b0, float a1, float* out, void* stream) {
+    BRV_REQUIRE(X && out, "null pointer argument");
+    BRV_REQUIRE(n_channels >= 2, "interaural coherence needs two channels, got %d", n_channels);
+    BRV_REQUIRE(n_bins >= 1 && n_batch < 65536, "bad shape");
+    if (n_batch == 0 || n_frames == 0) return BRV_OK;
+    // b0 = float32(1 - alpha), a1 = float32(-alpha): the coefficients the reference hands to lfilter
+    dim3 grid((unsigned)brv_ceil_div(n_bins, 128), (unsigned)n_batch);
+    ic_coherence_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)X, sb, sc, sf, st,
+                                                               n_bins, n_frames, b0, a1, out);
+    BRV_LAUNCH_CHECK("ic_coherence_kernel");
     return BRV_OK;
 }
 

@@ -157,6 +157,40 @@ int brv_fbe_features(const void* X, int64_t stride_b, int64_t stride_c,
                      int decimation, const float* mean, const float* std,
                      float* out, void* stream);
 
+/* ---- the other FeatureExtractor features (features.py:199-296) --------------
+ * The same one-pass kernel with a selectable per-bin quantity and an optional
+ * DCT stage; replaces FeatureExtractor.ild / .ipd / .ic and the dct=True branch
+ * of .fbe (mfcc, cubicmfcc, pdfcc):
+ *   mode 0  P = mean_c |X|^2                               (fbe family, as above)
+ *   mode 1  P = 20 log10((|X[:,1]| + eps) / (|X[:,0]| + eps))   ild, features.py:238-240
+ *   mode 2  P = angle(X[:,1]) - angle(X[:,0])                   ipd, features.py:258-260
+ *   mode 3  P = X read as a real (B, T, F) map, strides in floats (n_channels = 1):
+ *           the interaural coherence from brv_ic_coherence, then compression 3
+ *           (square root) gives ic, features.py:295-296
+ *   E = mel(P), normalize / compression as in brv_fbe_features (compression 3 = sqrt).
+ *   n_dct > 0: cc[k] = sum_m dct_basis[k, m] E[m] (k < n_dct; the caller passes rows
+ *   1..13 of the orthonormal DCT-II matrix, scipy.fft.dct(type=2, norm='ortho'),
+ *   features.py:201-206) and out is (B, 3*n_dct, T) = [cc | first difference |
+ *   second difference along frames], differences zero-padded on the left
+ *   (features.py:207-215).  n_dct == 0: out is (B, n_mel, T).                  */
+int brv_mel_features(const void* X, int64_t stride_b, int64_t stride_c,
+                     int64_t stride_f, int64_t stride_t, int64_t n_batch,
+                     int n_channels, int n_bins, int64_t n_frames, int mode,
+                     const float* mel_vals, const int32_t* mel_cols,
+                     const int32_t* mel_rowptr, int n_mel, int mel_nnz,
+                     int normalize, int compression, float eps,
+                     const float* dct_basis, int n_dct, float* out, void* stream);
+
+/* Interaural coherence before the mel projection (FeatureExtractor.ic,
+ * features.py:286-295): exponentially weighted auto / cross power spectra
+ * phi[t] = b0 x[t] - a1 phi[t-1] along frames (torchaudio lfilter with
+ * a = [1, a1 = -alpha], b = [b0 = 1 - alpha, 0], output clamped to [-1, 1]),
+ * out[b, t, f] = |phi_lr|^2 / (phi_ll phi_rr), float32 (B, T, F) contiguous.  */
+int brv_ic_coherence(const void* X, int64_t stride_b, int64_t stride_c,
+                     int64_t stride_f, int64_t stride_t, int64_t n_batch,
+                     int n_channels, int n_bins, int64_t n_frames, float b0,
+                     float a1, float* out, void* stream);
+
 /* FFNN.stack + decimate + StaticNormalizer on an existing feature tensor
  * (ffnn.py:122-135,186-187): x (B, nf, T) contiguous -> (B, nf*(stacks+1), T'). */
 int brv_stack_normalize(const float* x, int64_t n_batch, int n_features,

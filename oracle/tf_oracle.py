@@ -278,6 +278,90 @@ def fbe(spec, filters, normalize=False, compression='none'):
     return out[0] if unbatched else out
 
 
+def dct_features(energies, n_dct=14):
+    """DCT branch of FeatureExtractor.fbe, features.py:199-219 (defaults: type 2, ortho,
+    no DC term, deltas and double deltas): ``(B, M, T)`` -> ``(B, 3*(n_dct-1), T)``.
+
+    scipy.fft.dct(type=2, norm='ortho') along the filter axis:
+    ``y[k] = s_k * sum_n x[n] cos(pi k (2n+1) / (2M))``, ``s_0 = sqrt(1/M)``, ``s_k = sqrt(2/M)``;
+    coefficients 1..n_dct-1 are kept (features.py:205-206).  Deltas are first / second
+    differences along frames, zero-padded on the left (features.py:208-215).
+    """
+    x = np.asarray(energies, dtype=np.float64)
+    m = x.shape[1]
+    k = np.arange(1, n_dct)[:, None]
+    n = np.arange(m)[None, :]
+    basis = math.sqrt(2.0 / m) * np.cos(math.pi * k * (2 * n + 1) / (2 * m))
+    cc = np.einsum('km,bmt->bkt', basis, x)
+    d1 = np.zeros_like(cc)
+    d1[..., 1:] = cc[..., 1:] - cc[..., :-1]
+    d2 = np.zeros_like(cc)
+    d2[..., 2:] = cc[..., 2:] - 2 * cc[..., 1:-1] + cc[..., :-2]
+    return np.concatenate([cc, d1, d2], axis=1)
+
+
+def _batched(spec):
+    spec = np.asarray(spec).astype(np.complex128)
+    unbatched = spec.ndim == 3
+    if unbatched:
+        spec = spec[None]
+    if spec.ndim != 4:
+        raise ValueError(f'input must be 3 or 4 dimensional, got {spec.ndim}')
+    return spec, unbatched
+
+
+def ild(spec, filters):
+    """FeatureExtractor.ild, features.py:222-240: mel(20 log10((|R|+eps)/(|L|+eps)))."""
+    spec, unbatched = _batched(spec)
+    mag = np.abs(spec)
+    out = mel_forward(filters, 20 * np.log10((mag[:, 1] + EPS32) / (mag[:, 0] + EPS32)))
+    return out[0] if unbatched else out
+
+
+def ipd(spec, filters):
+    """FeatureExtractor.ipd, features.py:242-260: mel(angle(R) - angle(L)), not wrapped."""
+    spec, unbatched = _batched(spec)
+    phase = np.angle(spec)
+    out = mel_forward(filters, phase[:, 1] - phase[:, 0])
+    return out[0] if unbatched else out
+
+
+def ic(spec, filters, hop_length=256, fs=16e3, tau=10e-3):
+    """FeatureExtractor.ic, features.py:262-296.
+
+    Auto / cross power spectra smoothed along frames by ``y[t] = (1-a) x[t] + a y[t-1]``,
+    ``a = exp(-hop / (tau fs))`` (torchaudio.functional.lfilter with float32 coefficients,
+    whose default ``clamp=True`` clips the *output* to [-1, 1]); coherence
+    ``|phi_lr|^2 / (phi_ll phi_rr)``, mel projection, square root.
+    """
+    spec, unbatched = _batched(spec)
+    alpha = math.exp(-hop_length / (tau * fs))
+    a1 = float(np.float32(-alpha))             # a_coeffs = [1, -alpha], float32
+    b0 = float(np.float32(1 - alpha))          # b_coeffs = [1 - alpha, 0]
+    left, right = spec[:, 0], spec[:, 1]
+    cross = left * np.conj(right)              # |L||R| exp(j(phase_L - phase_R))
+    x = np.stack([np.abs(left) ** 2, np.abs(right) ** 2, cross.real, cross.imag])
+    phi = np.zeros_like(x)
+    prev = np.zeros(x.shape[:-1])
+    for t in range(x.shape[-1]):
+        prev = b0 * x[..., t] - a1 * prev
+        phi[..., t] = prev
+    phi = np.clip(phi, -1.0, 1.0)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        coh = (phi[2] ** 2 + phi[3] ** 2) / (phi[0] * phi[1])
+    out = np.sqrt(mel_forward(filters, coh))
+    return out[0] if unbatched else out
+
+
+DCT_FAMILY = {
+    'mfcc': dict(compression='log'),
+    'cubicmfcc': dict(compression='cubic'),
+    'pdfcc': dict(normalize=True, compression='log'),
+}
+# rows the reference *declares* per feature (features.py:21-101); the DCT features declare 13
+# but return 39 (deltas and double deltas are on by default) — quirk kept
+DECLARED_ROWS = {'mfcc': 13, 'cubicmfcc': 13, 'pdfcc': 13}
+
 FBE_FAMILY = {
     'fbe': dict(),
     'logfbe': dict(compression='log'),
@@ -288,13 +372,23 @@ FBE_FAMILY = {
 }
 
 
-def extract_features(spec, filters, features):
+def extract_features(spec, filters, features, hop_length=256, fs=16e3):
     """FeatureExtractor.__call__, features.py:103-113: sorted names, cat on dim 0."""
     out, indices, start = [], {}, 0
     for name in sorted(features):
-        if name not in FBE_FAMILY:
+        if name in FBE_FAMILY:
+            data = fbe(spec, filters, **FBE_FAMILY[name])
+        elif name in DCT_FAMILY:
+            unbatched = np.asarray(spec).ndim == 3
+            e = fbe(spec, filters, **DCT_FAMILY[name])
+            data = dct_features(e[None] if unbatched else e)
+            data = data[0] if unbatched else data
+        elif name in ('ild', 'ipd'):
+            data = {'ild': ild, 'ipd': ipd}[name](spec, filters)
+        elif name == 'ic':
+            data = ic(spec, filters, hop_length=hop_length, fs=fs)
+        else:
             raise ValueError(f'unrecognized feature, got {name}')
-        data = fbe(spec, filters, **FBE_FAMILY[name])
         out.append(data)
         indices[name] = (start, start + len(data))
         start += len(data)

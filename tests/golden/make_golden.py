@@ -141,6 +141,20 @@ def main():
         fe = FeatureExtractor(features=[name], mel_fb=fb)
         out[f'feat_u_{name}'] = fe(spec_u).numpy()
         out[f'feat_b_{name}'] = fe(spec_b).numpy()
+    # binaural cues and DCT features (features.py:203-296, :199-219); the 0.1x copies keep the
+    # recursive IC spectra below torchaudio.lfilter's default clamp to [-1, 1]
+    for name in ['ild', 'ipd', 'ic', 'mfcc', 'cubicmfcc', 'pdfcc']:
+        fe = FeatureExtractor(features=[name], mel_fb=fb)
+        out[f'feat_u_{name}'] = fe(spec_u).numpy()
+        out[f'feat_b_{name}'] = fe(spec_b).numpy()
+        out[f'feat_bs_{name}'] = fe(0.1 * spec_b).numpy()
+    fe = FeatureExtractor(features=['ic'], mel_fb=fb, hop_length=64)
+    out['feat_bs_ic_hop64'] = fe(0.1 * spec_b).numpy()
+    fe = FeatureExtractor(features=['mfcc', 'ild', 'logfbe', 'ic', 'ipd'], mel_fb=fb)
+    out['feat_multi2_u'] = fe(spec_u).numpy()
+    out['feat_multi2_u_idx'] = np.array(
+        [fe.indices[k] for k in sorted(fe.indices)], dtype=np.int64)
+    out['feat_multi2_n_features'] = np.array([fe.n_features], dtype=np.int64)
     fe = FeatureExtractor(features=['logfbe', 'fbe', 'cubicpdf'], mel_fb=fb)
     out['feat_multi_u'] = fe(spec_u).numpy()
     out['feat_multi_u_idx'] = np.array(
@@ -248,7 +262,12 @@ def main():
             (crit(e, ref, lengths) * weight).sum().backward()
             out[f'crit_mry_{name}_grad'] = e.grad.numpy()
 
-    np.savez_compressed(os.path.join(HERE, 'reference_vectors.npz'), **out)
+    path = os.path.join(HERE, 'reference_vectors.npz')
+    if os.path.exists(path):      # regenerating must not move any vector already committed
+        prev = np.load(path)
+        moved = [k for k in prev.files if k not in out or not np.array_equal(prev[k], out[k], equal_nan=True)]
+        print('arrays that differ from the committed file:', moved or 'none')
+    np.savez_compressed(path, **out)
     total = sum(v.nbytes for v in out.values())
     print(f'wrote {len(out)} arrays, {total / 1e6:.2f} MB raw')
 

@@ -292,10 +292,62 @@ def test_feature_concat_quirk_and_errors():
     assert_parity(cpu(out), g['feat_multi_b'], TOL)
     assert [fe.indices[k] for k in sorted(fe.indices)] == \
         [tuple(r) for r in g['feat_multi_b_idx']]
-    with pytest.raises(NotImplementedError):
-        brv.FeatureExtractor(['ild'], fb)(su.to(DEV))
     with pytest.raises(ValueError):
         brv.FeatureExtractor(['nope'], fb)(su.to(DEV))
+
+
+@pytest.mark.parametrize('name', ['ild', 'ipd', 'ic', 'mfcc', 'cubicmfcc', 'pdfcc'])
+def test_binaural_and_dct_feature_values(name):
+    """features.py:199-296: interaural level / phase difference, coherence (recursive spectra
+    along frames, lfilter clamp included) and the DCT features with their deltas, against
+    outputs of the reference itself and the float64 oracle."""
+    g = golden()
+    fb = brv.MelFilterbank()
+    fe = brv.FeatureExtractor([name], fb)
+    su, sb = crandn((2, 257, 30), 400), crandn((4, 2, 257, 30), 401)
+    rows = 39 if name in ('mfcc', 'cubicmfcc', 'pdfcc') else 64
+    out = fe(su.to(DEV))
+    assert tuple(out.shape) == (rows, 30)
+    assert_parity(cpu(out), g[f'feat_u_{name}'], TOL, name)
+    assert fe.indices == {name: (0, rows)}
+    assert_parity(cpu(fe(sb.to(DEV))), g[f'feat_b_{name}'], TOL, name)
+    assert_parity(cpu(fe((0.1 * sb).to(DEV))), g[f'feat_bs_{name}'], TOL, name + ' 0.1x')
+    # frame-major input (the layout our STFT produces) gives the same values
+    fm = sb.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2).to(DEV)
+    assert_parity(cpu(fe(fm)), g[f'feat_b_{name}'], TOL, name + ' frame-major')
+    # tile seams of the frame-tiled kernel, long recursion: 700 frames against the oracle
+    filters, _, _ = O.mel_filterbank()
+    big = 0.3 * crandn((3, 2, 257, 700), 402)
+    ref, _ = O.extract_features(big.numpy(), filters, [name])
+    assert_parity(cpu(fe(big.to(DEV))), ref, TOL, name + ' 700 frames')
+
+
+def test_mixed_features_and_ic_time_constant():
+    g = golden()
+    fb = brv.MelFilterbank()
+    su, sb = crandn((2, 257, 30), 400), crandn((4, 2, 257, 30), 401)
+    fe = brv.FeatureExtractor(['mfcc', 'ild', 'logfbe', 'ic', 'ipd'], fb)
+    out = fe(su.to(DEV))
+    assert_parity(cpu(out), g['feat_multi2_u'], TOL)
+    assert [fe.indices[k] for k in sorted(fe.indices)] == \
+        [tuple(r) for r in g['feat_multi2_u_idx']]
+    assert fe.n_features == int(g['feat_multi2_n_features'][0])   # declared 13 vs returned 39
+    fe = brv.FeatureExtractor(['ic'], fb, hop_length=64)
+    assert_parity(cpu(fe((0.1 * sb).to(DEV))), g['feat_bs_ic_hop64'], TOL)
+    with pytest.raises(IndexError):                 # mono input has no channel 1
+        brv.FeatureExtractor(['ild'], fb)(su[:1].to(DEV))
+    # features straight from our own STFT of a binaural mixture, against the oracle chain
+    x = 0.05 * randn((2, 8000), 403)                # one unbatched binaural mixture
+    stft = brv.STFT()
+    fe = brv.FeatureExtractor(['ic', 'ild', 'ipd', 'pdfcc'], fb)
+    got = fe(stft(x.to(DEV)))
+    filters, _, _ = O.mel_filterbank()
+    ref, _ = O.extract_features(O.stft(x.numpy()), filters, ['ic', 'ild', 'ipd', 'pdfcc'])
+    assert got.shape == ref.shape == (64 * 3 + 39, 33)
+    # (ipd of near-silent bins is ill-conditioned -- the angle of ~0 -- and is left out here)
+    assert_parity(cpu(got[:64]), ref[:64], 2e-4, 'ic from STFT')
+    assert_parity(cpu(got[64:128]), ref[64:128], 2e-4, 'ild from STFT')
+    assert_parity(cpu(got[192:]), ref[192:], 2e-4, 'pdfcc from STFT')
 
 
 def test_ffnn_glue_against_reference():
@@ -335,6 +387,22 @@ def test_ffnn_glue_against_reference():
     assert tuple(y.shape) == (3, 4000)
     assert_parity(cpu(y), g['ffnn_enh_out'], TOL)
     assert_parity(cpu(front.mel_fb.backward(mask)), g['ffnn_enh_mask_ext'], TOL)
+
+
+def test_ffnn_front_end_with_binaural_features():
+    """FFNN with features={'ild', 'ic', 'logfbe'} (config/models/ffnn.yaml allows any subset):
+    per-feature kernels, concatenated on the feature axis, stacked and decimated."""
+    mix, _ = synthetic_mixture((3, 2, 16000), 1002)
+    front = brv.ffnn.FFNNFrontEnd(features=('ild', 'ic', 'logfbe'), stacks=2, decimation=2)
+    assert front.input_size == 3 * 64 * 3
+    feats = front.features(front.stft(mix.to(DEV)))
+    filters, _, _ = O.mel_filterbank()
+    for idx in range(3):
+        spec = O.stft(mix[idx].numpy())
+        parts = [O.ic(spec, filters), O.ild(spec, filters), O.fbe(spec, filters, compression='log')]
+        ref = O.decimate(O.stack(np.concatenate(parts, axis=0), 2), 2)
+        assert tuple(feats[idx].shape) == ref.shape
+        assert_parity(cpu(feats[idx]), ref, 2e-4, f'item {idx}')
 
 
 def test_features_baseline_size_against_oracle():

@@ -151,6 +151,35 @@ def test_features(name):
                   g[f'feat_b_{name}'], 5e-6, name)
 
 
+@pytest.mark.parametrize('name', ['ild', 'ipd', 'ic', 'mfcc', 'cubicmfcc', 'pdfcc'])
+def test_binaural_and_dct_features(name):
+    """features.py:199-296 against outputs of the reference itself (unbatched, batched, and a
+    0.1x batch that keeps ic's recursive spectra below torchaudio.lfilter's clamp)."""
+    g = golden()
+    filters, _, _ = O.mel_filterbank()
+    su, sb = crandn((2, 257, 30), 400).numpy(), crandn((4, 2, 257, 30), 401).numpy()
+    for tag, spec in (('u', su), ('b', sb), ('bs', 0.1 * sb)):
+        out, idx = O.extract_features(spec, filters, [name])
+        assert_parity(out, g[f'feat_{tag}_{name}'], 5e-6, f'{name} {tag}')
+    rows = 39 if name in O.DCT_FAMILY else 64
+    assert out.shape == (4, rows, 30)
+
+
+def test_ic_time_constant_and_mixed_features():
+    g = golden()
+    filters, _, _ = O.mel_filterbank()
+    su, sb = crandn((2, 257, 30), 400).numpy(), crandn((4, 2, 257, 30), 401).numpy()
+    out, _ = O.extract_features(0.1 * sb, filters, ['ic'], hop_length=64)
+    assert_parity(out, g['feat_bs_ic_hop64'], 5e-6)
+    out, idx = O.extract_features(su, filters, ['mfcc', 'ild', 'logfbe', 'ic', 'ipd'])
+    assert_parity(out, g['feat_multi2_u'], 5e-6)
+    assert [idx[k] for k in sorted(idx)] == [tuple(r) for r in g['feat_multi2_u_idx']]
+    # the reference declares 13 rows for mfcc but returns 39 (features.py:76-84,207-215)
+    declared = sum(O.DECLARED_ROWS.get(k, 64) for k in idx)
+    assert declared == int(g['feat_multi2_n_features'][0]) == 269
+    assert out.shape[0] == 295
+
+
 def test_feature_concat_quirk():
     """features.py:113 concatenates on dim 0 even for batched input."""
     g = golden()
