@@ -11,10 +11,10 @@ CUDA tensors only; there is no CPU fallback.
 from . import criterion, ffnn, modules
 from .criterion import (CriterionRegistry, MultiResYuLoss, apply_mask, init_criterion, mse,
                         sisnr, snr)
-from .modules import STFT, FeatureExtractor, MelFilterbank
+from .modules import STFT, ConvSTFT, FeatureExtractor, MelFilterbank
 from .registry import Registry
 
 __version__ = '0.1.0'
-__all__ = ['STFT', 'MelFilterbank', 'FeatureExtractor', 'CriterionRegistry',
+__all__ = ['STFT', 'ConvSTFT', 'MelFilterbank', 'FeatureExtractor', 'CriterionRegistry',
            'init_criterion', 'sisnr', 'snr', 'mse', 'MultiResYuLoss', 'apply_mask', 'Registry',
            'criterion', 'ffnn', 'modules']

@@ -1,6 +1,7 @@
 // C entry points for the STFT / iSTFT pair: argument checks, geometry, and the
 // choice between the tensor-core kernels (brv_stft_tc.cu) and the generic
 // CUDA-core kernels (brv_stft_simt.cu).  There is no CPU path.
+#include <math.h>
 #include <stdlib.h>
 
 #include "brv_common.cuh"
@@ -28,6 +29,14 @@ int brv_fold_istft_grad(const brv_stft_plan* p, const float* gy, int64_t n_sig, 
 int brv_fold_stft_grad(const brv_stft_plan* p, const float2* gX, int64_t ss, int64_t sb, int64_t sf,
                        int64_t n_sig, int64_t n_frames, int64_t samples, float* gx,
                        cudaStream_t st);
+
+bool brv_fold_conv_supported(const brv_stft_plan* p);
+int brv_fold_conv_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
+                          int64_t x_stride, double gain, float2* out, int64_t n_frames,
+                          cudaStream_t st);
+int brv_fold_conv_backward(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t sb,
+                           int64_t sf, int64_t n_sig, int64_t n_frames, int64_t out_len,
+                           double gain, float* y, cudaStream_t st);
 
 static int g_force_generic = -1;
 extern int g_brv_fold_variant;
@@ -161,4 +170,66 @@ extern "C" int brv_istft_forward_grad(const brv_stft_plan* p, const float* gy, i
                 "workspace too small");
     return brv_simt_istft_grad(p, gy, n_signals, n_frames, (float2*)gX, (float*)workspace,
                                (cudaStream_t)stream);
+}
+
+// ---- ConvSTFT (brever/modules/stft.py:201-319) ------------------------------------------
+static int conv_check(const brv_stft_plan* p) {
+    BRV_REQUIRE(p, "plan is null");
+    if (!brv_fold_conv_supported(p))
+        return brv_fail(BRV_ERR_UNSUPPORTED,
+                        "ConvSTFT runs on the folded tensor-core kernels only: frame_length in "
+                        "{128, 256, 384, 512}, hop_length = frame_length / 4, / 2 or / 1, and a "
+                        "plan created with normalized = 0, n_fft = frame_length");
+    return BRV_OK;
+}
+
+// 0.5 L / sqrt(H), stft.py:232
+static double conv_normalization(const brv_stft_plan* p) {
+    return 0.5 * p->frame_length / sqrt((double)p->hop);
+}
+
+extern "C" int brv_convstft_geometry(const brv_stft_plan* p, int64_t samples, int64_t* n_frames) {
+    int rc = conv_check(p);
+    if (rc != BRV_OK) return rc;
+    BRV_REQUIRE(samples >= 0, "negative sample count");
+    // ConvSTFT.pad (stft.py:305-315): right pad to whole frames, then L - H on both sides;
+    // F.conv1d with stride H yields (len - L) / H + 1 frames
+    const int64_t over = samples > p->frame_length ? samples - p->frame_length : 0;
+    const int64_t frames0 = brv_ceil_div(over, p->hop) + 1;
+    const int64_t len = (frames0 - 1) * p->hop + p->frame_length +
+                        2 * (int64_t)(p->frame_length - p->hop);
+    if (n_frames) *n_frames = (len - p->frame_length) / p->hop + 1;
+    return BRV_OK;
+}
+
+extern "C" int brv_convstft_forward(const brv_stft_plan* p, const float* x, int64_t n_signals,
+                                    int64_t samples, int64_t x_stride, int normalized, void* out,
+                                    void* stream) {
+    int rc = conv_check(p);
+    if (rc != BRV_OK) return rc;
+    BRV_REQUIRE(out && (x || n_signals * samples == 0), "null pointer argument");
+    BRV_REQUIRE(n_signals >= 0 && samples >= 0, "negative shape");
+    int64_t n_frames = 0;
+    rc = brv_convstft_geometry(p, samples, &n_frames);
+    if (rc != BRV_OK) return rc;
+    if (n_signals == 0) return BRV_OK;
+    const double gain = normalized ? 1.0 / conv_normalization(p) : 1.0;
+    return brv_fold_conv_forward(p, x, n_signals, samples, x_stride, gain, (float2*)out, n_frames,
+                                 (cudaStream_t)stream);
+}
+
+extern "C" int brv_convstft_backward(const brv_stft_plan* p, const void* X, int64_t ss, int64_t sb,
+                                     int64_t sf, int64_t n_signals, int64_t n_frames,
+                                     int normalized, float* y, void* stream) {
+    int rc = conv_check(p);
+    if (rc != BRV_OK) return rc;
+    BRV_REQUIRE(X && n_signals >= 0 && n_frames >= 1, "bad arguments");
+    // conv_transpose1d gives (T - 1) H + L samples; L - H are cut from both ends (stft.py:294-298)
+    const int64_t out_len = (n_frames + 1) * p->hop - p->frame_length;
+    if (n_signals == 0 || out_len <= 0) return BRV_OK;
+    BRV_REQUIRE(y, "output pointer is null");
+    const double nf = conv_normalization(p);
+    const double gain = normalized ? 1.0 / nf : 1.0 / (nf * nf);
+    return brv_fold_conv_backward(p, (const float2*)X, ss, sb, sf, n_signals, n_frames, out_len,
+                                  gain, y, (cudaStream_t)stream);
 }

@@ -87,7 +87,11 @@ struct FoldFwdParams {
     // in_mul[sample] (1 / overlap-added w^2) while it is staged, and the DC and Nyquist bins,
     // which carry Hermitian weight 1 instead of 2, are multiplied by edge_scale = 1/2
     const float* in_mul;
-    float edge_scale;
+    float edge_scale;            // Nyquist bin
+    float dc_scale;              // DC bin (equal to edge_scale except for ConvSTFT's 1/sqrt(2) row)
+    // frame t starts origin samples before sample t * hop: n_fft / 2 (torch.stft centre
+    // padding) or frame_length - hop_length (ConvSTFT.pad, stft.py:311-313)
+    int origin;
     // n_fft = 4Q - 2 (N/2 odd, e.g. 510): same four contractions over n = 0..Q-1, but there is
     // no self-paired n = Q column and no separate Nyquist bin (k = N/2 is the last odd bin)
     int odd;
@@ -208,7 +212,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
         const int bt = bw * 32 + lane;             // 0..255
         const float* xs = p.x + sig * p.x_stride;
         const int shift = p.shift;
-        const int64_t span0 = t0 * H - Hf - shift; // first sample of the span (may be < 0)
+        const int64_t span0 = t0 * H - p.origin - shift; // first sample of the span (may be < 0)
         const int span_len = (rows_eff - 1) * H + N + shift;
         const int span_pad = (span_len + 31) & ~31;
 
@@ -363,7 +367,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
             for (int j = 0; j < 16; ++j) {
                 const float sg = (j & 1) ? -1.f : 1.f;        // m0 is even
                 float re_e = __uint_as_float(r0[j]) * g0 + sg * eeq;
-                if (j == 0 && m0 == 0) re_e *= p.edge_scale;       // DC bin (its Im is exactly 0)
+                if (j == 0 && m0 == 0) re_e *= p.dc_scale;         // DC bin (its Im is exactly 0)
                 float re_o = __uint_as_float(r1[j]) * g0;
                 float im_e = __uint_as_float(r2[j]) * g0;
                 float im_o = __uint_as_float(r3[j]) * g0 - sg * ooq;
@@ -594,7 +598,7 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
                     for (int j = 0; j < 16; ++j) {
                         float re = fmaf(__uint_as_float(r0[j]), g0, (j & 1) ? -rq : rq);   // m0 is even
                         float im = fmaf(__uint_as_float(r1[j]), g0, (j & 1) ? -iq : iq);
-                        if (j == 0 && c == 0 && pass == 0) re *= p.edge_scale;   // DC bin
+                        if (j == 0 && c == 0 && pass == 0) re *= p.dc_scale;     // DC bin
                         if (COMPRESS) {
                             compress(re, im, p.post_expo);
                             re *= p.post_scale;
@@ -639,7 +643,7 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
             const int rows_eff = (int)min((int64_t)p.rows, p.n_frames - t0);
             const float* xs = p.x + sig * p.x_stride;
             const int shift = p.shift;
-            const int64_t span0 = t0 * H - Hf - shift; // first sample of the span (may be < 0)
+            const int64_t span0 = t0 * H - p.origin - shift; // first sample of the span (may be < 0)
             const int span_len = (rows_eff - 1) * H + N + shift;
             const int span_pad = (span_len + 31) & ~31;
             if (n > 0) named_bar_sync(1, F2_BUILDER_THREADS);   // previous tile's span fully read
@@ -677,7 +681,7 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
                     const int64_t nsig = nt / p.tiles_per_signal;
                     const int64_t nt0 = (int64_t)(nt % p.tiles_per_signal) * p.rows;
                     const int nrows = (int)min((int64_t)p.rows, p.n_frames - nt0);
-                    int64_t lo = nt0 * H - Hf, hi = lo + (int64_t)(nrows - 1) * H + N;
+                    int64_t lo = nt0 * H - p.origin, hi = lo + (int64_t)(nrows - 1) * H + N;
                     if (lo < 0) lo = 0;
                     if (hi > p.samples) hi = p.samples;
                     const float* nx = p.x + nsig * p.x_stride;
@@ -881,6 +885,8 @@ struct FoldInvParams {
     // gradient of the forward transform (brv_fold_stft_grad): no envelope (inv_env == nullptr),
     // all bins weigh 1: the window table carries 1/2 and the DC / Nyquist inputs edge_gain = 2
     float edge_gain;
+    float dc_gain;               // DC input (equal to edge_gain except for ConvSTFT: sqrt(2))
+    int origin;                  // output sample i sits at overlap-add position i + origin
 };
 
 template <bool DECOMP>
@@ -1202,7 +1208,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                         for (int e = 0; e < 32; ++e) c[e] = prep_bin<DECOMP>(c[e], p.pre_scale, p.pre_expo);
                         if (bin0 == 0) {
                             c[0].y = 0.f;              // Im X[0] is ignored by the c2r inverse
-                            c[0].x *= p.edge_gain;
+                            c[0].x *= p.dc_gain;
                         }
                         if (ODD && bin0 + 32 == 2 * Q) c[31].y = 0.f;   // so is Im X[N/2]
 #pragma unroll
@@ -1286,7 +1292,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                             c[i][e] = prep_bin<DECOMP>(c[i][e], p.pre_scale, p.pre_expo);
                         if (m0 == 0) {
                             c[i][0].y = 0.f;           // Im X[0] is ignored by the c2r inverse
-                            c[i][0].x *= p.edge_gain;
+                            c[i][0].x *= p.dc_gain;
                         }
                         if (ODD && m0 == Q - 2) c[i][3].y = 0.f;      // so is Im X[N/2]
                         pacc[i] += c[i][0].x - c[i][2].x;
@@ -1470,7 +1476,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                     const float* src = orow + r * pitch;
                     const int qq = r >> 5, lr = r & 31;
                     const float* sp = (qq > 0 && lr < p.halo) ? spill + (qq * 3 + lr) * H : nullptr;
-                    const int64_t i0 = u * H - Hf;
+                    const int64_t i0 = u * H - p.origin;
                     const bool interior = u >= R - 1 && u <= p.n_frames - 1;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -1776,8 +1782,9 @@ static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool c
     prm.n_bins = p->n_bins;
     prm.q = fp->q;
     prm.odd = fp->odd;
+    if (prm.origin < 0) prm.origin = p->n_fft / 2;
     // 16-byte aligned span when the hop allows it (n_fft / 2 = 255 would otherwise force scalar loads)
-    prm.shift = p->hop % 4 == 0 ? (4 - ((p->n_fft / 2) & 3)) & 3 : 0;
+    prm.shift = p->hop % 4 == 0 ? (4 - (prm.origin & 3)) & 3 : 0;
     int rows = (SPAN_MAX - p->n_fft - prm.shift) / p->hop + 1;
     if (rows > TILE_M) rows = TILE_M;
     if (rows > n_frames) rows = (int)n_frames;
@@ -1824,7 +1831,8 @@ int brv_fold_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig,
     prm.post_scale = (float)p->scale;
     prm.post_expo = (float)(p->compression - 1.0);
     prm.in_mul = nullptr;
-    prm.edge_scale = 1.f;
+    prm.edge_scale = prm.dc_scale = 1.f;
+    prm.origin = -1;
     return fold_forward_launch(p, prm, p->compression != 1.0, n_sig, n_frames, st);
 }
 
@@ -1884,7 +1892,8 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     prm.q = fp->q;
     prm.halo = 4 / fp->hq - 1;
     prm.adv = TILE_M - prm.halo;
-    prm.n_blocks = (int)brv_ceil_div(p->n_fft / 2 + out_len, p->hop);
+    if (prm.origin < 0) prm.origin = p->n_fft / 2;
+    prm.n_blocks = (int)brv_ceil_div(prm.origin + out_len, p->hop);
     prm.tiles_per_signal =
         prm.n_blocks <= TILE_M ? 1 : 1 + (int)brv_ceil_div(prm.n_blocks - TILE_M, prm.adv);
     prm.tmem_cols = fp->tmem_cols;
@@ -1940,7 +1949,8 @@ int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t 
     prm.wtab = fp->wtab_inv;
     prm.wq = fp->wq_inv;
     prm.w3q = fp->w3q_inv;
-    prm.edge_gain = 1.f;
+    prm.edge_gain = prm.dc_gain = 1.f;
+    prm.origin = -1;
     return fold_inverse_launch(p, prm, p->compression != 1.0, n_sig, n_frames, out_len, st);
 }
 
@@ -1963,7 +1973,8 @@ int brv_fold_stft_grad(const brv_stft_plan* p, const float2* gX, int64_t ss, int
     prm.wtab = fp->wtab_fgrad;
     prm.wq = fp->wq_fg;
     prm.w3q = fp->w3q_fg;
-    prm.edge_gain = 2.f;
+    prm.edge_gain = prm.dc_gain = 2.f;
+    prm.origin = -1;
     return fold_inverse_launch(p, prm, false, n_sig, n_frames, samples, st);
 }
 
@@ -1985,6 +1996,68 @@ int brv_fold_istft_grad(const brv_stft_plan* p, const float* gy, int64_t n_sig, 
     prm.wmax = fp->wmax_g;
     prm.post_scale = (float)(1.0 / p->scale);
     prm.post_expo = 0.f;
-    prm.edge_scale = 0.5f;
+    prm.edge_scale = prm.dc_scale = 0.5f;
+    prm.origin = -1;
     return fold_forward_launch(p, prm, false, n_sig, n_frames, st);
+}
+
+// ---- ConvSTFT (brever/modules/stft.py:201-319) on the same kernels ------------------------
+// ConvSTFT.forward is a strided convolution with the rows k = 0..L/2 of the DFT matrix times
+// the window, the DC row divided by sqrt(2), all divided by 0.5 L / sqrt(H) when normalised
+// (stft.py:221-235): the folded forward kernel with frames starting L - H samples before
+// t * hop (ConvSTFT.pad, stft.py:305-315, instead of torch.stft's n_fft / 2), a DC gain of
+// 1 / sqrt(2) and `gain` folded into the post-compression scale ((g X)|g X|^(c-1) = g^c X|X|^(c-1)).
+bool brv_fold_conv_supported(const brv_stft_plan* p) {
+    const FoldPlan* fp = (const FoldPlan*)p->fold;
+    return fp && !fp->odd && fp->hq != 0 && !p->normalized && p->n_fft == p->frame_length &&
+           p->frame_length >= p->hop;
+}
+
+int brv_fold_conv_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
+                          int64_t x_stride, double gain, float2* out, int64_t n_frames,
+                          cudaStream_t st) {
+    const FoldPlan* fp = (const FoldPlan*)p->fold;
+    FoldFwdParams prm = {};
+    prm.x = x;
+    prm.x_stride = x_stride;
+    prm.samples = samples;
+    prm.out = reinterpret_cast<float*>(out);
+    prm.wtab = fp->wtab;
+    prm.wq = fp->wq;
+    prm.w3q = fp->w3q;
+    prm.wmax = fp->wmax;
+    prm.post_scale = (float)(p->scale * pow(gain, p->compression));
+    prm.post_expo = (float)(p->compression - 1.0);
+    prm.in_mul = nullptr;
+    prm.edge_scale = 1.f;
+    prm.dc_scale = (float)sqrt(0.5);
+    prm.origin = p->frame_length - p->hop;
+    return fold_forward_launch(p, prm, p->compression != 1.0, n_sig, n_frames, st);
+}
+
+// ConvSTFT.backward = conv_transpose1d with the same filters (stft.py:281-300): the adjoint of
+// the forward map, no envelope division, trimmed by L - H on both sides.  The folded inverse
+// kernel in its gradient configuration (every bin weighs 1; DC 1 / sqrt(2)), after / scale and
+// |X|^(1/c - 1) decompression in the loaders; `gain` (1 / normalisation, squared when the
+// filters are not normalised, stft.py:291-292) enters before the decompression as gain^c.
+int brv_fold_conv_backward(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t sb,
+                           int64_t sf, int64_t n_sig, int64_t n_frames, int64_t out_len,
+                           double gain, float* y, cudaStream_t st) {
+    const FoldPlan* fp = (const FoldPlan*)p->fold;
+    FoldInvParams prm = {};
+    prm.inv_env = nullptr;
+    prm.spec = X;
+    prm.ss = ss;
+    prm.sb = sb;
+    prm.sf = sf;
+    prm.pre_scale = (float)(pow(gain, p->compression) / p->scale);
+    prm.pre_expo = (float)(1.0 / p->compression - 1.0);
+    prm.y = y;
+    prm.wtab = fp->wtab_fgrad;
+    prm.wq = fp->wq_fg;
+    prm.w3q = fp->w3q_fg;
+    prm.edge_gain = 2.f;
+    prm.dc_gain = (float)sqrt(2.0);
+    prm.origin = p->frame_length - p->hop;
+    return fold_inverse_launch(p, prm, p->compression != 1.0, n_sig, n_frames, out_len, st);
 }

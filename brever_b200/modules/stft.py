@@ -271,6 +271,125 @@ class STFT:
         return y if out_dtype == torch.float32 else y.to(out_dtype)
 
 
+class ConvSTFT:
+    """Drop-in ``ConvSTFT`` (brever/modules/stft.py:201-319): the STFT written as a strided
+    convolution with windowed DFT rows, and its transposed convolution as the synthesis.
+
+    Same constructor keywords, attributes (``window`` is the square root of the scipy window,
+    ``filters`` the ``(2F, 1, L)`` float32 kernel bank, ``_normalization_factor``), padding
+    (``pad``, ``frame_count``) and return / input types as the reference.  The arithmetic is
+    the folded tensor-core pair of ``brv_convstft_forward`` / ``brv_convstft_backward``:
+    frames start ``L - H`` samples before ``t * H``, the DC row carries ``1 / sqrt(2)``, the
+    synthesis is the exact adjoint (no envelope division) trimmed by ``L - H`` per side.
+    Supported on the kernels' sizes only (``frame_length`` in {128, 256, 384, 512} and
+    ``hop_length`` = L/4, L/2 or L); no autograd (no reference model uses ConvSTFT).
+    """
+
+    def __init__(self, frame_length=512, hop_length=256, window='hann',
+                 compression_factor=1, scale_factor=1, normalized=True):
+        self.frame_length = frame_length
+        self.hop_length = hop_length
+        self.compression_factor = compression_factor
+        self.scale_factor = scale_factor
+        self.normalized = normalized
+        if isinstance(window, str):
+            window = scipy.signal.get_window(window, frame_length) ** 0.5   # stft.py:213-214
+        if isinstance(window, np.ndarray):
+            window = torch.from_numpy(window)
+        self.window = window
+        self._normalization_factor = 0.5 * frame_length / hop_length ** 0.5   # stft.py:232
+        # the kernels apply the normalisation themselves: the core plan is un-normalised
+        self._core = STFT(frame_length=frame_length, hop_length=hop_length, window=window,
+                          normalized=False, compression_factor=compression_factor,
+                          scale_factor=scale_factor)
+
+    @property
+    def filters(self):
+        """The reference's convolution kernels (stft.py:218-238), for inspection."""
+        L = self.frame_length
+        filters = torch.fft.fft(torch.eye(L))[:L // 2 + 1]
+        filters[0, :] /= 2 ** 0.5
+        if self.normalized:
+            filters /= self._normalization_factor
+        filters *= self.window
+        return torch.cat([filters.real, filters.imag]).unsqueeze(1).float()
+
+    def __call__(self, x, return_type='complex'):
+        return self.forward(x, return_type=return_type)
+
+    def frame_count(self, samples):
+        return math.ceil(max(samples - self.frame_length, 0) / self.hop_length) + 1
+
+    def pad(self, x):
+        samples = x.shape[-1]
+        padding = (self.frame_count(samples) - 1) * self.hop_length + self.frame_length - samples
+        x = torch.nn.functional.pad(x, (0, padding))
+        padding = self.frame_length - self.hop_length
+        return torch.nn.functional.pad(x, (padding, padding))
+
+    def n_frames(self, samples):
+        padded = (self.frame_count(samples) - 1) * self.hop_length + self.frame_length \
+            + 2 * (self.frame_length - self.hop_length)
+        return (padded - self.frame_length) // self.hop_length + 1
+
+    def forward(self, x, return_type='complex'):
+        if return_type not in ('complex', 'real_imag', 'mag_phase'):
+            raise ValueError('return_type must be complex, real_imag or '
+                             f'mag_phase, got {return_type}')
+        _lib.require_cuda(x, 'ConvSTFT input')
+        lead = x.shape[:-1]
+        x2d = x.reshape(-1, x.shape[-1])
+        if x2d.dtype != torch.float32:
+            x2d = x2d.float()
+        if x2d.stride(-1) != 1:
+            x2d = x2d.contiguous()
+        n_sig, samples = x2d.shape
+        frames, bins = self.n_frames(samples), self.frame_length // 2 + 1
+        out = torch.empty((n_sig, frames, bins), dtype=torch.complex64, device=x2d.device)
+        if n_sig:
+            with _lib.on_device(x2d.device):
+                _lib.check(_lib.lib().brv_convstft_forward(
+                    self._core._plan(x2d.device), _lib.ptr(x2d), n_sig, samples,
+                    x2d.stride(0) if n_sig > 1 else samples, int(bool(self.normalized)),
+                    _lib.ptr(out), _lib.stream_ptr(x2d.device)))
+        spec = out.transpose(1, 2).view(*lead, bins, frames)
+        if return_type == 'complex':
+            return spec
+        if return_type == 'real_imag':
+            return spec.real, spec.imag
+        return spec.abs(), spec.angle()
+
+    def backward(self, x, input_type='complex'):
+        if input_type == 'real_imag':
+            real, imag = x
+            x = torch.complex(real, imag)
+        elif input_type == 'mag_phase':
+            mag, phase = x
+            x = torch.polar(mag, phase)
+        elif input_type != 'complex':
+            raise ValueError('input_type must be complex, real_imag or '
+                             f'mag_phase, got {input_type}')
+        _lib.require_cuda(x, 'ConvSTFT.backward input')
+        if not x.is_complex():
+            raise RuntimeError('ConvSTFT.backward input must be complex')
+        lead = x.shape[:-2]
+        spec3d = x.reshape(-1, *x.shape[-2:]).to(torch.complex64)
+        n_sig, bins, frames = spec3d.shape
+        if bins != self.frame_length // 2 + 1:
+            raise RuntimeError(f'expected {self.frame_length // 2 + 1} frequency bins, got {bins}')
+        out_len = max((frames + 1) * self.hop_length - self.frame_length, 0)
+        if self.frame_length == self.hop_length:
+            out_len = 0   # the reference slices ``x[..., 0:-0]`` = nothing (stft.py:296-298)
+        y = torch.empty((n_sig, out_len), dtype=torch.float32, device=spec3d.device)
+        if n_sig and out_len:
+            with _lib.on_device(spec3d.device):
+                _lib.check(_lib.lib().brv_convstft_backward(
+                    self._core._plan(spec3d.device), _lib.ptr(spec3d), spec3d.stride(0),
+                    spec3d.stride(1), spec3d.stride(2), n_sig, frames,
+                    int(bool(self.normalized)), _lib.ptr(y), _lib.stream_ptr(spec3d.device)))
+        return y.view(*lead, -1)
+
+
 class _MelApply(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, fb, inverse):

@@ -126,6 +126,28 @@ int brv_istft_forward_grad(const brv_stft_plan* plan, const float* gy,
 size_t brv_stft_workspace_bytes(const brv_stft_plan* plan, int64_t n_signals,
                                 int64_t n_frames);
 
+/* ---- ConvSTFT (stft.py:201-319) ---------------------------------------------
+ * The convolutional STFT pair: analysis = F.conv1d with the windowed one-sided
+ * DFT rows (DC row / sqrt(2), all / (0.5 L / sqrt(H)) when `normalized`) after
+ * ConvSTFT.pad (right pad to whole frames, then L - H zeros on both sides);
+ * synthesis = F.conv_transpose1d with the same filters (/ normalisation^2 when
+ * not `normalized`), trimmed by L - H on both sides: (T + 1) H - L samples.
+ * The plan is created by brv_stft_plan_create with the (square-root) window,
+ * normalized = 0, n_fft = frame_length; compression_factor / scale_factor as in
+ * the STFT entries.  Runs on the folded tensor-core kernels only (frame_length
+ * in {128,256,384,512}, hop = L/4, L/2 or L): otherwise BRV_ERR_UNSUPPORTED.   */
+int brv_convstft_geometry(const brv_stft_plan* plan, int64_t samples,
+                          int64_t* n_frames);
+int brv_convstft_forward(const brv_stft_plan* plan, const float* x,
+                         int64_t n_signals, int64_t samples, int64_t x_stride,
+                         int normalized, void* out /* (n_signals, T, L/2+1) complex64 */,
+                         void* stream);
+int brv_convstft_backward(const brv_stft_plan* plan, const void* X,
+                          int64_t stride_signal, int64_t stride_bin,
+                          int64_t stride_frame, int64_t n_signals,
+                          int64_t n_frames, int normalized,
+                          float* y /* (n_signals, (T+1)H - L) */, void* stream);
+
 /* ---- mel filterbank (stft.py:152-198) -------------------------------------
  * Sparse (CSR) form of MelFilterbank.filters / inverse_filters applied along
  * the second-to-last axis:  out[b, r, t] = sum_j vals[j] * x[b, cols[j], t],

@@ -192,6 +192,73 @@ def istft(spec, frame_length=512, hop_length=256, window='hann',
     return out.reshape(*lead, -1)
 
 
+def _conv_filters(frame_length, hop_length, window, normalized):
+    """ConvSTFT.__init__, stft.py:213-238: rows k = 0..L/2 of the DFT matrix times the window
+    (square root of the scipy window when given by name), DC row / sqrt(2), everything
+    / (0.5 L / sqrt(H)) when normalised.  Returns the complex (F, L) bank and that factor."""
+    if isinstance(window, str) or window is None:
+        window = get_window(window, frame_length) ** 0.5
+    window = np.asarray(window, dtype=np.float64)
+    n = np.arange(frame_length)
+    k = np.arange(frame_length // 2 + 1)[:, None]
+    bank = np.exp(-2j * np.pi * ((k * n) % frame_length) / frame_length)
+    bank[0] /= math.sqrt(2.0)
+    factor = 0.5 * frame_length / math.sqrt(hop_length)
+    if normalized:
+        bank = bank / factor
+    return bank * window, factor
+
+
+def conv_stft(x, frame_length=512, hop_length=256, window='hann', compression_factor=1.0,
+              scale_factor=1.0, normalized=True):
+    """ConvSTFT.forward, stft.py:243-270: right pad to whole frames, L - H zeros on both
+    sides (pad, stft.py:305-315), strided correlation with the filter bank, optional
+    magnitude compression, scale."""
+    x = np.asarray(x)
+    lead, samples = x.shape[:-1], x.shape[-1]
+    sig = x.reshape(-1, samples).astype(np.float64)
+    bank, _ = _conv_filters(frame_length, hop_length, window, normalized)
+    edge = frame_length - hop_length
+    pad_r = right_padding(samples, frame_length, hop_length)
+    padded = np.zeros((sig.shape[0], samples + pad_r + 2 * edge))
+    padded[:, edge:edge + samples] = sig
+    n_frames = (padded.shape[1] - frame_length) // hop_length + 1
+    idx = np.arange(n_frames)[:, None] * hop_length + np.arange(frame_length)[None, :]
+    spec = np.einsum('stn,kn->skt', padded[:, idx], bank)
+    if compression_factor != 1:
+        spec = np.abs(spec) ** compression_factor * np.exp(1j * np.angle(spec))
+    spec = spec * scale_factor
+    return spec.reshape(*lead, *spec.shape[-2:])
+
+
+def conv_istft(spec, frame_length=512, hop_length=256, window='hann', compression_factor=1.0,
+               scale_factor=1.0, normalized=True):
+    """ConvSTFT.backward, stft.py:272-303: / scale, decompression, transposed convolution
+    with the same real / imaginary filters (the adjoint of the analysis), / factor^2 when the
+    filters are not normalised, L - H samples cut from both ends."""
+    spec = np.asarray(spec).astype(np.complex128)
+    lead = spec.shape[:-2]
+    n_bins, n_frames = spec.shape[-2:]
+    spec = spec.reshape(-1, n_bins, n_frames) / scale_factor
+    if compression_factor != 1:
+        spec = np.abs(spec) ** (1 / compression_factor) * np.exp(1j * np.angle(spec))
+    bank, factor = _conv_filters(frame_length, hop_length, window, normalized)
+    # real part of sum_k X[k, t] conj(bank[k, n]) = Re X * Re bank + Im X * Im bank
+    frames = np.einsum('skt,kn->stn', spec.real, bank.real) + \
+        np.einsum('skt,kn->stn', spec.imag, bank.imag)
+    full = frame_length + hop_length * (n_frames - 1)
+    out = np.zeros((spec.shape[0], full))
+    for t in range(n_frames):
+        out[:, t * hop_length:t * hop_length + frame_length] += frames[:, t]
+    if not normalized:
+        out = out / factor ** 2
+    edge = frame_length - hop_length
+    # ``x[..., padding:-padding]`` (stft.py:298): with hop == frame_length the slice is
+    # ``[0:-0]`` = empty -- the reference returns no samples at all in that case (kept)
+    out = out[:, edge:-edge] if edge else out[:, 0:0]
+    return out.reshape(*lead, -1)
+
+
 # --------------------------------------------------------------------------- #
 # mel filterbank                                                              #
 # --------------------------------------------------------------------------- #

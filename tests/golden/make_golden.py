@@ -121,6 +121,30 @@ def main():
     st = STFT(frame_length=512, hop_length=128)
     out['istft_random'] = st.backward(spec.clone()).numpy()
 
+    # ---- ConvSTFT (stft.py:201-319): the reference's own test input and parametrisation
+    #      (tests/test_modules.py:329-352) plus batched / ragged shapes
+    from brever.modules import ConvSTFT
+    x = randn((4096,), 42)
+    for hop, c, s, normalized in itertools.product([256, 128], [1.0, 0.5], [1.0, 0.15],
+                                                   [False, True]):
+        cs = ConvSTFT(frame_length=512, hop_length=hop, compression_factor=c,
+                      scale_factor=s, normalized=normalized)
+        spec = cs(x)
+        key = f'conv_h{hop}_c{c}_s{s}_n{int(normalized)}'
+        if (c, s) in ((1.0, 1.0), (0.5, 0.15)):
+            out[key + '_spec'] = spec.numpy()
+        out[key + '_back'] = cs.backward(spec.clone()).numpy()
+    for i, (S, L, H) in enumerate([(100, 512, 256), (3001, 512, 128), (777, 256, 64),
+                                   (2000, 256, 256), (1500, 128, 32)]):
+        xs = randn((2, 3, S), 150 + i)
+        cs = ConvSTFT(frame_length=L, hop_length=H)
+        spec = cs(xs)
+        out[f'convshape{i}_meta'] = np.array([S, L, H], dtype=np.int64)
+        out[f'convshape{i}_spec'] = spec.numpy()
+        out[f'convshape{i}_back'] = cs.backward(spec.clone()).numpy()
+    cs = ConvSTFT(frame_length=512, hop_length=128)
+    out['conv_random_back'] = cs.backward(crandn((2, 257, 20), 160)).numpy()
+
     # ---- mel filterbank constants (bit-exact)
     for tag, kw in [('mel512', {}), ('mel256', dict(n_fft=256)),
                     ('mel40', dict(n_filters=40, n_fft=400, fs=8000, fmax=4000))]:

@@ -422,6 +422,62 @@ def test_features_baseline_size_against_oracle():
     assert abs(float(normed.mean())) < 1e-3
 
 
+def test_conv_stft_against_reference():
+    """ConvSTFT (stft.py:201-319) on the folded tensor-core kernels: the reference's own test
+    input and parametrisation (tests/test_modules.py:329-352) against outputs of the reference,
+    its round-trip acceptance property, ragged / batched shapes, attributes."""
+    g = golden()
+    x = randn((4096,), 42)
+    lib = _lib.lib()
+    for hop, c, s, n in itertools.product([256, 128], [1.0, 0.5], [1.0, 0.15], [False, True]):
+        kw = dict(frame_length=512, hop_length=hop, compression_factor=c, scale_factor=s,
+                  normalized=n)
+        key = f'conv_h{hop}_c{c}_s{s}_n{int(n)}'
+        cs = brv.ConvSTFT(**kw)
+        n0 = lib.brv_launch_count()
+        spec = cs(x.to(DEV))
+        assert lib.brv_launch_count() - n0 == 1
+        ref = O.conv_stft(x.numpy(), **kw)
+        assert tuple(spec.shape) == ref.shape
+        if key + '_spec' in g.files:
+            assert_parity(cpu(spec), g[key + '_spec'], TOL, key)
+        assert_parity(cpu(spec), ref, TOL, key + ' oracle')
+        back = cs.backward(spec)
+        assert_parity(cpu(back), g[key + '_back'], TOL, key + ' back')
+        assert torch.allclose(x, back.cpu(), rtol=1e-1, atol=1e-1)   # tests/test_modules.py:352
+    for i in range(5):
+        S, L, H = (int(v) for v in g[f'convshape{i}_meta'])
+        xs = randn((2, 3, S), 150 + i)
+        cs = brv.ConvSTFT(frame_length=L, hop_length=H)
+        spec = cs(xs.to(DEV))
+        assert tuple(spec.shape) == g[f'convshape{i}_spec'].shape
+        assert_parity(cpu(spec), g[f'convshape{i}_spec'], TOL, f'shape {i}')
+        back = cs.backward(spec)
+        assert tuple(back.shape) == g[f'convshape{i}_back'].shape   # (…, 0) when hop == L
+        assert_parity(cpu(back), g[f'convshape{i}_back'], TOL, f'shape {i} back')
+        re, im = cs(xs.to(DEV), return_type='real_imag')
+        assert_parity(cpu(cs.backward((re, im), input_type='real_imag')),
+                      g[f'convshape{i}_back'], TOL)
+    cs = brv.ConvSTFT(frame_length=512, hop_length=128)
+    assert_parity(cpu(cs.backward(crandn((2, 257, 20), 160).to(DEV))), g['conv_random_back'], TOL)
+    # bin-major and frame-major inputs, a long signal crossing several 128-frame tiles
+    xs = randn((3, 40000), 161)
+    spec = cs(xs.to(DEV))
+    ref = O.conv_stft(xs.numpy(), 512, 128)
+    assert_parity(cpu(spec), ref, TOL)
+    ref_back = O.conv_istft(ref, 512, 128)
+    assert_parity(cpu(cs.backward(spec)), ref_back, TOL)
+    assert_parity(cpu(cs.backward(spec.contiguous())), ref_back, TOL)
+    # attributes the reference exposes
+    assert tuple(cs.filters.shape) == (514, 1, 512) and cs.filters.dtype == torch.float32
+    assert cs._normalization_factor == 0.5 * 512 / 128 ** 0.5
+    assert cs.frame_count(4096) == 29 and tuple(cs.pad(xs).shape) == (3, 40064 + 768)
+    with pytest.raises(ValueError):
+        cs(xs.to(DEV), return_type='nope')
+    with pytest.raises(NotImplementedError):
+        brv.ConvSTFT(frame_length=400, hop_length=100)(xs.to(DEV))
+
+
 # --------------------------------------------------------------------------- #
 # criteria                                                                    #
 # --------------------------------------------------------------------------- #

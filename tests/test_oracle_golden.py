@@ -140,6 +140,36 @@ def test_mel_apply():
                   g['mel_bwd'], 2e-6)
 
 
+def test_conv_stft_against_reference():
+    """ConvSTFT (stft.py:201-319): the reference's own test input and all 16 parametrisations
+    (tests/test_modules.py:329-352), its acceptance property, and ragged / batched shapes
+    including the hop == frame_length case where the reference returns nothing."""
+    import itertools
+    g = golden()
+    x = randn((4096,), 42).numpy()
+    for hop, c, s, n in itertools.product([256, 128], [1.0, 0.5], [1.0, 0.15], [False, True]):
+        kw = dict(frame_length=512, hop_length=hop, compression_factor=c, scale_factor=s,
+                  normalized=n)
+        key = f'conv_h{hop}_c{c}_s{s}_n{int(n)}'
+        spec = O.conv_stft(x, **kw)
+        if key + '_spec' in g.files:
+            assert_parity(spec, g[key + '_spec'], 5e-6, key)
+        back = O.conv_istft(spec, **kw)
+        assert_parity(back, g[key + '_back'], 5e-6, key)
+        assert np.allclose(x, back, rtol=1e-1, atol=1e-1)     # tests/test_modules.py:352
+    for i in range(5):
+        S, L, H = (int(v) for v in g[f'convshape{i}_meta'])
+        xs = randn((2, 3, S), 150 + i).numpy()
+        spec = O.conv_stft(xs, frame_length=L, hop_length=H)
+        assert spec.shape == g[f'convshape{i}_spec'].shape
+        assert_parity(spec, g[f'convshape{i}_spec'], 5e-6, f'shape {i}')
+        back = O.conv_istft(spec, frame_length=L, hop_length=H)
+        assert back.shape == g[f'convshape{i}_back'].shape
+        assert_parity(back, g[f'convshape{i}_back'], 5e-6, f'shape {i}')
+    assert_parity(O.conv_istft(crandn((2, 257, 20), 160).numpy(), 512, 128),
+                  g['conv_random_back'], 5e-6)
+
+
 @pytest.mark.parametrize('name', sorted(O.FBE_FAMILY))
 def test_features(name):
     g = golden()
