@@ -42,6 +42,25 @@
 #include "brv_common.cuh"
 #include "brv_tc_ptx.cuh"
 
+// Dev-only phase timing (compile with -DBRV_PHASE_TIMING): builder thread 0 of CTA 0 stamps
+// %globaltimer at the phase boundaries of its first tiles; read back with brv_debug_phase_times.
+#ifdef BRV_PHASE_TIMING
+__device__ unsigned long long g_brv_phase_ts[64];
+#define BRV_STAMP(i)                                                                    \
+    do {                                                                                \
+        if (blockIdx.x == 0 && bt == 0 && (i) < 64) {                                   \
+            unsigned long long t_;                                                      \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                       \
+            g_brv_phase_ts[(i)] = t_;                                                   \
+        }                                                                               \
+    } while (0)
+extern "C" int brv_debug_phase_times(unsigned long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_brv_phase_ts, sizeof(unsigned long long) * (n < 64 ? n : 64));
+}
+#else
+#define BRV_STAMP(i) do {} while (0)
+#endif
+
 namespace {
 
 using namespace brv_ptx;
@@ -216,6 +235,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
         const int span_len = (rows_eff - 1) * H + N + shift;
         const int span_pad = (span_len + 31) & ~31;
 
+        BRV_STAMP(32);
         for (int j = bt; j < Q; j += BUILDER_THREADS) wtab[j] = __ldg(p.wtab + j);
 
         // ---- stage the sample span + per-32-sample maxima ------------------------
@@ -257,6 +277,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
             }
         }
         named_bar_sync(1, BUILDER_THREADS);
+        BRV_STAMP(33);
 
         // ---- per-row power-of-two scale from a bound on the folded magnitudes ----
         if (bt < rows_eff) {
@@ -266,6 +287,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
             rowinfo[bt].x = row_scale(4.f * p.wmax * __uint_as_float(mx));
         }
         named_bar_sync(1, BUILDER_THREADS);
+        BRV_STAMP(34);
 
         // ---- main loop: window, fold, scale, split, store ------------------------
         const int half = lane >> 4;                // which of the warp's two rows per pass
@@ -331,6 +353,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
             if (pr == 0 && row < rows_eff) rowinfo[row].y = v;
         }
         named_bar_sync(1, BUILDER_THREADS);
+        BRV_STAMP(35);
 
         // ---- epilogue ---------------------------------------------------------------
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -348,6 +371,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
         }
         mbar_wait(&accum_bar, 0);
         tcgen05_fence_after();
+        BRV_STAMP(36);
         // every MMA has retired: the pipeline stages are free, reuse them as staging
         float* stg = reinterpret_cast<float*>(stages) + (size_t)bw * 32 * EPI_PITCH;
         const int pitch = 2 * p.n_bins;
@@ -394,6 +418,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
             *reinterpret_cast<float2*>(obase + (int64_t)lane * pitch + 2 * Hf) =
                 make_float2(v * p.post_scale, 0.f);
         }
+        BRV_STAMP(37);
         tcgen05_fence_before();
     }
     __syncthreads();
@@ -1188,7 +1213,9 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
             const int64_t t0 = (int64_t)tile * p.adv;
             const int rows_eff = (int)max((int64_t)0, min((int64_t)TILE_M, p.n_frames - t0));
             const float2* xs = p.spec + sig * p.ss;
+            BRV_STAMP(n * 8 + 0);
             mbar_wait(&scale_full[slot], (uint32_t)((n >> 1) & 1));
+            BRV_STAMP(n * 8 + 1);
 
             // ---- main loop: load (L2-resident after the scouts), scale, split, store ----
             if (FRAMES_FAST) {
@@ -1343,6 +1370,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                 }
             }
             named_bar_sync(1, BUILDER_THREADS);
+            BRV_STAMP(n * 8 + 2);
 
             // ---- epilogue: TMEM -> segments -> lane-rotated overlap-add -> skewed rows ----
             {
@@ -1355,6 +1383,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                 const float fq = live ? (ri.y - ri.z + ri.w) * p.wq : 0.f;
                 const float f3q = live ? (ri.y + ri.z + ri.w) * p.w3q : 0.f;
                 mbar_wait(&accum_bar, (uint32_t)(n & 1));
+                BRV_STAMP(n * 8 + 3);
                 tcgen05_fence_after();
                 float* my_row = orow + row * pitch;
                 float* my_spill = spill + ((q + 1) * 3 + lane) * H;
@@ -1463,8 +1492,10 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                     for (int a = 0; a < 4; ++a) carry[a] = B[a][0];
                 }
                 tcgen05_fence_before();
+                BRV_STAMP(n * 8 + 4);
             }
             named_bar_sync(1, BUILDER_THREADS);
+            BRV_STAMP(n * 8 + 5);
 
             // ---- copy-out: finished hop blocks, * 1 / envelope, centre trim ---------------
             {
@@ -1493,6 +1524,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
             // the output rows alias the operand stages: nobody may start building the
             // next tile before every warp has copied its rows out
             named_bar_sync(1, BUILDER_THREADS);
+            BRV_STAMP(n * 8 + 6);
             if (lane == 0) {
                 mbar_arrive(&region_free);
                 mbar_arrive(&scale_empty[slot]);
