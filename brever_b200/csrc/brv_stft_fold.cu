@@ -1832,8 +1832,13 @@ static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool c
     // consecutive tiles and wins once every SM has a few tiles to pipeline (cfg5: 760 -> 620 us);
     // with one or two tiles per SM its fill / drain latency loses to one CTA per tile
     // (cfg2: 46 vs 60 us).  Variant 2 / 3 force one or the other for A/B runs.
-    const bool one_per_cta = g_brv_fold_variant == 2 ||
-                             (g_brv_fold_variant != 3 && grid < 3LL * fp->sm_count);
+    // For Q = 128 with full 128-row tiles (n_fft 512 / 510 at hop <= 128) the persistent kernel's
+    // two operand-build passes per tile cost more than its overlap wins at any tile count
+    // (128 x 8 s: 163 vs 187 us plain, 224 vs 276 us compressed): one CTA per tile there too.
+    const bool one_per_cta =
+        g_brv_fold_variant == 2 ||
+        (g_brv_fold_variant != 3 &&
+         (grid < 3LL * fp->sm_count || (fp->q == MAX_Q && prm.rows == TILE_M)));
     if (one_per_cta) {
         stft_fold_kernel<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(fp->fwd.map, prm);
         BRV_LAUNCH_CHECK("stft_fold_kernel");
