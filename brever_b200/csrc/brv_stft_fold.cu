@@ -314,8 +314,10 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int row = bw * 16 + 2 * i + half;
-                    if (row >= rows_eff) continue;
-                    const float* fr = span + shift + row * H;
+                    // rows >= rows_eff are built too (their scale is 0 / their inputs are zero or stale,
+                    // their accumulator rows are never read): a `continue` here would split the unrolled rows
+                    // into separate basic blocks and serialise their dependent chains
+                    const float* fr = span + shift + (row < rows_eff ? row : 0) * H;   // stay inside the span
                     const float a0 = fr[n0] * w0.x, a1 = fr[n0 + 1] * w1.x;
                     const float b0 = fr[Hf - n0] * w0.y, b1 = fr[Hf - n0 - 1] * w1.y;
                     const float c0 = fr[Hf + n0] * w0.z, c1 = fr[Hf + n0 + 1] * w1.z;
@@ -387,22 +389,33 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
             tmem_ld16_nowait(tq + (uint32_t)(2 * Q + m0), r2);
             tmem_ld16_nowait(tq + (uint32_t)(3 * Q + m0), r3);
             tmem_ld_wait();
+            // three straight-line passes over the registers (a uniform `if (compress)` inside one
+            // loop would cut the 16 independent columns into basic blocks and serialise them)
+            float* f0 = reinterpret_cast<float*>(r0);      // Re X[2m]
+            float* f1 = reinterpret_cast<float*>(r1);      // Re X[2m+1]
+            float* f2 = reinterpret_cast<float*>(r2);      // Im X[2m]
+            float* f3 = reinterpret_cast<float*>(r3);      // Im X[2m+1]
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float sg = (j & 1) ? -1.f : 1.f;        // m0 is even
-                float re_e = __uint_as_float(r0[j]) * g0 + sg * eeq;
-                if (j == 0 && m0 == 0) re_e *= p.dc_scale;         // DC bin (its Im is exactly 0)
-                float re_o = __uint_as_float(r1[j]) * g0;
-                float im_e = __uint_as_float(r2[j]) * g0;
-                float im_o = __uint_as_float(r3[j]) * g0 - sg * ooq;
-                if (p.post_expo != 0.f) {
-                    compress(re_e, im_e, p.post_expo);
-                    compress(re_o, im_o, p.post_expo);
-                }
-                *reinterpret_cast<float4*>(stg + lane * EPI_PITCH + 4 * j) =
-                    make_float4(re_e * p.post_scale, im_e * p.post_scale, re_o * p.post_scale,
-                                im_o * p.post_scale);
+                f0[j] = f0[j] * g0 + sg * eeq;
+                if (j == 0 && m0 == 0) f0[j] *= p.dc_scale;        // DC bin (its Im is exactly 0)
+                f1[j] = f1[j] * g0;
+                f2[j] = f2[j] * g0;
+                f3[j] = f3[j] * g0 - sg * ooq;
             }
+            if (p.post_expo != 0.f) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    compress(f0[j], f2[j], p.post_expo);
+                    compress(f1[j], f3[j], p.post_expo);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                *reinterpret_cast<float4*>(stg + lane * EPI_PITCH + 4 * j) =
+                    make_float4(f0[j] * p.post_scale, f2[j] * p.post_scale, f1[j] * p.post_scale,
+                                f3[j] * p.post_scale);
             __syncwarp();
             float* ocol = obase + 4 * m0 + 2 * lane;
 #pragma unroll 4
@@ -768,6 +781,7 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
             }
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
+                const float psign = pass == 0 ? 1.f : -1.f, pnyq = pass == 0 ? 1.f : 0.f;
                 float nyq[RI];
 #pragma unroll
                 for (int i = 0; i < RI; ++i) nyq[i] = 0.f;
@@ -781,23 +795,21 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
 #pragma unroll
                     for (int i = 0; i < RI; ++i) {
                         const int row = bw * F2_ROWS_PER_WARP + 2 * i + half;
-                        if (row >= rows_eff) continue;
-                        const float* fr = span + shift + row * H;
+                        // rows >= rows_eff are built too (their scale is 0 / their inputs are zero or stale,
+                        // their accumulator rows are never read): a `continue` here would split the unrolled rows
+                        // into separate basic blocks and serialise their dependent chains
+                        const float* fr = span + shift + (row < rows_eff ? row : 0) * H;   // stay inside the span
                         const float a0 = fr[n0] * w0.x, a1 = fr[n0 + 1] * w1.x;
                         const float b0 = fr[Hf - n0] * w0.y, b1 = fr[Hf - n0 - 1] * w1.y;
                         const float c0 = fr[Hf + n0] * w0.z, c1 = fr[Hf + n0 + 1] * w1.z;
                         const float d0 = n0 ? fr[N - n0] * w0.w : 0.f, d1 = fr[N - n0 - 1] * w1.w;
                         const float s0 = a0 + d0, r0 = b0 + c0, s1 = a1 + d1, r1 = b1 + c1;
                         const float sd0 = a0 - d0, rd0 = b0 - c0, sd1 = a1 - d1, rd1 = b1 - c1;
-                        float u0, u1, v0, v1;
-                        if (pass == 0) {
-                            u0 = s0 + r0; u1 = s1 + r1;            // ee
-                            v0 = sd0 - rd0; v1 = sd1 - rd1;        // oe
-                            nyq[i] += u0 - u1;                     // (-1)^n ee[n], n0 even
-                        } else {
-                            u0 = s0 - r0; u1 = s1 - r1;            // eo
-                            v0 = sd0 + rd0; v1 = sd1 + rd1;        // oo
-                        }
+                        // pass 0: ee = s + r, oe = sd - rd; pass 1: eo = s - r, oo = sd + rd -- by
+                        // sign, not by branch (a branch would serialise the unrolled rows)
+                        const float u0 = fmaf(psign, r0, s0), u1 = fmaf(psign, r1, s1);
+                        const float v0 = fmaf(-psign, rd0, sd0), v1 = fmaf(-psign, rd1, sd1);
+                        nyq[i] = fmaf(pnyq, u0 - u1, nyq[i]);      // (-1)^n ee[n], n0 even (pass 0 only)
                         const float sc = rscale[i];
                         uint8_t* dst = sa + row * (BK * 2) +
                                        ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
@@ -1062,6 +1074,14 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
         for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
             const int slot = n & 1;
             mbar_wait_relaxed(&scale_empty[slot], (uint32_t)(((n >> 1) & 1) ^ 1));
+            if (n == 0) {
+                // nobody runs ahead of the first tile: the builders (twice the threads, plain
+                // 8-byte loads instead of a cp.async ring) take its row maxima themselves;
+                // the scouts start on tile 1
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&scale_full[slot]);
+                continue;
+            }
             float4* ri = rowinfo2 + slot * TILE_M;
             const int64_t sig = tile_id / p.tiles_per_signal;
             const int64_t t0 = (int64_t)(tile_id % p.tiles_per_signal) * p.adv;
@@ -1215,6 +1235,71 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
             const float2* xs = p.spec + sig * p.ss;
             BRV_STAMP(n * 8 + 0);
             mbar_wait(&scale_full[slot], (uint32_t)((n >> 1) & 1));
+            if (n == 0) {
+                // ---- first tile: row maxima (power-of-two scales) and Nyquist terms by the
+                //      builders; the tile is L2-resident afterwards for the main loop ----------
+                if (FRAMES_FAST) {
+                    const int row = bt & 127, kh = bt >> 7;
+                    const bool live = row < rows_eff;
+                    const float2* xr = xs + (t0 + (live ? row : 0)) * p.sf;
+                    float m = 0.f;
+                    for (int b0 = kh * Q; b0 < (kh + 1) * Q; b0 += 32) {
+                        float2 v[32];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            v[e] = live ? __ldg(xr + (int64_t)(b0 + e) * p.sb) : make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            float2 c = prep_bin<DECOMP>(v[e], p.pre_scale, p.pre_expo);
+                            if (b0 + e == 0) c.y = 0.f;
+                            m = fmaxf(m, abs2_finite(c));
+                        }
+                    }
+                    scratch[kh * 128 + row] = m;
+                    named_bar_sync(1, BUILDER_THREADS);
+                    if (kh == 0) {
+                        float ny = 0.f;
+                        if (live && !ODD)
+                            ny = prep_bin<DECOMP>(__ldg(xr + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x *
+                                 p.edge_gain;
+                        rowinfo[row] = make_float4(row_scale(fmaxf(scratch[row], scratch[128 + row])),
+                                                   0.f, 0.f, ny);
+                    }
+                } else {
+                    const int nj = Q / 16;             // 32-bin groups below the Nyquist bin
+#pragma unroll 1
+                    for (int rb = 0; rb < 16; rb += 4) {
+                        float2 v[4][9];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int row = bw * 16 + rb + r;
+                            const float2* xr = xs + (t0 + row) * p.sf;     // sb == 1
+#pragma unroll
+                            for (int j = 0; j < 9; ++j) {
+                                const int b = j * 32 + lane;
+                                v[r][j] = (row < rows_eff && b <= Hf) ? __ldg(xr + b)
+                                                                      : make_float2(0.f, 0.f);
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int row = bw * 16 + rb + r;
+                            float m = 0.f, ny = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 9; ++j) {
+                                float2 c = prep_bin<DECOMP>(v[r][j], p.pre_scale, p.pre_expo);
+                                if (j == 0 && lane == 0) c.y = 0.f;   // Im X[0] never reaches the output
+                                if (j < nj) m = fmaxf(m, abs2_finite(c));
+                                if (!ODD && j == nj && lane == 0) ny = c.x * p.edge_gain;
+                            }
+#pragma unroll
+                            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                            if (lane == 0) rowinfo[row] = make_float4(row_scale(m), 0.f, 0.f, ny);
+                        }
+                    }
+                }
+                named_bar_sync(1, BUILDER_THREADS);
+            }
             BRV_STAMP(n * 8 + 1);
 
             // ---- main loop: load (L2-resident after the scouts), scale, split, store ----
@@ -1335,7 +1420,9 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int row = bw * 16 + 2 * i + half;
-                            if (row >= rows_eff) continue;
+                            // rows >= rows_eff are built too (their scale is 0 / their inputs are zero or stale,
+                            // their accumulator rows are never read): a `continue` here would split the unrolled rows
+                            // into separate basic blocks and serialise their dependent chains
                             const float sc = rscale[i];
                             uint8_t* dst = sa + row * (BK * 2) +
                                            ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
@@ -1424,30 +1511,27 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                         float seg0 = (((ce + co) - (se + so)) * g0 + sg) * wa.x;
                         float seg2 = (((ce - co) - (se - so)) * g0 + sg) * wa.z;
                         float seg1, seg3;
+                        // (selects, not branches: a branch inside the unrolled offsets would split
+                        //  them into basic blocks and serialise their dependent chains; the table
+                        //  reads one entry past either end land in valid shared memory and are dropped)
                         if (ODD) {
                             // column Q-1-o -> position N/2 - n
                             const float ce1 = __uint_as_float(B[0][7 - i]), co1 = __uint_as_float(B[1][7 - i]);
                             const float se1 = __uint_as_float(B[2][7 - i]), so1 = __uint_as_float(B[3][7 - i]);
                             seg1 = ((ce1 - co1) + (se1 - so1)) * g0 * wtab[Q - 1 - o].y;
-                            if (o == Q - 1) {          // position N - (Q-1): column Q-1 = A[.][7]
-                                seg2 = ((ce + co) + (se + so)) * g0 * wa.w;
-                                seg3 = 0.f;
-                            } else {
-                                const float ce2 = __uint_as_float(i < 7 ? A[0][(i + 1) & 7] : XA[0]);
-                                const float co2 = __uint_as_float(i < 7 ? A[1][(i + 1) & 7] : XA[1]);
-                                const float se2 = __uint_as_float(i < 7 ? A[2][(i + 1) & 7] : XA[2]);
-                                const float so2 = __uint_as_float(i < 7 ? A[3][(i + 1) & 7] : XA[3]);
-                                seg2 = ((ce2 - co2) - (se2 - so2)) * g0 * wtab[o + 1].z;
-                                // column Q-2-o -> position N - n (column 0 carries weight 0)
-                                const float ce3 = __uint_as_float(i < 7 ? B[0][(6 - i) & 7] : XB[0]);
-                                const float co3 = __uint_as_float(i < 7 ? B[1][(6 - i) & 7] : XB[1]);
-                                const float se3 = __uint_as_float(i < 7 ? B[2][(6 - i) & 7] : XB[2]);
-                                const float so3 = __uint_as_float(i < 7 ? B[3][(6 - i) & 7] : XB[3]);
-                                seg3 = ((ce3 + co3) + (se3 + so3)) * g0 * wtab[Q - 2 - o].w;
-                            }
-                        } else if (o == 0) {
-                            seg1 = fq;
-                            seg3 = f3q;
+                            const float ce2 = __uint_as_float(i < 7 ? A[0][(i + 1) & 7] : XA[0]);
+                            const float co2 = __uint_as_float(i < 7 ? A[1][(i + 1) & 7] : XA[1]);
+                            const float se2 = __uint_as_float(i < 7 ? A[2][(i + 1) & 7] : XA[2]);
+                            const float so2 = __uint_as_float(i < 7 ? A[3][(i + 1) & 7] : XA[3]);
+                            // column Q-2-o -> position N - n (column 0 carries weight 0)
+                            const float ce3 = __uint_as_float(i < 7 ? B[0][(6 - i) & 7] : XB[0]);
+                            const float co3 = __uint_as_float(i < 7 ? B[1][(6 - i) & 7] : XB[1]);
+                            const float se3 = __uint_as_float(i < 7 ? B[2][(6 - i) & 7] : XB[2]);
+                            const float so3 = __uint_as_float(i < 7 ? B[3][(6 - i) & 7] : XB[3]);
+                            const bool last = i == 7 && o == Q - 1;    // position N - (Q-1): column Q-1 = A[.][7]
+                            seg2 = last ? ((ce + co) + (se + so)) * g0 * wa.w
+                                        : ((ce2 - co2) - (se2 - so2)) * g0 * wtab[o + 1].z;
+                            seg3 = last ? 0.f : ((ce3 + co3) + (se3 + so3)) * g0 * wtab[Q - 2 - o].w;
                         } else {
                             const float4 wb = wtab[Q - o];
                             const float ce2 = __uint_as_float(i == 0 ? carry[0] : B[0][8 - i]);
@@ -1456,23 +1540,24 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                             const float so2 = __uint_as_float(i == 0 ? carry[3] : B[3][8 - i]);
                             seg1 = (((ce2 - co2) + (se2 - so2)) * g0 + sg) * wb.y;
                             seg3 = (((ce2 + co2) + (se2 + so2)) * g0 + sg) * wb.w;
+                            if (i == 0) {                              // o == 0 only happens at i == 0
+                                seg1 = o == 0 ? fq : seg1;
+                                seg3 = o == 0 ? f3q : seg3;
+                            }
                         }
                         if (!live) seg0 = seg1 = seg2 = seg3 = 0.f;    // dead rows hold garbage
                         if (HQ == 1) {
                             const float r1 = rot(seg1, lane, 1), r2 = rot(seg2, lane, 2),
                                         r3 = rot(seg3, lane, 3);
                             float acc = seg0;
-                            if (lane >= 1) acc += r1;
-                            if (lane >= 2) acc += r2;
-                            if (lane >= 3) acc += r3;
+                            acc += lane >= 1 ? r1 : 0.f;
+                            acc += lane >= 2 ? r2 : 0.f;
+                            acc += lane >= 3 ? r3 : 0.f;
                             my_row[o] = acc;
-                            if (do_spill) {
-                                float sp = 0.f;
-                                if (lane < 1) sp += r1;
-                                if (lane < 2) sp += r2;
-                                sp += r3;
-                                my_spill[o] = sp;
-                            }
+                            float sp = lane < 1 ? r1 : 0.f;
+                            sp += lane < 2 ? r2 : 0.f;
+                            sp += r3;
+                            if (do_spill) my_spill[o] = sp;
                         } else if (HQ == 2) {
                             const float r2 = rot(seg2, lane, 1), r3 = rot(seg3, lane, 1);
                             my_row[o] = lane >= 1 ? seg0 + r2 : seg0;
@@ -1508,19 +1593,34 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                     const int qq = r >> 5, lr = r & 31;
                     const float* sp = (qq > 0 && lr < p.halo) ? spill + (qq * 3 + lr) * H : nullptr;
                     const int64_t i0 = u * H - p.origin;
-                    const bool interior = u >= R - 1 && u <= p.n_frames - 1;
+                    const bool use_reg = !p.inv_env || (u >= R - 1 && u <= p.n_frames - 1);
+                    // offsets [lo, hi) of this hop block that exist in the output, as 32-bit
+                    // values computed once per row (the warps of this phase run dependent
+                    // chains at ~1 instruction per 5 cycles: per-element 64-bit range checks
+                    // made the copy-out 4x longer than its loads and stores)
+                    const int lo = i0 < 0 ? (int)min((int64_t)H, -i0) : 0;
+                    const int hi = (int)max((int64_t)0, min((int64_t)H, p.out_len - i0));
+                    float* yrow = ys + i0;             // dereferenced inside [lo, hi) only
+                    if (lo == 0 && hi == H && use_reg && !sp) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int off = lane + 32 * j;
-                        const int64_t i = i0 + off;
-                        if (off < H && i >= 0 && i < p.out_len) {
-                            float v = src[off];
-                            if (sp) v += sp[off];
-                            ys[i] = v * ((interior || !p.inv_env) ? env_reg[j] : __ldg(p.inv_env + i));
+                        for (int j = 0; j < 8; ++j) {
+                            const int off = lane + 32 * j;
+                            if (off < H) yrow[off] = src[off] * env_reg[j];
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int off = lane + 32 * j;
+                            if (off >= lo && off < hi) {
+                                float v = src[off];
+                                if (sp) v += sp[off];
+                                yrow[off] = v * (use_reg ? env_reg[j] : __ldg(p.inv_env + i0 + off));
+                            }
                         }
                     }
                 }
             }
+            BRV_STAMP(n * 8 + 7);
             // the output rows alias the operand stages: nobody may start building the
             // next tile before every warp has copied its rows out
             named_bar_sync(1, BUILDER_THREADS);

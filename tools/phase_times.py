@@ -41,15 +41,16 @@ def main():
         f = t[32:38]
         print('forward  (us since start): span %.1f  rowscale %.1f  build %.1f  mma-drain %.1f  epilogue %.1f'
               % tuple((f[i] - f[0]) / 1e3 for i in range(1, 6)))
-        flush.zero_()
+        if '--chain' not in sys.argv:      # --chain: the spectrogram stays L2-resident, as in a step
+            flush.zero_()
         torch.cuda.synchronize()
         y = stft.backward(spec)
         torch.cuda.synchronize()
         t = stamps()
         for n in range(2):
-            s = t[n * 8:n * 8 + 7]
+            s = t[n * 8:n * 8 + 8]
             print('inverse tile %d (us since tile-0 start): top %.1f  scouts-done %.1f  build %.1f  mma-drain %.1f  '
-                  'epilogue %.1f  bar %.1f  copy-out %.1f' % ((n,) + tuple((v - t[0]) / 1e3 for v in s)))
+                  'epilogue %.1f  bar %.1f  copy-out+bar %.1f  (copy-out loop of warp 0 done %.1f)' % ((n,) + tuple((v - t[0]) / 1e3 for v in s)))
 
 
 if __name__ == '__main__':
