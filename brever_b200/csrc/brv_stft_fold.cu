@@ -304,6 +304,22 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
         for (int kc = 0; kc < Q / BK; ++kc) {
             const int n0 = kc * BK + 2 * pr;
             const float4 w0 = wtab[n0], w1 = wtab[n0 + 1];
+            // window and first fold once per k-chunk, before waiting for a stage: both sub-GEMM
+            // pairs read the same four samples per (row, n), and the loads run under the wait
+            float sp0[8], sp1[8], rp0[8], rp1[8], sm0[8], sm1[8], rm0[8], rm1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = bw * 16 + 2 * i + half;
+                // rows >= rows_eff are built too (scale 0, accumulator rows never read): a branch
+                // here would split the unrolled rows into basic blocks and serialise their chains
+                const float* fr = span + shift + (row < rows_eff ? row : 0) * H;   // stay inside the span
+                const float a0 = fr[n0] * w0.x, a1 = fr[n0 + 1] * w1.x;
+                const float b0 = fr[Hf - n0] * w0.y, b1 = fr[Hf - n0 - 1] * w1.y;
+                const float c0 = fr[Hf + n0] * w0.z, c1 = fr[Hf + n0 + 1] * w1.z;
+                const float d0 = n0 ? fr[N - n0] * w0.w : 0.f, d1 = fr[N - n0 - 1] * w1.w;
+                sp0[i] = a0 + d0; sp1[i] = a1 + d1; rp0[i] = b0 + c0; rp1[i] = b1 + c1;
+                sm0[i] = a0 - d0; sm1[i] = a1 - d1; rm0[i] = b0 - c0; rm1[i] = b1 - c1;
+            }
 #pragma unroll
             for (int pair = 0; pair < 2; ++pair) {
                 const int it = kc * 2 + pair;
@@ -314,24 +330,14 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int row = bw * 16 + 2 * i + half;
-                    // rows >= rows_eff are built too (their scale is 0 / their inputs are zero or stale,
-                    // their accumulator rows are never read): a `continue` here would split the unrolled rows
-                    // into separate basic blocks and serialise their dependent chains
-                    const float* fr = span + shift + (row < rows_eff ? row : 0) * H;   // stay inside the span
-                    const float a0 = fr[n0] * w0.x, a1 = fr[n0 + 1] * w1.x;
-                    const float b0 = fr[Hf - n0] * w0.y, b1 = fr[Hf - n0 - 1] * w1.y;
-                    const float c0 = fr[Hf + n0] * w0.z, c1 = fr[Hf + n0 + 1] * w1.z;
-                    const float d0 = n0 ? fr[N - n0] * w0.w : 0.f, d1 = fr[N - n0 - 1] * w1.w;
                     float u0, u1, v0, v1;          // the pair's two folded sequences at n0, n0+1
                     if (pair == 0) {
-                        const float s0 = a0 + d0, r0 = b0 + c0, s1 = a1 + d1, r1 = b1 + c1;
-                        u0 = s0 + r0; u1 = s1 + r1;            // ee
-                        v0 = s0 - r0; v1 = s1 - r1;            // eo
-                        nyq[i] += u0 - u1;                     // (-1)^n ee[n], n0 even
+                        u0 = sp0[i] + rp0[i]; u1 = sp1[i] + rp1[i];    // ee
+                        v0 = sp0[i] - rp0[i]; v1 = sp1[i] - rp1[i];    // eo
+                        nyq[i] += u0 - u1;                             // (-1)^n ee[n], n0 even
                     } else {
-                        const float s0 = a0 - d0, r0 = b0 - c0, s1 = a1 - d1, r1 = b1 - c1;
-                        u0 = s0 - r0; u1 = s1 - r1;            // oe
-                        v0 = s0 + r0; v1 = s1 + r1;            // oo
+                        u0 = sm0[i] - rm0[i]; u1 = sm1[i] - rm1[i];    // oe
+                        v0 = sm0[i] + rm0[i]; v1 = sm1[i] + rm1[i];    // oo
                     }
                     const float sc = rscale[i];
                     uint8_t* dst = sa + row * (BK * 2) +
@@ -418,10 +424,12 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
                                 f3[j] * p.post_scale);
             __syncwarp();
             float* ocol = obase + 4 * m0 + 2 * lane;
-#pragma unroll 4
+            const float* srow = stg + 2 * lane;
+#pragma unroll 8
             for (int rr = 0; rr < rows_w; ++rr) {
-                const float2 v = *reinterpret_cast<const float2*>(stg + rr * EPI_PITCH + 2 * lane);
-                *reinterpret_cast<float2*>(ocol + (int64_t)rr * pitch) = v;
+                *reinterpret_cast<float2*>(ocol) = *reinterpret_cast<const float2*>(srow);
+                ocol += pitch;
+                srow += EPI_PITCH;
             }
             __syncwarp();
         }
@@ -1385,31 +1393,39 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                     const int row = bw * 16 + 2 * i + half;
                     rscale[i] = row < rows_eff ? rowinfo[row].x : 0.f;
                 }
-                for (int kc = 0; kc < Q / BK; ++kc) {
-                    const int m0 = kc * BK + 2 * pr;   // bins 2 m0 .. 2 m0 + 3
-                    float2 c[8][4];
+                // bins 2 m0 .. 2 m0 + 3 of the warp's 16 rows for k-chunk kc (L2-resident after the
+                // row-maxima pass).  Issuing the next chunk's loads before this one is consumed was
+                // tried: 64 more live registers spill and cost more than the latency they hide.
+                auto load_chunk = [&](float2 (&dst)[8][4], int kc) {
+                    const int m0 = kc * BK + 2 * pr;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = bw * 16 + 2 * i + half;
                         const float2* xr = xs + (t0 + row) * p.sf + (int64_t)(2 * m0) * p.sb;
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            c[i][e] = row < rows_eff ? __ldg(xr + (int64_t)e * p.sb)
-                                                     : make_float2(0.f, 0.f);
+                            dst[i][e] = row < rows_eff ? __ldg(xr + (int64_t)e * p.sb)
+                                                       : make_float2(0.f, 0.f);
                     }
+                };
+                for (int kc = 0; kc < Q / BK; ++kc) {
+                    const int m0 = kc * BK + 2 * pr;   // bins 2 m0 .. 2 m0 + 3
+                    float2 c[8][4];
+                    load_chunk(c, kc);
+                    // (selects, not lane-dependent branches, inside the unrolled rows)
+                    const bool dc = m0 == 0, ny_im = ODD && m0 == Q - 2;
+                    const float dc_mul = dc ? p.dc_gain : 1.f, dc_half = dc ? 0.5f : 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             c[i][e] = prep_bin<DECOMP>(c[i][e], p.pre_scale, p.pre_expo);
-                        if (m0 == 0) {
-                            c[i][0].y = 0.f;           // Im X[0] is ignored by the c2r inverse
-                            c[i][0].x *= p.dc_gain;
-                        }
-                        if (ODD && m0 == Q - 2) c[i][3].y = 0.f;      // so is Im X[N/2]
+                        c[i][0].y = dc ? 0.f : c[i][0].y;      // Im X[0] is ignored by the c2r inverse
+                        c[i][0].x *= dc_mul;
+                        c[i][3].y = ny_im ? 0.f : c[i][3].y;   // so is Im X[N/2]
                         pacc[i] += c[i][0].x - c[i][2].x;
                         racc[i] += c[i][1].y - c[i][3].y;
-                        if (m0 == 0) pacc[i] -= 0.5f * c[i][0].x;
+                        pacc[i] -= dc_half * c[i][0].x;
                     }
 #pragma unroll
                     for (int pair = 0; pair < 2; ++pair, ++g) {
