@@ -1,9 +1,10 @@
 // Symmetry-folded tensor-core STFT for sm_100a (tcgen05 + TMEM + TMA), fp32-grade.
 //
 // STFT.forward (brever/modules/stft.py:59-89) for one-sided transforms with
-// n_fft in {128, 256, 384, 512} and {126, 254, 382, 510} (N = 4Q - 2: the same fold with
-// N/2 odd — SGMSE's 510-point transform; see FoldFwdParams::odd).  A real DFT of length N = 4Q splits, by the
-// even/odd symmetries of cos and sin about n = N/2 and n = N/4 (two radix-2
+// n_fft in {128, 256, 384, 512} and {126, 254, 382, 510} (N = 4Q - 2: the same fold
+// with N/2 odd — SGMSE's 510-point transform; see FoldFwdParams::odd).  ConvSTFT
+// (stft.py:201-319) runs on the same kernels with another frame origin (end of file).
+// A real DFT of length N = 4Q splits, by the even/odd symmetries of cos and sin about n = N/2 and n = N/4 (two radix-2
 // decimation-in-frequency steps done on the *input* side), into four independent
 // Q x Q contractions:
 //
@@ -84,8 +85,7 @@ constexpr int SMEM_STAGES = STAGES * STAGE_BYTES;              // 131072
 constexpr int SMEM_SPAN = SPAN_ALLOC * 4;                      // 67200
 constexpr int SMEM_WTAB = MAX_Q * 16;                          // 2048
 constexpr int SMEM_ROWINFO = TILE_M * 8;                       // 1024 (scale, nyquist)
-constexpr int SMEM_BMAX = (SPAN_ALLOC / 32) * 4;               // 2100
-constexpr int SMEM_BYTES = 1024 + SMEM_STAGES + SMEM_SPAN + SMEM_WTAB + SMEM_ROWINFO + 2112;
+constexpr int SMEM_BYTES = 1024 + SMEM_STAGES + SMEM_SPAN + SMEM_WTAB + SMEM_ROWINFO + 2112;   // + per-32-sample maxima
 
 struct FoldFwdParams {
     const float* x;
@@ -896,7 +896,6 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
 constexpr int INV_REGION = 132096;             // stages (128 KB) aliased with the output rows
 constexpr int INV_SPILL = 12 * 256 * 4;        // 4 warp quarters x 3 halo blocks x H floats
 constexpr int INV_SCOUT_WARPS = 4;
-constexpr int INV_SCOUT_THREADS = INV_SCOUT_WARPS * 32;
 constexpr int INV_THREADS = 512;              // 4 warpgroups: control, scouts, 2 x builders
 constexpr int INV_FIRST_BUILDER = 8;
 constexpr int RING_DEPTH = 4;
