@@ -931,6 +931,11 @@ struct FoldInvParams {
     float edge_gain;
     float dc_gain;               // DC input (equal to edge_gain except for ConvSTFT: sqrt(2))
     int origin;                  // output sample i sits at overlap-add position i + origin
+    // contiguous rows (sb == 1, sf == n_fft / 2 + 1): the scouts stage 8 rows with one bulk copy;
+    // a chunk whose 16-byte rounded range would leave [spec_lo, spec_hi) (the tensor's own
+    // bytes) is copied element-wise instead
+    int bulk;
+    uintptr_t spec_lo, spec_hi;
 };
 
 template <bool DECOMP>
@@ -952,6 +957,15 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld1_nowait(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(taddr));
+}
+// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on an mbarrier;
+// addresses and size are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ float rot(float v, int lane, int s) {
     return __shfl_sync(0xffffffffu, v, (lane - s) & 31);
@@ -979,6 +993,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
     __shared__ __align__(8) uint64_t region_free;      // output rows copied out: stages reusable
     __shared__ __align__(8) uint64_t scale_full[2];    // scouts -> builders (row scales ready)
     __shared__ __align__(8) uint64_t scale_empty[2];   // builders -> scouts (slot reusable)
+    __shared__ __align__(8) uint64_t chunk_bar[RING_DEPTH];   // bulk chunk copy landed in the ring slot
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -1004,6 +1019,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
             mbar_init(&scale_full[b], INV_SCOUT_WARPS);
             mbar_init(&scale_empty[b], BUILDERS);
         }
+        for (int b = 0; b < RING_DEPTH; ++b) mbar_init(&chunk_bar[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
@@ -1151,18 +1167,48 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                 // lanes along bins, so only warp-level synchronisation is needed
                 const int nch = TILE_M / 8;
                 constexpr int ROWS_PER_WARP = 8 / INV_SCOUT_WARPS;
+                // Chunk copies: when the rows are contiguous (sf == Hf + 1) the 8 rows of a chunk are
+                // one run of bytes and ONE bulk copy (TMA engine, no per-element instructions) brings
+                // them in, over the run's 16-byte rounded range (rows sit at 8-byte alignment: the
+                // data starts 0 or 8 bytes into the ring slot, rows at pitch Hf + 1).  Per-row bulk
+                // copies were tried first: 128 small requests per tile made the scouts the critical
+                // path (cfg5 510 -> 667 us).  A chunk whose rounded range would leave the tensor,
+                // and inputs that are not plain contiguous rows, use 8-byte cp.async as before.
+                // 16 chunks per tile = 4 uses of each ring slot: the mbarrier parity of chunk cc is
+                // (cc >> 2) & 1 in every tile.
+                const int f_in = Hf + 1;
+                auto chunk_range = [&](int c, uintptr_t& a0, uint32_t& sz, int& off) {
+                    const int nrows = min(8, rows_eff - 8 * c);
+                    const uintptr_t a = (uintptr_t)(xs + (t0 + 8 * c) * p.sf);
+                    a0 = a & ~(uintptr_t)15;
+                    off = (int)((a - a0) >> 3);
+                    sz = ((uint32_t)(a - a0) + (uint32_t)(nrows * f_in) * 8u + 15u) & ~15u;
+                    return p.bulk && nrows > 0 && a0 >= p.spec_lo && a0 + sz <= p.spec_hi;
+                };
                 for (int c = 0; c < nch + RING_DEPTH - 1; ++c) {
                     if (c < nch) {
                         float2* dst = reinterpret_cast<float2*>(ring + (c % RING_DEPTH) * RING_CHUNK);
+                        uintptr_t a0;
+                        uint32_t sz;
+                        int off;
+                        const bool bulk_chunk = chunk_range(c, a0, sz, off);
+                        if (bulk_chunk) {
+                            if (st == 0) {
+                                mbar_arrive_expect_tx(&chunk_bar[c % RING_DEPTH], sz);
+                                bulk_g2s(dst, reinterpret_cast<const void*>(a0), sz, &chunk_bar[c % RING_DEPTH]);
+                            }
+                        } else {
+                            if (st == 0) mbar_arrive_expect_tx(&chunk_bar[c % RING_DEPTH], 0u);
 #pragma unroll
-                        for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-                            const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * c + r;
-                            if (row < rows_eff) {
-                                const float2* xr = xs + (t0 + row) * p.sf;
+                            for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+                                const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * c + r;
+                                if (row < rows_eff) {
+                                    const float2* xr = xs + (t0 + row) * p.sf;
 #pragma unroll
-                                for (int j = 0; j < 9; ++j) {
-                                    const int b = j * 32 + lane;
-                                    if (b <= Hf) cp_async8(dst + r * RING_ROW + b, xr + b);   // sb == 1
+                                    for (int j = 0; j < 9; ++j) {
+                                        const int b = j * 32 + lane;
+                                        if (b <= Hf) cp_async8(dst + r * RING_ROW + b, xr + b);   // sb == 1
+                                    }
                                 }
                             }
                         }
@@ -1170,20 +1216,27 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                     cp_async_commit();
                     if (c >= RING_DEPTH - 1) {
                         cp_async_wait<RING_DEPTH - 1>();
-                        __syncwarp();
                         const int cc = c - (RING_DEPTH - 1);
-                        const float2* src =
+                        mbar_wait_relaxed(&chunk_bar[cc % RING_DEPTH], (uint32_t)((cc >> 2) & 1), 32);
+                        __syncwarp();
+                        const float2* ring_c =
                             reinterpret_cast<const float2*>(ring + (cc % RING_DEPTH) * RING_CHUNK);
+                        uintptr_t a0c;
+                        uint32_t szc;
+                        int offc;
+                        const bool bulk_chunk = chunk_range(cc, a0c, szc, offc);
+                        const int pitch_c = bulk_chunk ? f_in : RING_ROW;
 #pragma unroll
                         for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
                             const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * cc + r;
                             float m = 0.f, ny = 0.f;
                             if (row < rows_eff) {
+                                // data starts 0 or 1 elements into a bulk-copied slot
+                                const float2* src = ring_c + (bulk_chunk ? offc : 0) + r * pitch_c;
                                 float2 v[8];                 // bins lane + 32 j < Hf (Hf <= 256)
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
-                                    v[j] = j * 32 < Hf ? src[r * RING_ROW + j * 32 + lane]
-                                                       : make_float2(0.f, 0.f);
+                                    v[j] = j * 32 < Hf ? src[j * 32 + lane] : make_float2(0.f, 0.f);
                                 if (lane == 0) v[0].y = 0.f; // Im X[0] never reaches the output
                                 if (DECOMP) {
 #pragma unroll
@@ -1202,14 +1255,15 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                                     m = __uint_as_float(mb) * fabsf(p.pre_scale);
                                 }
                                 if (lane == 0 && !ODD)
-                                    ny = prep_bin<DECOMP>(src[r * RING_ROW + Hf], p.pre_scale, p.pre_expo).x *
-                                         p.edge_gain;
+                                    ny = prep_bin<DECOMP>(src[Hf], p.pre_scale, p.pre_expo).x * p.edge_gain;
                             }
 #pragma unroll
                             for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
                             if (lane == 0) ri[row] = make_float4(row_scale(m), 0.f, 0.f, ny);
                         }
-                        __syncwarp();
+                        // every scout warp reads the same chunk: all of them are done with the
+                        // slot before scout thread 0 refills it
+                        named_bar_sync(2, INV_SCOUT_WARPS * 32);
                     }
                 }
             }
@@ -2054,6 +2108,15 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     prm.total_tiles = n_sig * prm.tiles_per_signal;
     const unsigned grid = (unsigned)(prm.total_tiles < fp->sm_count ? prm.total_tiles : fp->sm_count);
     const bool frames_fast = prm.sb != 1;
+    {   // the bytes the (signal, frame, bin) view itself covers: bulk row copies stay inside them
+        const int64_t f_in = p->n_fft / 2 + 1;
+        // (16 KB chunks only: with the 8 KB chunks of n_fft = 256 three copies in flight do not
+        //  cover the bulk-copy latency and the scouts fall behind the builders, cfg5 510 -> 542 us)
+        prm.bulk = (!frames_fast && prm.sf == f_in && f_in >= 256 && (prm.ss >= 0 || n_sig == 1)) ? 1 : 0;
+        prm.spec_lo = (uintptr_t)prm.spec;
+        prm.spec_hi = prm.spec_lo +
+                      (uintptr_t)(((n_sig - 1) * (prm.ss > 0 ? prm.ss : 0) + (n_frames - 1) * prm.sf + f_in) * 8);
+    }
 #define BRV_LAUNCH_INV(HQ_, FF_)                                                                  \
     do {                                                                                          \
         if (decomp)                                                                               \
