@@ -1198,7 +1198,10 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                                 bulk_g2s(dst, reinterpret_cast<const void*>(a0), sz, &chunk_bar[c % RING_DEPTH]);
                             }
                         } else {
-                            if (st == 0) mbar_arrive_expect_tx(&chunk_bar[c % RING_DEPTH], 0u);
+                            // (the chunk barriers are used only when the scout warps run in lock
+                            //  step, i.e. with bulk copies: free-running warps could lap the 1-bit
+                            //  phase parity of a barrier that another warp arrives on)
+                            if (p.bulk && st == 0) mbar_arrive_expect_tx(&chunk_bar[c % RING_DEPTH], 0u);
 #pragma unroll
                             for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
                                 const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * c + r;
@@ -1217,7 +1220,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                     if (c >= RING_DEPTH - 1) {
                         cp_async_wait<RING_DEPTH - 1>();
                         const int cc = c - (RING_DEPTH - 1);
-                        mbar_wait_relaxed(&chunk_bar[cc % RING_DEPTH], (uint32_t)((cc >> 2) & 1), 32);
+                        if (p.bulk) mbar_wait_relaxed(&chunk_bar[cc % RING_DEPTH], (uint32_t)((cc >> 2) & 1), 32);
                         __syncwarp();
                         const float2* ring_c =
                             reinterpret_cast<const float2*>(ring + (cc % RING_DEPTH) * RING_CHUNK);
@@ -1261,9 +1264,11 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                             for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
                             if (lane == 0) ri[row] = make_float4(row_scale(m), 0.f, 0.f, ny);
                         }
-                        // every scout warp reads the same chunk: all of them are done with the
-                        // slot before scout thread 0 refills it
-                        named_bar_sync(2, INV_SCOUT_WARPS * 32);
+                        // a bulk-copied chunk is read by every scout warp: all of them are done with
+                        // the slot before scout thread 0 refills it (the cp.async path refills only
+                        // the warp's own rows: lock-stepping the warps there cost cfg5 510 -> 606 us)
+                        if (p.bulk) named_bar_sync(2, INV_SCOUT_WARPS * 32);
+                        else __syncwarp();
                     }
                 }
             }
