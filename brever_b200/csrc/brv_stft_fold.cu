@@ -1165,43 +1165,121 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
             } else {
                 // chunk = 8 frames; warp sw owns rows sw and sw + 4 of every chunk (bins contiguous),
                 // lanes along bins, so only warp-level synchronisation is needed
-                const int nch = TILE_M / 8;
-                constexpr int ROWS_PER_WARP = 8 / INV_SCOUT_WARPS;
-                // Chunk copies: when the rows are contiguous (sf == Hf + 1) the 8 rows of a chunk are
-                // one run of bytes and ONE bulk copy (TMA engine, no per-element instructions) brings
-                // them in, over the run's 16-byte rounded range (rows sit at 8-byte alignment: the
-                // data starts 0 or 8 bytes into the ring slot, rows at pitch Hf + 1).  Per-row bulk
-                // copies were tried first: 128 small requests per tile made the scouts the critical
-                // path (cfg5 510 -> 667 us).  A chunk whose rounded range would leave the tensor,
-                // and inputs that are not plain contiguous rows, use 8-byte cp.async as before.
-                // 16 chunks per tile = 4 uses of each ring slot: the mbarrier parity of chunk cc is
-                // (cc >> 2) & 1 in every tile.
-                const int f_in = Hf + 1;
-                auto chunk_range = [&](int c, uintptr_t& a0, uint32_t& sz, int& off) {
-                    const int nrows = min(8, rows_eff - 8 * c);
-                    const uintptr_t a = (uintptr_t)(xs + (t0 + 8 * c) * p.sf);
-                    a0 = a & ~(uintptr_t)15;
-                    off = (int)((a - a0) >> 3);
-                    sz = ((uint32_t)(a - a0) + (uint32_t)(nrows * f_in) * 8u + 15u) & ~15u;
-                    return p.bulk && nrows > 0 && a0 >= p.spec_lo && a0 + sz <= p.spec_hi;
-                };
-                for (int c = 0; c < nch + RING_DEPTH - 1; ++c) {
-                    if (c < nch) {
-                        float2* dst = reinterpret_cast<float2*>(ring + (c % RING_DEPTH) * RING_CHUNK);
-                        uintptr_t a0;
-                        uint32_t sz;
-                        int off;
-                        const bool bulk_chunk = chunk_range(c, a0, sz, off);
-                        if (bulk_chunk) {
-                            if (st == 0) {
-                                mbar_arrive_expect_tx(&chunk_bar[c % RING_DEPTH], sz);
-                                bulk_g2s(dst, reinterpret_cast<const void*>(a0), sz, &chunk_bar[c % RING_DEPTH]);
+                if (p.bulk) {
+                    const int nch = TILE_M / 8;
+                    constexpr int ROWS_PER_WARP = 8 / INV_SCOUT_WARPS;
+                    // Chunk copies: when the rows are contiguous (sf == Hf + 1) the 8 rows of a chunk are
+                    // one run of bytes and ONE bulk copy (TMA engine, no per-element instructions) brings
+                    // them in, over the run's 16-byte rounded range (rows sit at 8-byte alignment: the
+                    // data starts 0 or 8 bytes into the ring slot, rows at pitch Hf + 1).  Per-row bulk
+                    // copies were tried first: 128 small requests per tile made the scouts the critical
+                    // path (cfg5 510 -> 667 us).  A chunk whose rounded range would leave the tensor,
+                    // and inputs that are not plain contiguous rows, use 8-byte cp.async as before.
+                    // 16 chunks per tile = 4 uses of each ring slot: the mbarrier parity of chunk cc is
+                    // (cc >> 2) & 1 in every tile.
+                    const int f_in = Hf + 1;
+                    auto chunk_range = [&](int c, uintptr_t& a0, uint32_t& sz, int& off) {
+                        const int nrows = min(8, rows_eff - 8 * c);
+                        const uintptr_t a = (uintptr_t)(xs + (t0 + 8 * c) * p.sf);
+                        a0 = a & ~(uintptr_t)15;
+                        off = (int)((a - a0) >> 3);
+                        sz = ((uint32_t)(a - a0) + (uint32_t)(nrows * f_in) * 8u + 15u) & ~15u;
+                        return p.bulk && nrows > 0 && a0 >= p.spec_lo && a0 + sz <= p.spec_hi;
+                    };
+                    for (int c = 0; c < nch + RING_DEPTH - 1; ++c) {
+                        if (c < nch) {
+                            float2* dst = reinterpret_cast<float2*>(ring + (c % RING_DEPTH) * RING_CHUNK);
+                            uintptr_t a0;
+                            uint32_t sz;
+                            int off;
+                            const bool bulk_chunk = chunk_range(c, a0, sz, off);
+                            if (bulk_chunk) {
+                                if (st == 0) {
+                                    mbar_arrive_expect_tx(&chunk_bar[c % RING_DEPTH], sz);
+                                    bulk_g2s(dst, reinterpret_cast<const void*>(a0), sz, &chunk_bar[c % RING_DEPTH]);
+                                }
+                            } else {
+                                // (the chunk barriers are used only when the scout warps run in lock
+                                //  step, i.e. with bulk copies: free-running warps could lap the 1-bit
+                                //  phase parity of a barrier that another warp arrives on)
+                                if (p.bulk && st == 0) mbar_arrive_expect_tx(&chunk_bar[c % RING_DEPTH], 0u);
+#pragma unroll
+                                for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+                                    const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * c + r;
+                                    if (row < rows_eff) {
+                                        const float2* xr = xs + (t0 + row) * p.sf;
+#pragma unroll
+                                        for (int j = 0; j < 9; ++j) {
+                                            const int b = j * 32 + lane;
+                                            if (b <= Hf) cp_async8(dst + r * RING_ROW + b, xr + b);   // sb == 1
+                                        }
+                                    }
+                                }
                             }
-                        } else {
-                            // (the chunk barriers are used only when the scout warps run in lock
-                            //  step, i.e. with bulk copies: free-running warps could lap the 1-bit
-                            //  phase parity of a barrier that another warp arrives on)
-                            if (p.bulk && st == 0) mbar_arrive_expect_tx(&chunk_bar[c % RING_DEPTH], 0u);
+                        }
+                        cp_async_commit();
+                        if (c >= RING_DEPTH - 1) {
+                            cp_async_wait<RING_DEPTH - 1>();
+                            const int cc = c - (RING_DEPTH - 1);
+                            if (p.bulk) mbar_wait_relaxed(&chunk_bar[cc % RING_DEPTH], (uint32_t)((cc >> 2) & 1), 32);
+                            __syncwarp();
+                            const float2* ring_c =
+                                reinterpret_cast<const float2*>(ring + (cc % RING_DEPTH) * RING_CHUNK);
+                            uintptr_t a0c;
+                            uint32_t szc;
+                            int offc;
+                            const bool bulk_chunk = chunk_range(cc, a0c, szc, offc);
+                            const int pitch_c = bulk_chunk ? f_in : RING_ROW;
+#pragma unroll
+                            for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+                                const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * cc + r;
+                                float m = 0.f, ny = 0.f;
+                                if (row < rows_eff) {
+                                    // data starts 0 or 1 elements into a bulk-copied slot
+                                    const float2* src = ring_c + (bulk_chunk ? offc : 0) + r * pitch_c;
+                                    float2 v[8];                 // bins lane + 32 j < Hf (Hf <= 256)
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        v[j] = j * 32 < Hf ? src[j * 32 + lane] : make_float2(0.f, 0.f);
+                                    if (lane == 0) v[0].y = 0.f; // Im X[0] never reaches the output
+                                    if (DECOMP) {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j)
+                                            m = fmaxf(m, abs2_finite(prep_bin<true>(v[j], p.pre_scale, p.pre_expo)));
+                                    } else {
+                                        uint32_t mb = 0u;
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) mb = absbits_max(mb, v[j]);
+                                        if (mb >= 0x7f800000u) {  // inf / nan: exclude them
+                                            float mf = 0.f;
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) mf = fmaxf(mf, abs2_finite(v[j]));
+                                            mb = __float_as_uint(mf);
+                                        }
+                                        m = __uint_as_float(mb) * fabsf(p.pre_scale);
+                                    }
+                                    if (lane == 0 && !ODD)
+                                        ny = prep_bin<DECOMP>(src[Hf], p.pre_scale, p.pre_expo).x * p.edge_gain;
+                                }
+#pragma unroll
+                                for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                                if (lane == 0) ri[row] = make_float4(row_scale(m), 0.f, 0.f, ny);
+                            }
+                            // a bulk-copied chunk is read by every scout warp: all of them are done with
+                            // the slot before scout thread 0 refills it (the cp.async path refills only
+                            // the warp's own rows: lock-stepping the warps there cost cfg5 510 -> 606 us)
+                            if (p.bulk) named_bar_sync(2, INV_SCOUT_WARPS * 32);
+                            else __syncwarp();
+                        }
+                    }
+                } else {
+                    // (verbatim the pre-bulk loop: compile-time ring offsets and free-running warps;
+                    //  sharing one loop with runtime pitches cost cfg5 510 -> 600 us)
+                    const int nch = TILE_M / 8;
+                    constexpr int ROWS_PER_WARP = 8 / INV_SCOUT_WARPS;
+                    for (int c = 0; c < nch + RING_DEPTH - 1; ++c) {
+                        if (c < nch) {
+                            float2* dst = reinterpret_cast<float2*>(ring + (c % RING_DEPTH) * RING_CHUNK);
 #pragma unroll
                             for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
                                 const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * c + r;
@@ -1215,60 +1293,50 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                                 }
                             }
                         }
-                    }
-                    cp_async_commit();
-                    if (c >= RING_DEPTH - 1) {
-                        cp_async_wait<RING_DEPTH - 1>();
-                        const int cc = c - (RING_DEPTH - 1);
-                        if (p.bulk) mbar_wait_relaxed(&chunk_bar[cc % RING_DEPTH], (uint32_t)((cc >> 2) & 1), 32);
-                        __syncwarp();
-                        const float2* ring_c =
-                            reinterpret_cast<const float2*>(ring + (cc % RING_DEPTH) * RING_CHUNK);
-                        uintptr_t a0c;
-                        uint32_t szc;
-                        int offc;
-                        const bool bulk_chunk = chunk_range(cc, a0c, szc, offc);
-                        const int pitch_c = bulk_chunk ? f_in : RING_ROW;
+                        cp_async_commit();
+                        if (c >= RING_DEPTH - 1) {
+                            cp_async_wait<RING_DEPTH - 1>();
+                            __syncwarp();
+                            const int cc = c - (RING_DEPTH - 1);
+                            const float2* src =
+                                reinterpret_cast<const float2*>(ring + (cc % RING_DEPTH) * RING_CHUNK);
 #pragma unroll
-                        for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-                            const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * cc + r;
-                            float m = 0.f, ny = 0.f;
-                            if (row < rows_eff) {
-                                // data starts 0 or 1 elements into a bulk-copied slot
-                                const float2* src = ring_c + (bulk_chunk ? offc : 0) + r * pitch_c;
-                                float2 v[8];                 // bins lane + 32 j < Hf (Hf <= 256)
-#pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    v[j] = j * 32 < Hf ? src[j * 32 + lane] : make_float2(0.f, 0.f);
-                                if (lane == 0) v[0].y = 0.f; // Im X[0] never reaches the output
-                                if (DECOMP) {
+                            for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+                                const int r = sw + INV_SCOUT_WARPS * rr, row = 8 * cc + r;
+                                float m = 0.f, ny = 0.f;
+                                if (row < rows_eff) {
+                                    float2 v[8];                 // bins lane + 32 j < Hf (Hf <= 256)
 #pragma unroll
                                     for (int j = 0; j < 8; ++j)
-                                        m = fmaxf(m, abs2_finite(prep_bin<true>(v[j], p.pre_scale, p.pre_expo)));
-                                } else {
-                                    uint32_t mb = 0u;
+                                        v[j] = j * 32 < Hf ? src[r * RING_ROW + j * 32 + lane]
+                                                           : make_float2(0.f, 0.f);
+                                    if (lane == 0) v[0].y = 0.f; // Im X[0] never reaches the output
+                                    if (DECOMP) {
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) mb = absbits_max(mb, v[j]);
-                                    if (mb >= 0x7f800000u) {  // inf / nan: exclude them
-                                        float mf = 0.f;
+                                        for (int j = 0; j < 8; ++j)
+                                            m = fmaxf(m, abs2_finite(prep_bin<true>(v[j], p.pre_scale, p.pre_expo)));
+                                    } else {
+                                        uint32_t mb = 0u;
 #pragma unroll
-                                        for (int j = 0; j < 8; ++j) mf = fmaxf(mf, abs2_finite(v[j]));
-                                        mb = __float_as_uint(mf);
+                                        for (int j = 0; j < 8; ++j) mb = absbits_max(mb, v[j]);
+                                        if (mb >= 0x7f800000u) {  // inf / nan: exclude them
+                                            float mf = 0.f;
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) mf = fmaxf(mf, abs2_finite(v[j]));
+                                            mb = __float_as_uint(mf);
+                                        }
+                                        m = __uint_as_float(mb) * fabsf(p.pre_scale);
                                     }
-                                    m = __uint_as_float(mb) * fabsf(p.pre_scale);
+                                    if (lane == 0 && !ODD)
+                                        ny = prep_bin<DECOMP>(src[r * RING_ROW + Hf], p.pre_scale, p.pre_expo).x *
+                                             p.edge_gain;
                                 }
-                                if (lane == 0 && !ODD)
-                                    ny = prep_bin<DECOMP>(src[Hf], p.pre_scale, p.pre_expo).x * p.edge_gain;
-                            }
 #pragma unroll
-                            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                            if (lane == 0) ri[row] = make_float4(row_scale(m), 0.f, 0.f, ny);
+                                for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                                if (lane == 0) ri[row] = make_float4(row_scale(m), 0.f, 0.f, ny);
+                            }
+                            __syncwarp();
                         }
-                        // a bulk-copied chunk is read by every scout warp: all of them are done with
-                        // the slot before scout thread 0 refills it (the cp.async path refills only
-                        // the warp's own rows: lock-stepping the warps there cost cfg5 510 -> 606 us)
-                        if (p.bulk) named_bar_sync(2, INV_SCOUT_WARPS * 32);
-                        else __syncwarp();
                     }
                 }
             }
