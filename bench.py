@@ -2,7 +2,7 @@
 """Benchmark of the time-frequency front-end hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload cfg2|cfg1|cfg4|cfg5]
+                    [--workload cfg2|cfg1|cfg3|cfg4|cfg5]
 
 A "step" is one pass of the hot path over one batch of synthetic mixtures.  At
 N=1 the default workload is BASELINE.json configs[1]: the DCCRN-style complex
