@@ -41,6 +41,7 @@ PROTOTYPES = {
     'brv_istft_forward_grad': (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _sz,
                                       _ptr]),
     'brv_stft_workspace_bytes': (_sz, [_ptr, _i64, _i64]),
+    'brv_stft_workspace_bytes_op': (_sz, [_ptr, _i64, _i64, _int]),
     'brv_convstft_geometry': (_int, [_ptr, _i64, _ptr]),
     'brv_convstft_forward': (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _ptr, _ptr]),
     'brv_convstft_backward': (_int, [_ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _int,

@@ -76,6 +76,23 @@ extern "C" int brv_set_force_generic(int on) {
     return prev;
 }
 
+extern "C" size_t brv_stft_workspace_bytes_op(const brv_stft_plan* p, int64_t n_signals,
+                                              int64_t n_frames, int op) {
+    if (!p || n_signals <= 0 || n_frames <= 0) return 0;
+    // mirrors the dispatch conditions of the three entry points below
+    const bool fold_ok = !force_generic() && tc_variant() != 1;
+    bool fused = false;
+    if (op == 0)
+        fused = fold_ok && brv_fold_inverse_supported(p);
+    else if (op == 1)
+        fused = fold_ok && brv_fold_inverse_supported(p) && brv_fold_grad_supported(p) &&
+                p->n_bins == p->n_bins_inv;
+    else if (op == 2)
+        fused = fold_ok && brv_fold_grad_supported(p) && p->n_bins == p->n_bins_inv &&
+                (int64_t)p->hop * (n_frames - 1) + p->n_fft - 2 * (int64_t)(p->n_fft / 2) > 0;
+    return fused ? 256 : brv_stft_workspace_bytes(p, n_signals, n_frames);
+}
+
 extern "C" int brv_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_signals,
                                 int64_t samples, int64_t x_stride, void* out, void* stream) {
     BRV_REQUIRE(p && out, "null pointer argument");

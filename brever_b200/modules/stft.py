@@ -174,7 +174,7 @@ class STFT:
             lib = _lib.lib()
             with _lib.on_device(grad.device):
                 plan = self._plan(grad.device)
-                nbytes = lib.brv_stft_workspace_bytes(plan, n_sig, frames)
+                nbytes = lib.brv_stft_workspace_bytes_op(plan, n_sig, frames, 1)
                 ws = _lib.workspace(nbytes, grad.device)
                 _lib.check(lib.brv_stft_forward_grad(
                     plan, _lib.ptr(grad), grad.stride(0), grad.stride(1),
@@ -193,7 +193,7 @@ class STFT:
         lib = _lib.lib()
         with _lib.on_device(spec3d.device):
             plan = self._plan(spec3d.device)
-            nbytes = lib.brv_stft_workspace_bytes(plan, n_sig, frames)
+            nbytes = lib.brv_stft_workspace_bytes_op(plan, n_sig, frames, 0)
             ws = _lib.workspace(nbytes, spec3d.device)
             _lib.check(lib.brv_istft_forward(
                 plan, _lib.ptr(spec3d), spec3d.stride(0), spec3d.stride(1),
@@ -210,7 +210,7 @@ class STFT:
             lib = _lib.lib()
             with _lib.on_device(grad.device):
                 plan = self._plan(grad.device)
-                nbytes = lib.brv_stft_workspace_bytes(plan, n_sig, frames)
+                nbytes = lib.brv_stft_workspace_bytes_op(plan, n_sig, frames, 2)
                 ws = _lib.workspace(nbytes, grad.device)
                 _lib.check(lib.brv_istft_forward_grad(
                     plan, _lib.ptr(grad), n_sig, frames, _lib.ptr(gX),

@@ -125,6 +125,13 @@ int brv_istft_forward_grad(const brv_stft_plan* plan, const float* gy,
                            void* stream);
 size_t brv_stft_workspace_bytes(const brv_stft_plan* plan, int64_t n_signals,
                                 int64_t n_frames);
+/* The same bound for one operation under the current dispatch settings: a few
+ * bytes when the call will run on a fused kernel that needs no frames workspace
+ * (op: 0 = brv_istft_forward, 1 = brv_stft_forward_grad, 2 = brv_istft_forward_grad),
+ * else brv_stft_workspace_bytes.  Lets the caller skip the (n_signals, T, n_fft)
+ * float allocation — 525 MB for 1024 x 2 x 4 s at 256 / 128 — on the common path. */
+size_t brv_stft_workspace_bytes_op(const brv_stft_plan* plan, int64_t n_signals,
+                                   int64_t n_frames, int op);
 
 /* ---- ConvSTFT (stft.py:201-319) ---------------------------------------------
  * The convolutional STFT pair: analysis = F.conv1d with the windowed one-sided
