@@ -145,6 +145,29 @@ def test_feature_extractor_surface():
         fe.calc_feature(torch.zeros(257, 4, dtype=torch.complex64), 'logfbe')
 
 
+def test_conv_stft_host_surface():
+    """ConvSTFT (stft.py:201-319): constructor state, padding arithmetic and the kernel bank are
+    host-side and must match the reference / the oracle without a GPU."""
+    g = golden()
+    cs = brv.ConvSTFT(frame_length=512, hop_length=128)
+    assert cs.frame_length == 512 and cs.hop_length == 128 and cs.normalized
+    assert cs._normalization_factor == 0.5 * 512 / 128 ** 0.5
+    assert torch.allclose(cs.window.pow(2), torch.from_numpy(O.get_window('hann', 512)))
+    bank, factor = O._conv_filters(512, 128, 'hann', True)
+    ref = np.concatenate([bank.real, bank.imag])[:, None, :]
+    assert cs.filters.shape == (514, 1, 512)
+    assert np.abs(cs.filters.numpy() - ref).max() < 1e-7 and factor == cs._normalization_factor
+    for i in range(5):
+        S, L, H = (int(v) for v in g[f'convshape{i}_meta'])
+        c = brv.ConvSTFT(frame_length=L, hop_length=H)
+        assert c.n_frames(S) == g[f'convshape{i}_spec'].shape[-1]
+        assert c.frame_count(S) == O.frame_count(S, L, H)
+        assert c.pad(torch.zeros(S)).shape[-1] == (c.n_frames(S) - 1) * H + L + ((S + O.right_padding(S, L, H) + 2 * (L - H) - L) % H)
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        cs(torch.zeros(4096))
+    pickle.loads(pickle.dumps(cs))
+
+
 def test_registry_contract():
     assert set(brv.CriterionRegistry.keys()) >= {'sisnr', 'snr'}
     assert brv.init_criterion('snr') is brv.snr
