@@ -40,15 +40,16 @@ int brv_fold_conv_backward(const brv_stft_plan* p, const float2* X, int64_t ss, 
 
 static int g_force_generic = -1;
 extern int g_brv_fold_variant;
-// 0: folded kernels where supported (forward kernel picked by tile count), 1: dense contraction
-// only, 2 / 3: folded kernels with the forward forced to one tile per CTA / persistent two-pass
+// 0: folded kernels where supported (transposed strip kernels first), 1: dense contraction only,
+// 4: the one-tile-per-TMEM folded kernels (forward picked by tile count), 2 / 3: those with the
+// forward forced to one tile per CTA / persistent two-pass
 static int g_tc_variant = -1;
 
 static int tc_variant() {
     if (g_tc_variant < 0) {
         const char* e = getenv("BRV_TC_VARIANT");
         const int v = e ? atoi(e) : 0;
-        g_tc_variant = (v >= 1 && v <= 3) ? v : 0;
+        g_tc_variant = (v >= 1 && v <= 6) ? v : 0;
         g_brv_fold_variant = g_tc_variant >= 2 ? g_tc_variant : 0;
     }
     return g_tc_variant;
@@ -56,7 +57,7 @@ static int tc_variant() {
 
 extern "C" int brv_set_tc_variant(int variant) {
     int prev = tc_variant();
-    g_tc_variant = (variant >= 1 && variant <= 3) ? variant : 0;
+    g_tc_variant = (variant >= 1 && variant <= 6) ? variant : 0;
     g_brv_fold_variant = g_tc_variant >= 2 ? g_tc_variant : 0;
     return prev;
 }

@@ -116,7 +116,29 @@ struct FoldFwdParams {
     int odd;
     // the staged span starts `shift` samples early so that it is 16-byte aligned in HBM
     int shift;
+    // transposed strip kernel (brv_fold_t.cuh): total_tiles counts frames; grad_env = multiply the
+    // input by 1 / overlap-added w^2 (periodic table + edges summed from the squared window)
+    // instead of by an in_mul table
+    int grad_env;
+    const float* env_per;
+    const float* wsq;
 };
+
+// 1 / (overlap-added squared window) at offset `off` of hop block `u` (torch.istft divides by
+// this envelope; NOLA was checked by the caller).  Interior blocks see all ceil(N / H) frames:
+// periodic table; edge blocks are summed from the squared window.  No per-frame-count table.
+__device__ __forceinline__ float ola_inv_envelope(const float* env_per, const float* wsq, int N,
+                                                  int H, int64_t n_frames, int64_t u, int off) {
+    const int rmax = (N + H - 1) / H;
+    if (u >= rmax - 1 && u <= n_frames - 1) return __ldg(env_per + off);
+    float acc = 0.f;
+    for (int j = 0; j < rmax; ++j) {
+        const int64_t t = u - j;
+        const int pos = j * H + off;
+        if (t >= 0 && t <= n_frames - 1 && pos < N) acc += __ldg(wsq + pos);
+    }
+    return 1.f / acc;
+}
 
 __device__ __forceinline__ float4 mul4(float4 a, float4 b) {
     return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
@@ -914,8 +936,9 @@ struct FoldInvParams {
     float pre_scale, pre_expo;   // 1 / scale_factor, 1 / c - 1
     float* y;                    // (sig, out_len)
     int64_t out_len;
-    const float* inv_env;        // out_len: 1 / overlap-added w^2 (trimmed grid)
-    const float* env_per;        // hop: the same for interior hop blocks (periodic)
+    const float* env_per;        // hop: 1 / overlap-added w^2 of interior hop blocks (periodic)
+    const float* wsq;            // n_fft: squared window (edge hop blocks are summed on the fly)
+    int no_env;                  // gradient / ConvSTFT use: no division by the envelope
     const float4* wtab;          // Q entries: (w[n], w[N/2-n], w[N/2+n], w[N-n]) * norm / N
     int64_t n_frames;
     int n_fft, hop, q;
@@ -926,7 +949,7 @@ struct FoldInvParams {
     int tmem_cols;
     float wq, w3q;               // w[Q] * norm / N, w[3Q] * norm / N
     float basis_scale_inv;
-    // gradient of the forward transform (brv_fold_stft_grad): no envelope (inv_env == nullptr),
+    // gradient of the forward transform (brv_fold_stft_grad): no envelope (no_env),
     // all bins weigh 1: the window table carries 1/2 and the DC / Nyquist inputs edge_gain = 2
     float edge_gain;
     float dc_gain;               // DC input (equal to edge_gain except for ConvSTFT: sqrt(2))
@@ -1356,7 +1379,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
         float env_reg[8];                          // 1 / envelope of interior hop blocks
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            env_reg[j] = !p.inv_env ? 1.f : (lane + 32 * j < H ? __ldg(p.env_per + lane + 32 * j) : 0.f);
+            env_reg[j] = p.no_env ? 1.f : (lane + 32 * j < H ? __ldg(p.env_per + lane + 32 * j) : 0.f);
 
         int g = 0, n = 0;
         for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
@@ -1735,7 +1758,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                     const int qq = r >> 5, lr = r & 31;
                     const float* sp = (qq > 0 && lr < p.halo) ? spill + (qq * 3 + lr) * H : nullptr;
                     const int64_t i0 = u * H - p.origin;
-                    const bool use_reg = !p.inv_env || (u >= R - 1 && u <= p.n_frames - 1);
+                    const bool use_reg = p.no_env || (u >= R - 1 && u <= p.n_frames - 1);
                     // offsets [lo, hi) of this hop block that exist in the output, as 32-bit
                     // values computed once per row (the warps of this phase run dependent
                     // chains at ~1 instruction per 5 cycles: per-element 64-bit range checks
@@ -1756,7 +1779,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                             if (off >= lo && off < hi) {
                                 float v = src[off];
                                 if (sp) v += sp[off];
-                                yrow[off] = v * (use_reg ? env_reg[j] : __ldg(p.inv_env + i0 + off));
+                                yrow[off] = v * (use_reg ? env_reg[j] : ola_inv_envelope(p.env_per, p.wsq, N, H, p.n_frames, u, off));
                             }
                         }
                     }
@@ -1779,6 +1802,8 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
         tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
+
+#include "brv_fold_t.cuh"
 
 struct FoldBasis {
     __half* data = nullptr;      // [plane 2][sub 4][m Q][n Q]
@@ -1877,7 +1902,10 @@ void free_fold(FoldPlan* fp) {
 
 }  // namespace
 
-int g_brv_fold_variant = 0;   // 0: by tile count, 2: one tile per CTA, 3: persistent two-pass (brv_set_tc_variant)
+// 0: transposed strip kernels (brv_fold_t.cuh) where they apply; 4: the one-tile-per-TMEM kernels,
+// forward picked by tile count; 2 / 3: those with the forward forced to one tile per CTA /
+// persistent two-pass; 5 / 6: transposed forward only / transposed inverse only (brv_set_tc_variant)
+int g_brv_fold_variant = 0;
 
 bool brv_fold_supported(const brv_stft_plan* p) { return p->fold != nullptr; }
 
@@ -1954,6 +1982,12 @@ int brv_fold_plan_init(brv_stft_plan* p) {
                               F2_SMEM_BYTES) != cudaSuccess))
         rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(stft_fold2_kernel)");
     if (rc == BRV_OK &&
+        (cudaFuncSetAttribute(stft_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              FT_SMEM_BYTES) != cudaSuccess ||
+         cudaFuncSetAttribute(stft_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              FT_SMEM_BYTES) != cudaSuccess))
+        rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(stft_t_kernel)");
+    if (rc == BRV_OK &&
         cudaDeviceGetAttribute(&fp->sm_count, cudaDevAttrMultiProcessorCount, p->device) !=
             cudaSuccess)
         rc = brv_fail_cuda(cudaGetLastError(), "cudaDeviceGetAttribute(SM count)");
@@ -2002,14 +2036,15 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             if ((size_t)TILE_M * (H + 1) * sizeof(float) <= (size_t)INV_REGION && H <= 256)
                 fp->hq = H / Q;
     }
-    if (rc == BRV_OK && fp->hq) {
-        // interior hop blocks see all R = N / hop frames: the envelope is periodic
+    if (rc == BRV_OK) {
+        // interior hop blocks see all ceil(N / hop) frames: the envelope is periodic (any hop:
+        // the iSTFT gradient runs on the forward kernel, which has no hop restriction)
         const int H = p->hop;
         std::vector<float> per(H);
         for (int off = 0; off < H; ++off) {
             double e = 0;
             for (int pos = off; pos < N; pos += H) e += p->window[pos] * p->window[pos];
-            per[off] = (float)(1.0 / e);
+            per[off] = e > 0 ? (float)(1.0 / e) : 0.f;
         }
         if (cudaMalloc((void**)&fp->env_per, H * sizeof(float)) != cudaSuccess ||
             cudaMemcpy(fp->env_per, per.data(), H * sizeof(float), cudaMemcpyHostToDevice) !=
@@ -2033,6 +2068,15 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      INV_SMEM_BYTES) != cudaSuccess)
                 rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_fold_kernel)");
+        const void* tkernels[8] = {
+            (const void*)istft_t_kernel<1, false, false>, (const void*)istft_t_kernel<1, true, false>,
+            (const void*)istft_t_kernel<2, false, false>, (const void*)istft_t_kernel<2, true, false>,
+            (const void*)istft_t_kernel<1, false, true>, (const void*)istft_t_kernel<1, true, true>,
+            (const void*)istft_t_kernel<2, false, true>, (const void*)istft_t_kernel<2, true, true>};
+        for (const void* k : tkernels)
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     IT_SMEM_BYTES) != cudaSuccess)
+                rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_t_kernel)");
     }
     if (rc != BRV_OK) {
         free_fold(fp);
@@ -2059,6 +2103,26 @@ static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool c
     if (prm.origin < 0) prm.origin = p->n_fft / 2;
     // 16-byte aligned span when the hop allows it (n_fft / 2 = 255 would otherwise force scalar loads)
     prm.shift = p->hop % 4 == 0 ? (4 - (prm.origin & 3)) & 3 : 0;
+    prm.tmem_cols = fp->tmem_cols;
+    prm.basis_scale_inv = fp->fwd.scale_inv;
+    if (g_brv_fold_variant == 0 || g_brv_fold_variant == 5) {
+        // transposed strip kernel: every SM walks the same number of frames in <= 64-frame tiles
+        const int nf = ft_tile_frames(p->n_fft, p->hop, prm.shift);
+        if (nf >= 16) {
+            prm.rows = nf;
+            prm.tiles_per_signal = 0;
+            prm.total_tiles = n_sig * n_frames;              // columns (frames), not tiles
+            BRV_REQUIRE(prm.total_tiles < (1LL << 40), "too many frames (%lld)", (long long)prm.total_tiles);
+            const int64_t want = brv_ceil_div(prm.total_tiles, 16);
+            const unsigned ctas = (unsigned)(want < fp->sm_count ? want : fp->sm_count);
+            if (compress)
+                stft_t_kernel<true><<<ctas, FT_THREADS, FT_SMEM_BYTES, st>>>(fp->fwd.map, prm);
+            else
+                stft_t_kernel<false><<<ctas, FT_THREADS, FT_SMEM_BYTES, st>>>(fp->fwd.map, prm);
+            BRV_LAUNCH_CHECK("stft_t_kernel");
+            return BRV_OK;
+        }
+    }
     int rows = (SPAN_MAX - p->n_fft - prm.shift) / p->hop + 1;
     if (rows > TILE_M) rows = TILE_M;
     if (rows > n_frames) rows = (int)n_frames;
@@ -2142,10 +2206,9 @@ static int fold_inv_envelope(const brv_stft_plan* p, int64_t n_frames, int64_t o
             }
             host[(size_t)i] = (float)(1.0 / e);
         }
-        if (fp->inv_env.size() >= 64) {           // bounded cache
-            for (auto& kv : fp->inv_env) cudaFree(kv.second);
-            fp->inv_env.clear();
-        }
+        // (only the A/B variants 2-4 of the iSTFT gradient still use this table; entries are never
+        //  freed while the plan lives: a captured CUDA graph may hold the pointer)
+        BRV_REQUIRE(fp->inv_env.size() < 1024, "too many distinct frame counts for the tabulated envelope");
         float* dev = nullptr;
         BRV_CUDA(cudaMalloc((void**)&dev, (size_t)out_len * sizeof(float)));
         cudaError_t e = cudaMemcpy(dev, host.data(), (size_t)out_len * sizeof(float),
@@ -2178,9 +2241,31 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     prm.tmem_cols = fp->tmem_cols;
     prm.basis_scale_inv = fp->inv.scale_inv;
     prm.env_per = fp->env_per;
+    prm.wsq = p->window_sq;
     prm.total_tiles = n_sig * prm.tiles_per_signal;
-    const unsigned grid = (unsigned)(prm.total_tiles < fp->sm_count ? prm.total_tiles : fp->sm_count);
     const bool frames_fast = prm.sb != 1;
+    if ((g_brv_fold_variant == 0 || g_brv_fold_variant == 6) && !fp->odd && (fp->hq == 1 || fp->hq == 2)) {
+        // transposed strip kernel: every SM walks the same number of hop blocks in <= 64-column tiles
+        prm.total_tiles = n_sig * (int64_t)prm.n_blocks;     // columns (hop blocks), not tiles
+        const int64_t want = brv_ceil_div(prm.total_tiles, 16);
+        const unsigned ctas = (unsigned)(want < fp->sm_count ? want : fp->sm_count);
+#define BRV_LAUNCH_INV_T(HQ_, FF_)                                                                \
+    do {                                                                                          \
+        if (decomp)                                                                               \
+            istft_t_kernel<HQ_, FF_, true><<<ctas, IT_THREADS, IT_SMEM_BYTES, st>>>(fp->inv.map, prm); \
+        else                                                                                      \
+            istft_t_kernel<HQ_, FF_, false><<<ctas, IT_THREADS, IT_SMEM_BYTES, st>>>(fp->inv.map, prm); \
+    } while (0)
+        if (fp->hq == 1) {
+            if (frames_fast) BRV_LAUNCH_INV_T(1, true); else BRV_LAUNCH_INV_T(1, false);
+        } else {
+            if (frames_fast) BRV_LAUNCH_INV_T(2, true); else BRV_LAUNCH_INV_T(2, false);
+        }
+#undef BRV_LAUNCH_INV_T
+        BRV_LAUNCH_CHECK("istft_t_kernel");
+        return BRV_OK;
+    }
+    const unsigned grid = (unsigned)(prm.total_tiles < fp->sm_count ? prm.total_tiles : fp->sm_count);
     {   // the bytes the (signal, frame, bin) view itself covers: bulk row copies stay inside them
         const int64_t f_in = p->n_fft / 2 + 1;
         // (16 KB chunks only: with the 8 KB chunks of n_fft = 256 three copies in flight do not
@@ -2225,8 +2310,7 @@ int brv_fold_istft(const brv_stft_plan* p, const float2* X, int64_t ss, int64_t 
                    int64_t n_sig, int64_t n_frames, int64_t out_len, float* y, cudaStream_t st) {
     const FoldPlan* fp = (const FoldPlan*)p->fold;
     FoldInvParams prm = {};
-    int rc = fold_inv_envelope(p, n_frames, out_len, &prm.inv_env);
-    if (rc != BRV_OK) return rc;
+    prm.no_env = 0;
     prm.spec = X;
     prm.ss = ss;
     prm.sb = sb;
@@ -2250,7 +2334,7 @@ int brv_fold_stft_grad(const brv_stft_plan* p, const float2* gX, int64_t ss, int
                        cudaStream_t st) {
     const FoldPlan* fp = (const FoldPlan*)p->fold;
     FoldInvParams prm = {};
-    prm.inv_env = nullptr;
+    prm.no_env = 1;
     prm.spec = gX;
     prm.ss = ss;
     prm.sb = sb;
@@ -2272,8 +2356,14 @@ int brv_fold_istft_grad(const brv_stft_plan* p, const float* gy, int64_t n_sig, 
                         int64_t out_len, float2* gX, cudaStream_t st) {
     const FoldPlan* fp = (const FoldPlan*)p->fold;
     FoldFwdParams prm = {};
-    int rc = fold_inv_envelope(p, n_frames, out_len, &prm.in_mul);
-    if (rc != BRV_OK) return rc;
+    if (g_brv_fold_variant == 0 || g_brv_fold_variant == 5) {
+        prm.grad_env = 1;                          // the transposed kernel sums the envelope itself
+        prm.env_per = fp->env_per;
+        prm.wsq = p->window_sq;
+    } else {
+        int rc = fold_inv_envelope(p, n_frames, out_len, &prm.in_mul);
+        if (rc != BRV_OK) return rc;
+    }
     prm.x = gy;
     prm.x_stride = out_len;
     prm.samples = out_len;
@@ -2333,7 +2423,7 @@ int brv_fold_conv_backward(const brv_stft_plan* p, const float2* X, int64_t ss, 
                            double gain, float* y, cudaStream_t st) {
     const FoldPlan* fp = (const FoldPlan*)p->fold;
     FoldInvParams prm = {};
-    prm.inv_env = nullptr;
+    prm.no_env = 1;
     prm.spec = X;
     prm.ss = ss;
     prm.sb = sb;

@@ -90,21 +90,28 @@ def check_inverse():
 
 
 def bench():
+    # variant 0: transposed strip kernels; 4: one-tile-per-TMEM kernels; 1: dense contraction
+    variants = [int(v) for v in os.environ.get('FOLD_CHECK_VARIANTS', '0,4').split(',')]
     for name, shape, kw in [('cfg2', (64, 64000), dict(frame_length=512, hop_length=128)),
                             ('cfg1', (32, 64000), dict(frame_length=512, hop_length=256)),
-                            ('cfg5', (256, 64000), dict(frame_length=256, hop_length=128,
-                                                        normalized=False))]:
+                            ('cfg4', (128, 128000), dict(frame_length=510, hop_length=128, normalized=False,
+                                                         compression_factor=0.5, scale_factor=0.15)),
+                            ('cfg5', (2048, 64000), dict(frame_length=256, hop_length=128,
+                                                         normalized=False))]:
         mix, _ = synthetic_mixture(shape, 1000)
         x = mix.to(DEV)
         stft = brv.STFT(**kw)
         spec = stft(x)
-        for variant in (0, 1):
+        spec_bm = spec.contiguous()          # bin-major copy (what a network hands to the iSTFT)
+        for variant in variants:
             lib.brv_set_tc_variant(variant)
             t_f = timed(lambda: stft(x))
             t_i = timed(lambda: stft.backward(spec))
-            print(f'[time] {name} variant={variant}: stft {t_f:.1f} us, istft {t_i:.1f} us',
-                  flush=True)
+            t_b = timed(lambda: stft.backward(spec_bm))
+            print(f'[time] {name} variant={variant}: stft {t_f:.1f} us, istft {t_i:.1f} us, '
+                  f'istft(bin-major) {t_b:.1f} us', flush=True)
         lib.brv_set_tc_variant(0)
+        del x, spec, spec_bm
 
 
 if __name__ == '__main__':
