@@ -51,13 +51,23 @@ def _rows(t):
     return t3
 
 
-def _workspace(nbytes, device):
-    """Ticket buffer the kernel leaves zeroed; cached per (device, stream)."""
+def _workspace(nbytes, n_tickets, device):
+    """Reduction workspace, cached per (device, stream): `n_tickets` uint32 counters first (the
+    kernels need them zero on entry and leave them zero), partial sums after.  The partial sums
+    stay dirty, so when a call puts its counters over bytes that no earlier call used as
+    counters, that range is zeroed first (stream-ordered) -- a small-batch / long-rows call
+    followed by a many-rows call would otherwise read stale partial sums as counters."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
+    ticket_bytes = (4 * int(n_tickets) + 255) & ~255
+    entry = _workspaces.get(key)
+    if entry is None or entry[0].numel() < nbytes:
         ws = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+        entry = [ws, ws.numel()]
+        _workspaces[key] = entry
+    ws, clean = entry                      # bytes [0, clean) are zero at rest
+    if ticket_bytes > clean:
+        ws[clean:ticket_bytes].zero_()
+    entry[1] = ticket_bytes                # everything after this call's counters is dirty now
     return ws
 
 
@@ -70,7 +80,7 @@ def _moments(x3, y3, lengths, pairwise, sign=1.0):
     if pairs:
         lib = _lib.lib()
         nbytes = lib.brv_snr_workspace_bytes(pairs, length)
-        ws = _workspace(nbytes, x3.device)
+        ws = _workspace(nbytes, pairs, x3.device)
         with _lib.on_device(x3.device):
             _lib.check(lib.brv_snr_forward(
                 _lib.ptr(x3), _lib.ptr(y3), _lib.ptr(lengths), batch, rows,
@@ -255,7 +265,7 @@ class _L1RowsFunction(torch.autograd.Function):
         if out.numel():
             lib = _lib.lib()
             nbytes = lib.brv_l1_workspace_bytes(batch * rows, length)
-            ws = _workspace(nbytes, x3.device)
+            ws = _workspace(nbytes, batch * rows, x3.device)
             with _lib.on_device(x3.device):
                 _lib.check(lib.brv_l1_forward(
                     _lib.ptr(x3), _lib.ptr(y3), _lib.ptr(lengths), _lib.ptr(scale),
@@ -294,7 +304,7 @@ class _MagL1Function(torch.autograd.Function):
         if n_sig:
             lib = _lib.lib()
             nbytes = lib.brv_l1_workspace_bytes(n_sig, n_elems)
-            ws = _workspace(nbytes, X.device)
+            ws = _workspace(nbytes, n_sig, X.device)
             with _lib.on_device(X.device):
                 _lib.check(lib.brv_mag_l1_forward(
                     _lib.ptr(X), _lib.ptr(Y), n_sig, n_elems, _lib.ptr(out), _lib.ptr(ws),

@@ -29,17 +29,53 @@ constexpr int T_STAGES = 3;
 constexpr int T_SMEM_STAGES = T_STAGES * T_STAGE_BYTES;    // 144 KB
 constexpr int T_TMEM_COLS = 512;                           // 2 buffers x 4 accumulators x 64 frames
 
-// the strip of CTA `cta` out of `ctas` over `total` columns, walked in tiles
+// Dev-only role timing (-DBRV_PHASE_TIMING): lane 0 of each role's first warp of CTA 0 stamps
+// %globaltimer when it starts waiting for a tile (0), starts working on it (1) and is done (2);
+// tools/t_phase.py reads them back through brv_debug_t_times.
+#ifdef BRV_PHASE_TIMING
+__device__ unsigned long long g_brv_t_ts[5 * 8 * 4];
+#define T_STAMP(role, tile, which)                                                      \
+    do {                                                                                \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile) < 8) {                 \
+            unsigned long long t_;                                                      \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                       \
+            g_brv_t_ts[((role) * 8 + (tile)) * 4 + (which)] = t_;                       \
+        }                                                                               \
+    } while (0)
+// cycles a role's lane 0 spent inside one kind of wait, summed over the kernel (slot 0..31)
+__device__ unsigned long long g_brv_t_wait[32];
+#define T_WAIT_DECL long long t_wacc_[4] = {0, 0, 0, 0}
+#define T_WAITED(k, stmt)                                                               \
+    do {                                                                                \
+        const long long t0_ = clock64();                                                \
+        stmt;                                                                           \
+        t_wacc_[k] += clock64() - t0_;                                                  \
+    } while (0)
+#define T_WAIT_FLUSH(role)                                                              \
+    do {                                                                                \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)                                 \
+            for (int k_ = 0; k_ < 4; ++k_) g_brv_t_wait[(role) * 4 + k_] = (unsigned long long)t_wacc_[k_]; \
+    } while (0)
+#else
+#define T_STAMP(role, tile, which) do {} while (0)
+#define T_WAIT_DECL do {} while (0)
+#define T_WAITED(k, stmt) stmt
+#define T_WAIT_FLUSH(role) do {} while (0)
+#endif
+
+// the strip of CTA `cta` out of `ctas` over `total` columns (< 2^31), walked in tiles
 struct StripIter {
-    int64_t g, g1, per_signal;
+    uint32_t g, g1, per_signal;
     int nf;
     __device__ StripIter(int64_t total, int64_t per_signal_, int nf_, int cta, int ctas)
-        : g(total * cta / ctas), g1(total * (cta + 1) / ctas), per_signal(per_signal_), nf(nf_) {}
-    __device__ bool next(int64_t& sig, int64_t& c0, int& ncols) {
+        : g((uint32_t)(total * cta / ctas)), g1((uint32_t)(total * (cta + 1) / ctas)),
+          per_signal((uint32_t)per_signal_), nf(nf_) {}
+    __device__ __forceinline__ bool next(int64_t& sig, int64_t& c0, int& ncols) {
         if (g >= g1) return false;
-        sig = g / per_signal;
-        c0 = g - sig * per_signal;
-        const int64_t m = min((int64_t)nf, min(per_signal - c0, g1 - g));
+        const uint32_t s = g / per_signal, c = g - s * per_signal;
+        sig = s;
+        c0 = c;
+        const uint32_t m = min((uint32_t)nf, min(per_signal - c, g1 - g));
         ncols = (int)m;
         g += m;
         return true;
@@ -63,12 +99,15 @@ __device__ __forceinline__ void bulk_g2s_t(void* smem_dst, const void* gsrc, uin
 //
 //   warp 0        TMA producer: basis k-chunks (3-stage mbarrier ring)
 //   warp 1        TMEM owner + MMA issuer
-//   warps 2-3     span loaders: bulk-copy the NEXT tile's sample span into the other span
-//                 buffer, per-32-sample maxima, per-frame power-of-two scales and rank-1 terms
-//   warps 4-11    epilogue: thread = bin pair (TMEM lane), 32 frames per warp
-//   warps 12-19   operand builders: window, fold, scale, split (from the staged span)
+//   warp 2        span loader: bulk-copies the NEXT tile's sample span into the other span buffer
+//                 (zero padding and ragged edges by its lanes; the iSTFT gradient's 1 / envelope
+//                 multiplier is applied here too); warp 3 idle
+//   warps 4-11    epilogue: thread = bin pair (TMEM lane), 32 frames per warp, 16-byte stores
+//   warps 12-19   operand builders: a warp owns 8 frames: per-32-sample maxima of their samples ->
+//                 per-frame power-of-two scales and rank-1 terms (no CTA-wide barrier), then
+//                 window, fold, scale, split from the staged span
 constexpr int FT_THREADS = 640;
-constexpr int FT_LOADER_WARP0 = 2, FT_LOADER_THREADS = 64;
+constexpr int FT_LOADER_WARP0 = 2;
 constexpr int FT_EPI_WARP0 = 4, FT_EPI_WARPS = 8;
 constexpr int FT_BUILD_WARP0 = 12, FT_BUILD_WARPS = 8;
 constexpr int FT_SPAN = (T_NF - 1) * 128 + 512 + 64;        // floats per span buffer (8640)
@@ -77,13 +116,32 @@ constexpr int FT_OFF_SPAN = T_SMEM_STAGES;
 constexpr int FT_OFF_WTAB = FT_OFF_SPAN + 2 * FT_SPAN * 4;
 constexpr int FT_OFF_ROWINFO = FT_OFF_WTAB + SMEM_WTAB;      // 2 slots x 64 float4
 constexpr int FT_OFF_BMAX = FT_OFF_ROWINFO + 2 * T_NF * 16;
-constexpr int FT_SMEM_BYTES = 1024 + FT_OFF_BMAX + 2 * FT_BMAX * 4;
+constexpr int FT_SMEM_BYTES = 1024 + FT_OFF_BMAX + 2 * FT_BMAX * 4 + 32;
 static_assert(FT_SMEM_BYTES <= 227 * 1024, "transposed forward kernel shared memory");
 
 // frames per tile for a given geometry: the tile's span must fit one span buffer
 static inline int ft_tile_frames(int n_fft, int hop, int shift) {
     int nf = (FT_SPAN - 32 - n_fft - shift) / hop + 1;
     return nf > T_NF ? T_NF : nf;
+}
+
+// iSTFT gradient: span[i] *= 1 / (overlap-added w^2) of sample span0 + i (position + origin)
+__device__ __noinline__ void ft_apply_envelope(float* span, int i_begin, int i_end, int i_step, int64_t span0,
+                                               const float* in_mul, const float* env_per, const float* wsq,
+                                               int N, int H, int64_t n_frames, int64_t samples, int origin) {
+    for (int i = i_begin; i < i_end; i += i_step) {
+        const int64_t j = span0 + i;
+        if (j < 0 || j >= samples) continue;
+        float m;
+        if (in_mul) {
+            m = __ldg(in_mul + j);
+        } else {
+            const int64_t pos = j + origin;
+            const int64_t u = pos / H;
+            m = ola_inv_envelope(env_per, wsq, N, H, n_frames, u, (int)(pos - u * H));
+        }
+        span[i] *= m;
+    }
 }
 
 template <bool COMPRESS>
@@ -94,11 +152,11 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
     __shared__ __align__(8) uint64_t empty_bar[T_STAGES];
     __shared__ __align__(8) uint64_t tmem_full[2];     // MMA -> epilogue
     __shared__ __align__(8) uint64_t tmem_empty[2];    // epilogue -> MMA
-    __shared__ __align__(8) uint64_t span_full[2];     // loaders -> builders (span + row info)
-    __shared__ __align__(8) uint64_t span_empty[2];    // builders -> loaders
-    __shared__ __align__(8) uint64_t ri_full[2];       // builders -> epilogue (Nyquist sums written)
-    __shared__ __align__(8) uint64_t ri_empty[2];      // epilogue -> loaders (row info slot)
-    __shared__ __align__(8) uint64_t span_landed[2];   // bulk copy of the span
+    __shared__ __align__(8) uint64_t span_empty[2];    // builders -> loader
+    __shared__ __align__(8) uint64_t ri_full[2];       // builders -> epilogue (row info complete)
+    __shared__ __align__(8) uint64_t ri_empty[2];      // epilogue -> builders (row info slot)
+    __shared__ __align__(8) uint64_t span_landed[2];   // loader -> builders: span staged (bulk copy + edges)
+    __shared__ __align__(8) uint64_t span_copied[2];   // bulk copy landed (loader's own, gradient use)
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -120,11 +178,11 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
             mbar_init(&tmem_empty[b], FT_EPI_WARPS);
-            mbar_init(&span_full[b], FT_LOADER_THREADS / 32);
             mbar_init(&span_empty[b], FT_BUILD_WARPS);
             mbar_init(&ri_full[b], FT_BUILD_WARPS);
             mbar_init(&ri_empty[b], FT_EPI_WARPS);
-            mbar_init(&span_landed[b], 1);
+            mbar_init(&span_landed[b], 2);              // expect_tx arrive + edge fills done
+            mbar_init(&span_copied[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -142,13 +200,14 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
     if (warp == 0) {
         // ===================== TMA producer: basis k-chunks =====================
         if (elect_one()) {
+            T_WAIT_DECL;
             int g = 0;
             while (strip.next(sig, t0, ncols))
                 for (int it = 0; it < n_it; ++it, ++g) {
                     const int s = g % T_STAGES;
                     const uint32_t ph = (g / T_STAGES) & 1;
                     const int kc = it >> 1, pair = it & 1;
-                    mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
+                    T_WAITED(0, mbar_wait_relaxed(&empty_bar[s], ph ^ 1));
                     mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
                     uint8_t* sb = stages + (size_t)s * T_STAGE_BYTES;
 #pragma unroll
@@ -157,22 +216,26 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                         for (int pl = 0; pl < 2; ++pl)
                             tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
                                         &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
+                    T_WAIT_FLUSH(4);
                 }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer ======================================
         if (elect_one()) {
+            T_WAIT_DECL;
             int g = 0, n = 0;
             for (; strip.next(sig, t0, ncols); ++n) {
                 const int buf = n & 1;
                 const uint32_t idesc = umma_idesc_f16(TILE_M, (ncols + 15) & ~15);
-                mbar_wait_relaxed(&tmem_empty[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
+                T_STAMP(2, n, 0);
+                T_WAITED(0, mbar_wait_relaxed(&tmem_empty[buf], (uint32_t)(((n >> 1) & 1) ^ 1)));
                 tcgen05_fence_after();
+                T_STAMP(2, n, 1);
                 for (int it = 0; it < n_it; ++it, ++g) {
                     const int s = g % T_STAGES;
                     const uint32_t ph = (g / T_STAGES) & 1;
                     const int kc = it >> 1, pair = it & 1;
-                    mbar_wait_relaxed(&full_bar[s], ph, 32);
+                    T_WAITED(1, mbar_wait_relaxed(&full_bar[s], ph, 32));
                     tcgen05_fence_after();
                     const uint32_t a0 = smem_u32(stages + (size_t)s * T_STAGE_BYTES);
                     const uint32_t b0 = a0 + T_STAGE_BASIS;
@@ -194,24 +257,26 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                     umma_commit(&empty_bar[s]);
                 }
                 umma_commit(&tmem_full[buf]);
+                T_STAMP(2, n, 2);
+                T_WAIT_FLUSH(2);
             }
         }
-    } else if (warp < FT_EPI_WARP0) {
-        // ===================== span loaders ====================================
-        const int lt = threadIdx.x - FT_LOADER_WARP0 * 32;         // 0..63
+    } else if (warp == FT_LOADER_WARP0) {
+        // ===================== span loader =====================================
+        T_WAIT_DECL;
         const int shift = p.shift;
+        const bool mul = p.in_mul != nullptr || p.grad_env;
         for (int n = 0; strip.next(sig, t0, ncols); ++n) {
             const int b = n & 1;
             float* span = span2 + b * FT_SPAN;
-            uint32_t* bmax = bmax2 + b * FT_BMAX;
-            float4* rowinfo = rowinfo2 + b * T_NF;
             const float* xs = p.x + sig * p.x_stride;
             const int64_t span0 = t0 * H - p.origin - shift;       // first sample of the span (may be < 0)
             const int span_len = (ncols - 1) * H + N + shift;
             const int span_pad = (span_len + 31) & ~31;
             const uint32_t kph = (uint32_t)((n >> 1) & 1);
-            mbar_wait_relaxed(&span_empty[b], kph ^ 1);
-            mbar_wait_relaxed(&ri_empty[b], kph ^ 1);
+            T_STAMP(0, n, 0);
+            T_WAITED(0, mbar_wait_relaxed(&span_empty[b], kph ^ 1));
+            T_STAMP(0, n, 1);
             // valid samples are span indices [lo, hi); [lo4, hi4) leaves by one bulk copy
             const int lo = (int)min((int64_t)span_pad, max((int64_t)0, -span0));
             const int hi = (int)max((int64_t)lo, min((int64_t)span_pad, p.samples - span0));
@@ -222,78 +287,34 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                 hi4 = hi & ~3;
                 if (hi4 < lo4) hi4 = lo4;
             }
-            if (lt == 0) {
+            uint64_t* landing = mul ? &span_copied[b] : &span_landed[b];
+            if (lane == 0) {
                 const uint32_t bytes = (uint32_t)(hi4 - lo4) * 4u;
-                mbar_arrive_expect_tx(&span_landed[b], bytes);
-                if (bytes) bulk_g2s_t(span + lo4, xs + span0 + lo4, bytes, &span_landed[b]);
+                mbar_arrive_expect_tx(landing, bytes);
+                if (bytes) bulk_g2s_t(span + lo4, xs + span0 + lo4, bytes, landing);
             }
             // everything outside the bulk range: zero padding, ragged edges, unaligned rows
-            for (int i = lt; i < lo4; i += FT_LOADER_THREADS)
-                span[i] = i >= lo ? __ldg(xs + span0 + i) : 0.f;
-            for (int i = hi4 + lt; i < span_pad; i += FT_LOADER_THREADS)
-                span[i] = i < hi ? __ldg(xs + span0 + i) : 0.f;
-            mbar_wait_relaxed(&span_landed[b], kph, 32);
-            named_bar_sync(2, FT_LOADER_THREADS);
-            // ---- per-32-sample maxima (and the gradient's input multiplier) ----------
-            for (int k = lt; k < span_pad / 32; k += FT_LOADER_THREADS) {
-                float4* blk = reinterpret_cast<float4*>(span + 32 * k);
-                float m = 0.f;
-                // iSTFT gradient: gy / (overlap-added w^2); sample i sits at position i + origin =
-                // hop block eu, offset eoff (one division per 32 samples, then incremental)
-                int64_t eu = 0;
-                int eoff = 0;
-                if (p.grad_env) {
-                    const int64_t kk = (N + H - 1) / H + 1;
-                    const int64_t pb = span0 + 32 * k + p.origin + kk * H;     // >= 0
-                    eu = pb / H - kk;
-                    eoff = (int)(pb % H);
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float4 f = blk[e];
-                    if (p.in_mul) {
-                        f = mul4(f, load4_clamped(p.in_mul, span0 + 32 * k + 4 * e, p.samples));
-                        blk[e] = f;
-                    } else if (p.grad_env) {
-                        float* fe = reinterpret_cast<float*>(&f);
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            const int64_t i = span0 + 32 * k + 4 * e + cc;
-                            if (i >= 0 && i < p.samples)
-                                fe[cc] *= ola_inv_envelope(p.env_per, p.wsq, N, H, p.n_frames, eu, eoff);
-                            if (++eoff >= H) {
-                                eoff = 0;
-                                ++eu;
-                            }
-                        }
-                        blk[e] = f;
-                    }
-                    m = fmaxf(m, fmaxf(fmaxf(finite_abs(f.x), finite_abs(f.y)),
-                                       fmaxf(finite_abs(f.z), finite_abs(f.w))));
-                }
-                bmax[k] = __float_as_uint(m);
-            }
-            named_bar_sync(2, FT_LOADER_THREADS);
-            // ---- per-frame scale and rank-1 terms -------------------------------------
-            if (lt < T_NF) {
-                float4 ri = make_float4(1.f, 0.f, 0.f, 0.f);
-                if (lt < ncols) {
-                    const int b0 = (lt * H + shift) >> 5, b1 = (lt * H + shift + N - 1) >> 5;
-                    uint32_t mx = 0u;
-                    for (int k = b0; k <= b1; ++k) mx = max(mx, bmax[k]);
-                    ri.x = row_scale(4.f * p.wmax * __uint_as_float(mx));
-                    const float xq = span[shift + lt * H + Q] * p.wq,
-                                x3q = span[shift + lt * H + 3 * Q] * p.w3q;
-                    ri.z = xq + x3q;                   // ee[Q]
-                    ri.w = xq - x3q;                   // oo[Q]
-                }
-                rowinfo[lt] = ri;
+            for (int i = lane; i < lo4; i += 32) span[i] = i >= lo ? __ldg(xs + span0 + i) : 0.f;
+            for (int i = hi4 + lane; i < span_pad; i += 32) span[i] = i < hi ? __ldg(xs + span0 + i) : 0.f;
+            if (mul) {
+                // gradient of the inverse transform: gy / envelope, once the copy has landed
+                mbar_wait_relaxed(&span_copied[b], kph, 32);
+                __syncwarp();
+                ft_apply_envelope(span, lane, span_pad, 32, span0, p.in_mul, p.env_per, p.wsq, N, H, p.n_frames,
+                                  p.samples, p.origin);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&span_landed[b]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&span_full[b]);
+            if (lane == 0) mbar_arrive(&span_landed[b]);
+            T_STAMP(0, n, 2);
+            T_WAIT_FLUSH(0);
         }
+    } else if (warp < FT_EPI_WARP0) {
+        // (warp 3 idles)
     } else if (warp < FT_BUILD_WARP0) {
         // ===================== epilogue ========================================
+        T_WAIT_DECL;
         const int e = warp - FT_EPI_WARP0;         // 0..7
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         const int chalf = e >> 2;                  // which 32 frames of the tile
@@ -301,15 +322,19 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
         const bool valid = m < Q;
         const float sgn = (m & 1) ? -1.f : 1.f;
         const int pitch = 2 * p.n_bins;
+        const bool alt = (pitch & 3) != 0;         // row alignment alternates between 16 and 8 bytes
         const float ps = COMPRESS ? 1.f : p.post_scale;   // without compression scale_factor folds in
         const float dcs = m == 0 ? p.dc_scale : 1.f;
+        const float gb = ps * p.basis_scale_inv;
         for (int n = 0; strip.next(sig, t0, ncols); ++n) {
             const int buf = n & 1;
             const float4* rowinfo = rowinfo2 + buf * T_NF;
             const uint32_t kph = (uint32_t)((n >> 1) & 1);
-            mbar_wait_relaxed(&ri_full[buf], kph);
-            mbar_wait_relaxed(&tmem_full[buf], kph);
+            if (warp == FT_EPI_WARP0) T_STAMP(3, n, 0);
+            T_WAITED(0, mbar_wait_relaxed(&ri_full[buf], kph));
+            T_WAITED(1, mbar_wait_relaxed(&tmem_full[buf], kph));
             tcgen05_fence_after();
+            if (warp == FT_EPI_WARP0) T_STAMP(3, n, 1);
             float* obase = p.out + ((sig * p.n_frames + t0) * (int64_t)pitch + 4 * m);
             const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * T_NF);
 #pragma unroll 1
@@ -321,13 +346,14 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                 tmem_ld16_nowait(tq + (uint32_t)(T_NF + c0), r1);       // Re X[2m+1]
                 tmem_ld16_nowait(tq + (uint32_t)(2 * T_NF + c0), r2);   // Im X[2m]
                 tmem_ld16_nowait(tq + (uint32_t)(3 * T_NF + c0), r3);   // Im X[2m+1]
+                float* o0 = obase + (int64_t)c0 * pitch;
+                const bool a0 = (reinterpret_cast<uintptr_t>(o0) & 15) == 0;    // c0 is even
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int c = c0 + j;
-                    if (c < ncols && valid) {
-                        const float4 ri = rowinfo[c];              // scale, nyquist sum, ee[Q], oo[Q]
-                        const float g0 = ps * p.basis_scale_inv * pow2_inv(ri.x);
+                    if (c0 + j < ncols && valid) {
+                        const float4 ri = rowinfo[c0 + j];         // scale, nyquist sum, ee[Q], oo[Q]
+                        const float g0 = gb * pow2_inv(ri.x);
                         float re_e = fmaf(__uint_as_float(r0[j]), g0, sgn * ps * ri.z) * dcs;
                         float re_o = __uint_as_float(r1[j]) * g0;
                         float im_e = __uint_as_float(r2[j]) * g0;
@@ -338,8 +364,8 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                             re_e *= p.post_scale; im_e *= p.post_scale;
                             re_o *= p.post_scale; im_o *= p.post_scale;
                         }
-                        float* o = obase + (int64_t)c * pitch;
-                        if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                        float* o = o0 + j * pitch;
+                        if ((j & 1) && alt ? !a0 : a0) {
                             *reinterpret_cast<float4*>(o) = make_float4(re_e, im_e, re_o, im_o);
                         } else {
                             *reinterpret_cast<float2*>(o) = make_float2(re_e, im_e);
@@ -362,26 +388,70 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ri_empty[buf]);
+            if (warp == FT_EPI_WARP0) T_STAMP(3, n, 2);
+            if (warp == FT_EPI_WARP0) T_WAIT_FLUSH(3);
         }
     } else {
         // ===================== builders ========================================
+        T_WAIT_DECL;
         const int bw = warp - FT_BUILD_WARP0;      // 0..7
         const int half = lane >> 4;                // which of the warp's two rows per pass
         const int pr = lane & 15;                  // n pair inside the 32-wide k-chunk
         const uint32_t chunk = (uint32_t)(pr >> 2);
         const int shift = p.shift;
         constexpr int RI = T_NF / FT_BUILD_WARPS / 2;     // row pairs per warp (4)
+        constexpr int ROWS_W = 2 * RI;                    // rows per warp (8)
         int g = 0;
         for (int n = 0; strip.next(sig, t0, ncols); ++n) {
             const int b = n & 1;
             const float* span = span2 + b * FT_SPAN;
             float4* rowinfo = rowinfo2 + b * T_NF;
-            mbar_wait(&span_full[b], (uint32_t)((n >> 1) & 1));
+            uint32_t* bmax = bmax2 + b * FT_BMAX;
+            if (bw == 0) T_STAMP(1, n, 0);
+            const uint32_t kph = (uint32_t)((n >> 1) & 1);
+            T_WAITED(0, mbar_wait_relaxed(&span_landed[b], kph, 20));
+            T_WAITED(1, mbar_wait_relaxed(&ri_empty[b], kph ^ 1, 20));
+            if (bw == 0) T_STAMP(1, n, 1);
+            if (bw * ROWS_W < ncols) {
+                // ---- this warp's frames: per-32-sample maxima of the samples they cover (the
+                //      neighbouring warps scan the overlap again and store the same values),
+                //      then the per-frame scale and rank-1 terms ---------------------------
+                const int rows_w = min(ROWS_W, ncols - bw * ROWS_W);
+                const int s_lo = (bw * ROWS_W * H + shift) & ~31;
+                const int s_hi = ((bw * ROWS_W + rows_w - 1) * H + shift + N + 31) & ~31;   // whole blocks (<= span_pad)
+                for (int i0 = s_lo; i0 < s_hi; i0 += 128) {
+                    const int i = i0 + lane * 4;
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < s_hi) f = *reinterpret_cast<const float4*>(span + i);
+                    // fmaxf drops NaNs; an inf is removed by the slow path
+                    float m = fmaxf(fmaxf(fabsf(f.x), fabsf(f.y)), fmaxf(fabsf(f.z), fabsf(f.w)));
+                    if (!(m <= 3.0e38f))
+                        m = fmaxf(fmaxf(finite_abs(f.x), finite_abs(f.y)),
+                                  fmaxf(finite_abs(f.z), finite_abs(f.w)));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                    if ((lane & 7) == 0 && i < s_hi) bmax[i >> 5] = __float_as_uint(m);
+                }
+                __syncwarp();
+                if (lane < rows_w) {
+                    const int row = bw * ROWS_W + lane;
+                    const int b0 = (row * H + shift) >> 5, b1 = (row * H + shift + N - 1) >> 5;
+                    uint32_t mx = 0u;
+                    for (int k = b0; k <= b1; ++k) mx = max(mx, bmax[k]);
+                    const float xq = span[shift + row * H + Q] * p.wq,
+                                x3q = span[shift + row * H + 3 * Q] * p.w3q;
+                    // scale, (nyquist sum: below), ee[Q], oo[Q]
+                    rowinfo[row] = make_float4(row_scale(4.f * p.wmax * __uint_as_float(mx)), 0.f,
+                                               xq + x3q, xq - x3q);
+                }
+                __syncwarp();
+            }
             float rscale[RI], nyq[RI];
             const float* frow[RI];
 #pragma unroll
             for (int i = 0; i < RI; ++i) {
-                const int row = bw * (2 * RI) + 2 * i + half;
+                const int row = bw * ROWS_W + 2 * i + half;
                 rscale[i] = row < ncols ? rowinfo[row].x : 0.f;
                 nyq[i] = 0.f;
                 // rows >= ncols are built too (scale 0, accumulator columns never read)
@@ -405,11 +475,11 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                 for (int pair = 0; pair < 2; ++pair, ++g) {
                     const int s = g % T_STAGES;
                     const uint32_t ph = (g / T_STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    T_WAITED(2, mbar_wait_relaxed(&empty_bar[s], ph ^ 1, 20));
                     uint8_t* sa = stages + (size_t)s * T_STAGE_BYTES + T_STAGE_BASIS;
 #pragma unroll
                     for (int i = 0; i < RI; ++i) {
-                        const int row = bw * (2 * RI) + 2 * i + half;
+                        const int row = bw * ROWS_W + 2 * i + half;
                         float u0, u1, v0, v1;
                         if (pair == 0) {
                             u0 = sp0[i] + rp0[i]; u1 = sp1[i] + rp1[i];    // ee
@@ -434,7 +504,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                             v += __shfl_xor_sync(0xffffffffu, v, 4);
                             v += __shfl_xor_sync(0xffffffffu, v, 2);
                             v += __shfl_xor_sync(0xffffffffu, v, 1);
-                            const int row = bw * (2 * RI) + 2 * i + half;
+                            const int row = bw * ROWS_W + 2 * i + half;
                             if (pr == 0 && row < ncols) rowinfo[row].y = v;
                         }
                     }
@@ -448,6 +518,8 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                 mbar_arrive(&ri_full[b]);
                 mbar_arrive(&span_empty[b]);
             }
+            if (bw == 0) T_STAMP(1, n, 2);
+            if (bw == 0) T_WAIT_FLUSH(1);
         }
     }
     tcgen05_fence_before();
@@ -465,49 +537,58 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
 // when v >= n_frames).  An epilogue thread owns sample offset n (its TMEM lane, row n of Ce, Co,
 // Se, So) and produces, per frame, the four values
 //     a = f[n]  b = f[N/2 - n]  c = f[N/2 + n]  d = f[N - n]      (thread 0: b = f[Q], d = f[3Q])
-// which land in hop blocks v .. v + R - 1 at offset n (a, c) or at the mirrored offset (b, d).
-// Walking along the frames it keeps the values of the previous R - 1 frames in registers, so a
-// hop block is finished with two shared-memory writes (direct + mirrored) and no exchange
-// between threads; the carried values survive from one tile to the next of the same strip.
-// A strip that starts inside a signal recomputes the R - 1 frames before it (`skip` columns
-// whose hop blocks belong to the previous CTA).
+// which land in hop blocks v .. v + R - 1 at offset n (a, c: "direct") or at the mirrored offset
+// (b, d).  Walking along the frames it keeps the values of the previous R - 1 frames in registers:
+//     hop = Q :  direct(v) = a(v) + c(v-2)   mirrored(v) = b(v-1) + d(v-3)   at offset (Q - n) % Q
+//     hop = 2Q:  direct(v) = a(v) + c(v-1)   mirrored(v) = b(v) + d(v-1)     at offset 2Q - n (Q for n = 0)
+// For hop = 2Q the two land on different offsets and go straight to HBM; for hop = Q the mirrored
+// sums of 8 frames cross the 128 threads through a small shared-memory exchange, are added to the
+// direct sums in registers and leave as 128-byte rows per warp, multiplied by 1 / envelope (periodic
+// in the interior, summed on the fly at the edges) -- no staged output tile, no copy-out phase.
+// Two sets of four epilogue warps alternate tiles (set = TMEM buffer); the carried values of a
+// tile's last R - 1 frames are computed FIRST and handed to the other set, so both sets run
+// concurrently.  A strip that starts inside a signal recomputes the R - 1 frames before it (`skip`
+// columns whose hop blocks belong to the previous CTA).
 //
-//   warp 0        TMA producer: basis k-chunks (3-stage ring)      warps 2-3 idle
+//   warp 0        TMA producer: basis k-chunks (3-stage ring)
 //   warp 1        TMEM owner + MMA issuer
-//   warps 4-7     epilogue + copy-out (1 / envelope, centre trim)
-//   warps 8-15    operand builders: spectrogram (L2-resident after the scouts) -> scaled fp16
-//                 hi / lo planes; the next k-chunk's loads are in flight while one is converted
-//   warps 16-23   scouts: per-frame maxima of the NEXT tile straight from HBM (18 loads in
+//   warps 4-7     epilogue set 0 (even tiles)      warps 8-11  epilogue set 1 (odd tiles)
+//   warps 12-19   operand builders: spectrogram (L2-resident after the scouts) -> scaled fp16
+//                 hi / lo planes; two register buffers alternate so that the next k-chunk's loads
+//                 (also across tiles) are in flight while one is converted
+//   warps 20-27   scouts: per-frame maxima of the NEXT tile straight from HBM (18 loads in
 //                 flight per lane), which also leaves that tile L2-resident for the builders
-constexpr int IT_THREADS = 768;
-constexpr int IT_EPI_WARP0 = 4, IT_EPI_WARPS = 4;
-constexpr int IT_BUILD_WARP0 = 8, IT_BUILD_WARPS = 8, IT_BUILD_THREADS = IT_BUILD_WARPS * 32;
-constexpr int IT_SCOUT_WARP0 = 16, IT_SCOUT_WARPS = 8, IT_SCOUT_THREADS = IT_SCOUT_WARPS * 32;
-constexpr int IT_OUT_FLOATS = T_NF * 258;                   // HQ = 1: 2 x [64][129]; HQ = 2: [64][257]
-constexpr int IT_OFF_OUT = T_SMEM_STAGES;
-constexpr int IT_OFF_ROWINFO = IT_OFF_OUT + IT_OUT_FLOATS * 4;   // 2 slots x 64 float4
-constexpr int IT_OFF_SCRATCH = IT_OFF_ROWINFO + 2 * T_NF * 16;   // [12][64] floats (builders 0..7, scouts 8..11)
+constexpr int IT_THREADS = 896;
+constexpr int IT_EPI_WARP0 = 4, IT_EPI_SET_WARPS = 4;
+constexpr int IT_BUILD_WARP0 = 12, IT_BUILD_WARPS = 8, IT_BUILD_THREADS = IT_BUILD_WARPS * 32;
+constexpr int IT_SCOUT_WARP0 = 20, IT_SCOUT_WARPS = 8, IT_SCOUT_THREADS = IT_SCOUT_WARPS * 32;
+constexpr int IT_XP = MAX_Q + 1;                              // exchange row pitch (floats)
+constexpr int IT_OFF_EXCH = T_SMEM_STAGES;                    // [set 2][buffer 2][8 frames][IT_XP]
+constexpr int IT_OFF_CARRY = IT_OFF_EXCH + 2 * 2 * 8 * IT_XP * 4;   // [consumer set 2][slot 2][6][128]
+constexpr int IT_OFF_ROWINFO = IT_OFF_CARRY + 2 * 2 * 6 * 128 * 4;  // 2 slots x 64 float4
+constexpr int IT_OFF_SCRATCH = IT_OFF_ROWINFO + 2 * T_NF * 16;      // [12][64] floats (builders 0..7, scouts 8..11)
 constexpr int IT_SMEM_BYTES = 1024 + IT_OFF_SCRATCH + 12 * T_NF * 4;
 static_assert(IT_SMEM_BYTES <= 227 * 1024, "transposed inverse kernel shared memory");
 
 struct InvStrip {
-    int64_t g, g1, per_signal;
+    uint32_t g, g1, per_signal;
     int nf, halo;
     bool first;
     __device__ InvStrip(int64_t total, int64_t per_signal_, int nf_, int halo_, int cta, int ctas)
-        : g(total * cta / ctas), g1(total * (cta + 1) / ctas), per_signal(per_signal_), nf(nf_),
-          halo(halo_), first(true) {}
+        : g((uint32_t)(total * cta / ctas)), g1((uint32_t)(total * (cta + 1) / ctas)),
+          per_signal((uint32_t)per_signal_), nf(nf_), halo(halo_), first(true) {}
     // tile = columns [c0, c0 + ncols) of signal `sig`; the first `skip` columns only warm up
     // the carried state (their hop blocks belong to the previous strip); `fresh`: no carried
-    // state from the previous tile
-    __device__ bool next(int64_t& sig, int64_t& c0, int& ncols, int& skip, bool& fresh) {
+    // state from the previous tile.  A tile that is followed by a non-fresh one is always full
+    // (ncols == nf): only the end of a signal or of the strip cuts a tile short.
+    __device__ __forceinline__ bool next(int64_t& sig, int64_t& c0, int& ncols, int& skip, bool& fresh) {
         if (g >= g1) return false;
-        sig = g / per_signal;
-        const int64_t v = g - sig * per_signal;
+        const uint32_t s = g / per_signal, v = g - s * per_signal;
+        sig = s;
         fresh = first || v == 0;
-        skip = first ? (int)min((int64_t)halo, v) : 0;
+        skip = first ? (int)min((uint32_t)halo, v) : 0;
         c0 = v - skip;
-        const int64_t m = min((int64_t)nf, min(per_signal - c0, g1 - g + skip));
+        const uint32_t m = min((uint32_t)nf, min(per_signal - (v - skip), g1 - g + skip));
         ncols = (int)m;
         g += m - skip;
         first = false;
@@ -515,22 +596,54 @@ struct InvStrip {
     }
 };
 
+__device__ __noinline__ float it_edge_envelope(const float* env_per, const float* wsq, int N, int H,
+                                               int64_t n_frames, int64_t u, int off) {
+    return ola_inv_envelope(env_per, wsq, N, H, n_frames, u, off);
+}
+
+// the four values of one frame for sample offset n from its row of Ce, Co, Se, So
+__device__ __forceinline__ void it_frame_values(uint32_t ace, uint32_t aco, uint32_t ase, uint32_t aso,
+                                                const float4 ri, bool live, bool t0, float sgn,
+                                                const float4 wn, float bsi, float wq, float w3q,
+                                                float& a, float& b, float& c, float& d) {
+    // columns >= ncols hold stale accumulators: select, do not multiply, them away
+    const float g0 = bsi * pow2_inv(ri.x);             // ri = scale, 2 pacc, 2 racc, nyquist term
+    const float ce = live ? __uint_as_float(ace) * g0 : 0.f;
+    const float co = live ? __uint_as_float(aco) * g0 : 0.f;
+    const float se = live ? __uint_as_float(ase) * g0 : 0.f;
+    const float so = live ? __uint_as_float(aso) * g0 : 0.f;
+    const float ny = live ? sgn * ri.w : 0.f;
+    const float cp = ce + co, cm = ce - co, sp = se + so, sm = se - so;
+    a = ((cp - sp) + ny) * wn.x;
+    b = ((cm + sm) + ny) * wn.y;
+    c = ((cm - sm) + ny) * wn.z;
+    d = ((cp + sp) + ny) * wn.w;
+    // thread 0: f[Q], f[3Q] (Q is even: the Nyquist term enters with +1); selects, not a branch
+    const float fq = live ? (ri.y - ri.z + ri.w) * wq : 0.f;
+    const float f3q = live ? (ri.y + ri.z + ri.w) * w3q : 0.f;
+    b = t0 ? fq : b;
+    d = t0 ? f3q : d;
+}
+
 template <int HQ, bool FRAMES_FAST, bool DECOMP>
 __global__ void __launch_bounds__(IT_THREADS, 1)
 istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[T_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[T_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full[2];     // MMA -> epilogue
-    __shared__ __align__(8) uint64_t tmem_empty[2];    // epilogue -> MMA
+    __shared__ __align__(8) uint64_t tmem_full[2];     // MMA -> epilogue set
+    __shared__ __align__(8) uint64_t tmem_empty[2];    // epilogue set -> MMA
     __shared__ __align__(8) uint64_t scale_full[2];    // scouts -> builders (frame scales ready)
-    __shared__ __align__(8) uint64_t scale_empty[2];   // epilogue -> scouts (row info slot reusable)
+    __shared__ __align__(8) uint64_t scale_empty[2];   // epilogue set -> scouts (row info slot reusable)
     __shared__ __align__(8) uint64_t ri_full[2];       // builders -> epilogue (rank-1 sums written)
+    __shared__ __align__(8) uint64_t carry_full[2];    // other set -> set: carried values written
+    __shared__ __align__(8) uint64_t carry_empty[2];   // set -> other set: carried values read
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     uint8_t* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* outbuf = reinterpret_cast<float*>(stages + IT_OFF_OUT);
+    float* exch_base = reinterpret_cast<float*>(stages + IT_OFF_EXCH);
+    float* carry_base = reinterpret_cast<float*>(stages + IT_OFF_CARRY);
     float4* rowinfo2 = reinterpret_cast<float4*>(stages + IT_OFF_ROWINFO);
     float* scratch = reinterpret_cast<float*>(stages + IT_OFF_SCRATCH);
 
@@ -546,10 +659,12 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], IT_EPI_WARPS);
+            mbar_init(&tmem_empty[b], IT_EPI_SET_WARPS);
             mbar_init(&scale_full[b], IT_SCOUT_WARPS);
-            mbar_init(&scale_empty[b], IT_EPI_WARPS);
+            mbar_init(&scale_empty[b], IT_EPI_SET_WARPS);
             mbar_init(&ri_full[b], IT_BUILD_WARPS);
+            mbar_init(&carry_full[b], IT_EPI_SET_WARPS);
+            mbar_init(&carry_empty[b], IT_EPI_SET_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -564,180 +679,224 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
     int ncols, skip;
     bool fresh;
 
+    // register budget (72 x 896 at launch): control 24, scouts 48, epilogue 80, builders 112
     if (warp < IT_EPI_WARP0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (warp == 0) {
-            // ===================== TMA producer: basis k-chunks =====================
-            if (elect_one()) {
-                int g = 0;
-                while (strip.next(sig, c0, ncols, skip, fresh))
-                    for (int it = 0; it < n_it; ++it, ++g) {
-                        const int s = g % T_STAGES;
-                        const uint32_t ph = (g / T_STAGES) & 1;
-                        const int kc = it >> 1, pair = it & 1;
-                        mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
-                        uint8_t* sb = stages + (size_t)s * T_STAGE_BYTES;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == 0) {
+        // ===================== TMA producer: basis k-chunks =====================
+        if (elect_one()) {
+            T_WAIT_DECL;
+            int g = 0;
+            while (strip.next(sig, c0, ncols, skip, fresh))
+                for (int it = 0; it < n_it; ++it, ++g) {
+                    const int s = g % T_STAGES;
+                    const uint32_t ph = (g / T_STAGES) & 1;
+                    const int kc = it >> 1, pair = it & 1;
+                    T_WAITED(0, mbar_wait_relaxed(&empty_bar[s], ph ^ 1));
+                    mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
+                    uint8_t* sb = stages + (size_t)s * T_STAGE_BYTES;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)
+                    for (int j = 0; j < 2; ++j)
 #pragma unroll
-                            for (int pl = 0; pl < 2; ++pl)
-                                tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
-                                            &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
-                    }
-            }
-        } else if (warp == 1) {
-            // ===================== MMA issuer ======================================
-            if (elect_one()) {
-                int g = 0, n = 0;
-                for (; strip.next(sig, c0, ncols, skip, fresh); ++n) {
-                    const int buf = n & 1;
-                    const uint32_t idesc = umma_idesc_f16(TILE_M, (ncols + 15) & ~15);
-                    mbar_wait_relaxed(&tmem_empty[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
-                    tcgen05_fence_after();
-                    for (int it = 0; it < n_it; ++it, ++g) {
-                        const int s = g % T_STAGES;
-                        const uint32_t ph = (g / T_STAGES) & 1;
-                        const int kc = it >> 1, pair = it & 1;
-                        mbar_wait_relaxed(&full_bar[s], ph, 32);
-                        tcgen05_fence_after();
-                        const uint32_t a0 = smem_u32(stages + (size_t)s * T_STAGE_BYTES);
-                        const uint32_t b0 = a0 + T_STAGE_BASIS;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const uint32_t d = tmem_base + (uint32_t)(buf * 4 * T_NF + (pair * 2 + j) * T_NF);
-#pragma unroll
-                            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                                const uint32_t off = ks * UMMA_K * 2;
-                                const uint64_t bh = umma_desc_sw64(a0 + (j * 2) * SUB_TILE + off);
-                                const uint64_t bl = umma_desc_sw64(a0 + (j * 2 + 1) * SUB_TILE + off);
-                                const uint64_t dh = umma_desc_sw64(b0 + (j * 2) * T_DATA_TILE + off);
-                                const uint64_t dl = umma_desc_sw64(b0 + (j * 2 + 1) * T_DATA_TILE + off);
-                                umma_f16(d, bh, dh, idesc, (kc | ks) != 0);
-                                umma_f16(d, bh, dl, idesc, 1);
-                                umma_f16(d, bl, dh, idesc, 1);
-                            }
-                        }
-                        umma_commit(&empty_bar[s]);
-                    }
-                    umma_commit(&tmem_full[buf]);
+                        for (int pl = 0; pl < 2; ++pl)
+                            tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
+                                        &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
+                    T_WAIT_FLUSH(4);
                 }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer ======================================
+        if (elect_one()) {
+            T_WAIT_DECL;
+            int g = 0, n = 0;
+            for (; strip.next(sig, c0, ncols, skip, fresh); ++n) {
+                const int buf = n & 1;
+                const uint32_t idesc = umma_idesc_f16(TILE_M, (ncols + 15) & ~15);
+                T_STAMP(2, n, 0);
+                T_WAITED(0, mbar_wait_relaxed(&tmem_empty[buf], (uint32_t)(((n >> 1) & 1) ^ 1)));
+                tcgen05_fence_after();
+                T_STAMP(2, n, 1);
+                for (int it = 0; it < n_it; ++it, ++g) {
+                    const int s = g % T_STAGES;
+                    const uint32_t ph = (g / T_STAGES) & 1;
+                    const int kc = it >> 1, pair = it & 1;
+                    T_WAITED(1, mbar_wait_relaxed(&full_bar[s], ph, 32));
+                    tcgen05_fence_after();
+                    const uint32_t a0 = smem_u32(stages + (size_t)s * T_STAGE_BYTES);
+                    const uint32_t b0 = a0 + T_STAGE_BASIS;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t d = tmem_base + (uint32_t)(buf * 4 * T_NF + (pair * 2 + j) * T_NF);
+#pragma unroll
+                        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                            const uint32_t off = ks * UMMA_K * 2;
+                            const uint64_t bh = umma_desc_sw64(a0 + (j * 2) * SUB_TILE + off);
+                            const uint64_t bl = umma_desc_sw64(a0 + (j * 2 + 1) * SUB_TILE + off);
+                            const uint64_t dh = umma_desc_sw64(b0 + (j * 2) * T_DATA_TILE + off);
+                            const uint64_t dl = umma_desc_sw64(b0 + (j * 2 + 1) * T_DATA_TILE + off);
+                            umma_f16(d, bh, dh, idesc, (kc | ks) != 0);
+                            umma_f16(d, bh, dl, idesc, 1);
+                            umma_f16(d, bl, dh, idesc, 1);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full[buf]);
+                T_STAMP(2, n, 2);
+                T_WAIT_FLUSH(2);
             }
         }
+    }
     } else if (warp < IT_BUILD_WARP0) {
-        // ===================== epilogue + copy-out ==============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // ===================== epilogue sets ===================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+        T_WAIT_DECL;
+        const int set = (warp - IT_EPI_WARP0) >> 2;      // even / odd tiles; also the TMEM buffer
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         const int nn = q * 32 + lane;              // sample offset n (row of Ce, Co, Se, So)
         const bool valid = nn < Q;
         const float4 wn = valid ? __ldg(p.wtab + nn) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float sgn = (nn & 1) ? -1.f : 1.f;
         const bool t0 = nn == 0;                   // carries f[Q], f[3Q] in its b, d slots
-        const int pitch = H + 1;                   // row skew (copy-out reads lanes along offsets)
-        float* outD = outbuf;
-        float* outM = HQ == 1 ? outbuf + T_NF * (Q + 1) : outbuf;
         const int moff = HQ == 1 ? (t0 ? 0 : Q - nn) : (t0 ? Q : 2 * Q - nn);   // mirrored offset
-        float env_reg[8];                          // 1 / envelope of interior hop blocks
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            env_reg[j] = p.no_env ? 1.f : (lane + 32 * j < H ? __ldg(p.env_per + lane + 32 * j) : 0.f);
-        float c1 = 0.f, c2 = 0.f, b1 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;   // previous frames' values
+        const float env_n = p.no_env ? 1.f : (valid ? __ldg(p.env_per + nn) : 0.f);
+        const float env_m = p.no_env ? 1.f : ((valid && HQ == 2) ? __ldg(p.env_per + moff) : 0.f);
+        float* exch = exch_base + set * (2 * 8 * IT_XP);
+        float* carry_in = carry_base + set * (2 * 6 * 128);
+        float* carry_out = carry_base + (set ^ 1) * (2 * 6 * 128);
+        uint32_t n_in = 0, n_out = 0;              // carried-state hand-offs received / sent
+        int pp = 0;                                // exchange buffer
+        InvStrip ahead = strip;
+        int64_t sig_n, c0_n;
+        int ncols_n, skip_n;
+        bool fresh_n;
+        bool more = ahead.next(sig_n, c0_n, ncols_n, skip_n, fresh_n);
         for (int n = 0; strip.next(sig, c0, ncols, skip, fresh); ++n) {
-            const int buf = n & 1;
+            more = ahead.next(sig_n, c0_n, ncols_n, skip_n, fresh_n);      // tile n + 1
+            if ((n & 1) != set) continue;
+            const int buf = set;
             const float4* rowinfo = rowinfo2 + buf * T_NF;
             const uint32_t kph = (uint32_t)((n >> 1) & 1);
-            if (fresh) c1 = c2 = b1 = d1 = d2 = d3 = 0.f;
-            mbar_wait_relaxed(&ri_full[buf], kph);
-            mbar_wait_relaxed(&tmem_full[buf], kph);
+            if (q == 0) T_STAMP(3, n, 0);
+            T_WAITED(0, mbar_wait_relaxed(&ri_full[buf], kph));
+            T_WAITED(1, mbar_wait_relaxed(&tmem_full[buf], kph));
             tcgen05_fence_after();
+            if (q == 0) T_STAMP(3, n, 1);
             const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * T_NF);
+            if (more && !fresh_n) {
+                // ---- the next tile continues this signal (this one is full): the values its
+                //      first hop blocks need from this tile's last R - 1 frames go out first ----
+                uint32_t A[4][8];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) tmem_ld8_nowait(tq + (uint32_t)(a * T_NF + T_NF - 8), A[a]);
+                tmem_ld_wait();
+                float va[3], vb[3], vc[3], vd[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    it_frame_values(A[0][5 + j], A[1][5 + j], A[2][5 + j], A[3][5 + j],
+                                    rowinfo[T_NF - 3 + j], valid, t0, sgn, wn, p.basis_scale_inv, p.wq,
+                                    p.w3q, va[j], vb[j], vc[j], vd[j]);
+                T_WAITED(2, mbar_wait_relaxed(&carry_empty[set ^ 1], (n_out & 1) ^ 1));
+                float* co = carry_out + (int)kph * (6 * 128) + nn;
+                co[0 * 128] = vc[2];               // c(v-1)
+                co[1 * 128] = vc[1];               // c(v-2)
+                co[2 * 128] = vb[2];               // b(v-1)
+                co[3 * 128] = vd[2];               // d(v-1)
+                co[4 * 128] = vd[1];               // d(v-2)
+                co[5 * 128] = vd[0];               // d(v-3)
+                ++n_out;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&carry_full[set ^ 1]);
+            }
+            float c1 = 0.f, c2 = 0.f, b1 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;   // previous frames' values
+            if (!fresh) {
+                T_WAITED(2, mbar_wait_relaxed(&carry_full[set], n_in & 1));
+                ++n_in;
+                const float* ci = carry_in + (int)(((n - 1) >> 1) & 1) * (6 * 128) + nn;
+                c1 = ci[0 * 128]; c2 = ci[1 * 128]; b1 = ci[2 * 128];
+                d1 = ci[3 * 128]; d2 = ci[4 * 128]; d3 = ci[5 * 128];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&carry_empty[set]);
+            }
+            float* ys = p.y + sig * p.out_len;
+            const int64_t ibase = c0 * H + nn - p.origin;        // output index of (column 0, offset n)
 #pragma unroll 1
             for (int cb = 0; cb < ncols; cb += 8) {
                 uint32_t A[4][8];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) tmem_ld8_nowait(tq + (uint32_t)(a * T_NF + cb), A[a]);
                 tmem_ld_wait();
+                float dv[8], mv[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int col = cb + j;
-                    // columns >= ncols hold stale accumulators: select, do not multiply, them away
-                    const bool live = col < ncols && valid;
-                    const float4 ri = rowinfo[min(col, T_NF - 1)];   // scale, 2 pacc, 2 racc, nyquist term
-                    const float g0 = p.basis_scale_inv * pow2_inv(ri.x);
-                    const float ce = live ? __uint_as_float(A[0][j]) * g0 : 0.f;
-                    const float co = live ? __uint_as_float(A[1][j]) * g0 : 0.f;
-                    const float se = live ? __uint_as_float(A[2][j]) * g0 : 0.f;
-                    const float so = live ? __uint_as_float(A[3][j]) * g0 : 0.f;
-                    const float ny = live ? sgn * ri.w : 0.f;
-                    const float cp = ce + co, cm = ce - co, sp = se + so, sm = se - so;
-                    const float a = ((cp - sp) + ny) * wn.x;
-                    float b = ((cm + sm) + ny) * wn.y;
-                    const float c = ((cm - sm) + ny) * wn.z;
-                    float d = ((cp + sp) + ny) * wn.w;
-                    // thread 0: f[Q], f[3Q] (Q is even: the Nyquist term enters with +1); selects,
-                    // not a branch, inside the unrolled columns
-                    const float fq = live ? (ri.y - ri.z + ri.w) * p.wq : 0.f;
-                    const float f3q = live ? (ri.y + ri.z + ri.w) * p.w3q : 0.f;
-                    b = t0 ? fq : b;
-                    d = t0 ? f3q : d;
-                    float dv, mv;
+                    float a, b, c, d;
+                    it_frame_values(A[0][j], A[1][j], A[2][j], A[3][j], rowinfo[min(col, T_NF - 1)],
+                                    col < ncols && valid, t0, sgn, wn, p.basis_scale_inv, p.wq, p.w3q,
+                                    a, b, c, d);
                     if (HQ == 1) {
-                        dv = a + c2; mv = b1 + d3;
+                        dv[j] = a + c2; mv[j] = b1 + d3;
                         c2 = c1; c1 = c; d3 = d2; d2 = d1; d1 = d; b1 = b;
                     } else {
-                        dv = a + c1; mv = b + d1;
+                        dv[j] = a + c1; mv[j] = b + d1;
                         c1 = c; d1 = d;
                     }
-                    if (col < ncols && valid) {
-                        outD[col * pitch + nn] = dv;
-                        outM[col * pitch + moff] = mv;
+                }
+                if (cb + 8 >= ncols) {
+                    // last read of this tile's accumulators and row info: hand both back
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&tmem_empty[buf]);
+                        mbar_arrive(&scale_empty[buf]);
                     }
                 }
-            }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&tmem_empty[buf]);
-                mbar_arrive(&scale_empty[buf]);
-            }
-            named_bar_sync(3, IT_EPI_WARPS * 32);
-            // ---- copy-out: finished hop blocks, * 1 / envelope, centre trim ---------------
-            {
-                float* ys = p.y + sig * p.out_len;
-                for (int r = skip + q; r < ncols; r += IT_EPI_WARPS) {
-                    const int64_t u = c0 + r;
-                    const float* srcD = outD + r * pitch;
-                    const float* srcM = outM + r * pitch;
-                    const int64_t i0 = u * H - p.origin;
-                    const bool use_reg = p.no_env || (u >= R - 1 && u <= p.n_frames - 1);
-                    const int lo = i0 < 0 ? (int)min((int64_t)H, -i0) : 0;
-                    const int hi = (int)max((int64_t)0, min((int64_t)H, p.out_len - i0));
-                    float* yrow = ys + i0;             // dereferenced inside [lo, hi) only
+                if (HQ == 1) {
+                    float* xb = exch + pp * (8 * IT_XP);
+                    pp ^= 1;
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) xb[j * IT_XP + moff] = mv[j];
+                    }
+                    named_bar_sync(3 + set, IT_EPI_SET_WARPS * 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int off = lane + 32 * j;
-                        if (off >= lo && off < hi) {
-                            float v = HQ == 1 ? srcD[off] + srcM[off] : srcD[off];
-                            float e = env_reg[j];
-                            if (!use_reg) {
-                                // edge hop blocks see fewer than R frames: overlap-added w^2 on the fly
-                                float acc = 0.f;
-                                const int64_t t_lo = max((int64_t)0, u - (R - 1));
-                                const int64_t t_hi = min(u, p.n_frames - 1);
-                                for (int64_t t = t_lo; t <= t_hi; ++t)
-                                    acc += __ldg(p.wsq + (int)(u - t) * H + off);
-                                e = 1.f / acc;
-                            }
-                            yrow[off] = v * e;
+                        const int col = cb + j;
+                        const int64_t u = c0 + col;
+                        const int64_t i = ibase + (int64_t)col * H;
+                        if (col >= skip && col < ncols && valid && i >= 0 && i < p.out_len) {
+                            const float v = dv[j] + xb[j * IT_XP + nn];
+                            const bool interior = p.no_env || (u >= R - 1 && u <= p.n_frames - 1);
+                            ys[i] = v * (interior ? env_n
+                                                  : it_edge_envelope(p.env_per, p.wsq, N, H, p.n_frames, u, nn));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = cb + j;
+                        const int64_t u = c0 + col;
+                        const int64_t i = ibase + (int64_t)col * H;
+                        const int64_t im = i + (moff - nn);
+                        if (col >= skip && col < ncols && valid) {
+                            const bool interior = p.no_env || (u >= R - 1 && u <= p.n_frames - 1);
+                            if (i >= 0 && i < p.out_len)
+                                ys[i] = dv[j] * (interior ? env_n
+                                                          : it_edge_envelope(p.env_per, p.wsq, N, H, p.n_frames, u, nn));
+                            if (im >= 0 && im < p.out_len)
+                                ys[im] = mv[j] * (interior ? env_m
+                                                           : it_edge_envelope(p.env_per, p.wsq, N, H, p.n_frames, u, moff));
                         }
                     }
                 }
             }
-            named_bar_sync(3, IT_EPI_WARPS * 32);      // rows are rewritten by the next tile
+            if (q == 0) T_STAMP(3, n, 2);
+            if (q == 0) T_WAIT_FLUSH(3);
         }
     } else if (warp < IT_SCOUT_WARP0) {
         // ===================== builders ========================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        T_WAIT_DECL;
         const int bw = warp - IT_BUILD_WARP0;      // 0..7
         const int bt = bw * 32 + lane;             // 0..255
         int g = 0;
@@ -750,7 +909,9 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 float4* rowinfo = rowinfo2 + slot * T_NF;
                 const bool live = row < ncols && c0 + row < p.n_frames;
                 const float2* xr = p.spec + sig * p.ss + (c0 + (live ? row : 0)) * p.sf;
-                mbar_wait(&scale_full[slot], (uint32_t)((n >> 1) & 1));
+                if (bw == 0) T_STAMP(1, n, 0);
+                T_WAITED(0, mbar_wait_relaxed(&scale_full[slot], (uint32_t)((n >> 1) & 1), 20));
+                if (bw == 0) T_STAMP(1, n, 1);
                 const float sc = live ? rowinfo[row].x : 0.f;
                 float pacc = 0.f, racc = 0.f;
                 for (int kc = 0; kc < n_kc; ++kc) {
@@ -775,7 +936,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                     for (int pair = 0; pair < 2; ++pair, ++g) {
                         const int s = g % T_STAGES;
                         const uint32_t ph = (g / T_STAGES) & 1;
-                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        T_WAITED(2, mbar_wait_relaxed(&empty_bar[s], ph ^ 1, 20));
                         uint8_t* sa = stages + (size_t)s * T_STAGE_BYTES + T_STAGE_BASIS + row * (BK * 2);
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {          // sub-GEMM: even / odd bins
@@ -800,7 +961,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         if (pair == 1 && kc == n_kc - 1) {
                             scratch[kq * T_NF + row] = pacc;
                             scratch[4 * T_NF + kq * T_NF + row] = racc;
-                            named_bar_sync(1, IT_BUILD_THREADS);
+                            T_WAITED(3, named_bar_sync(1, IT_BUILD_THREADS));
                             if (kq == 0) {
                                 rowinfo[row].y = 2.f * ((scratch[row] + scratch[T_NF + row]) +
                                                         (scratch[2 * T_NF + row] + scratch[3 * T_NF + row]));
@@ -813,8 +974,10 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         if (lane == 0) mbar_arrive(&full_bar[s]);
                     }
                 }
-                named_bar_sync(1, IT_BUILD_THREADS);       // scratch is rewritten by the next tile
+                T_WAITED(3, named_bar_sync(1, IT_BUILD_THREADS));       // scratch is rewritten by the next tile
                 if (lane == 0) mbar_arrive(&ri_full[slot]);
+                if (bw == 0) T_STAMP(1, n, 2);
+                if (bw == 0) T_WAIT_FLUSH(1);
             }
         } else {
             // lanes along bins: a warp owns 8 frames; lane = (one of two frames, 4 bins)
@@ -834,114 +997,127 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         dst[i][e] = live ? __ldg(xr + e) : make_float2(0.f, 0.f);      // sb == 1
                 }
             };
-            float2 cur[RI][4], nxt[RI][4];
+            float pacc[RI], racc[RI], rscale[RI];
+            float4* rowinfo = rowinfo2;
+            // one k-chunk: scale, split, store both sub-GEMM pairs
+            auto convert = [&](float2 (&cur)[RI][4], int kc) {
+                const int m0 = kc * BK + 2 * pr;   // bins 2 m0 .. 2 m0 + 3
+                const bool dc = m0 == 0;
+                const float dc_mul = dc ? p.dc_gain : 1.f, dc_half = dc ? 0.5f : 0.f;
+#pragma unroll
+                for (int i = 0; i < RI; ++i) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        cur[i][e] = prep_bin<DECOMP>(cur[i][e], p.pre_scale, p.pre_expo);
+                    cur[i][0].y = dc ? 0.f : cur[i][0].y;      // Im X[0] is ignored by the c2r inverse
+                    cur[i][0].x *= dc_mul;
+                    pacc[i] += cur[i][0].x - cur[i][2].x;
+                    racc[i] += cur[i][1].y - cur[i][3].y;
+                    pacc[i] -= dc_half * cur[i][0].x;
+                }
+#pragma unroll
+                for (int pair = 0; pair < 2; ++pair, ++g) {
+                    const int s = g % T_STAGES;
+                    const uint32_t ph = (g / T_STAGES) & 1;
+                    T_WAITED(2, mbar_wait_relaxed(&empty_bar[s], ph ^ 1, 20));
+                    uint8_t* sa = stages + (size_t)s * T_STAGE_BYTES + T_STAGE_BASIS;
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) {
+                        const int row = bw * (2 * RI) + 2 * i + half;
+                        const float sc = rscale[i];
+                        uint8_t* dst = sa + row * (BK * 2) +
+                                       ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
+                        if (pair == 0) {
+                            split_store(dst, dst + T_DATA_TILE, cur[i][0].x * sc, cur[i][2].x * sc);
+                            split_store(dst + 2 * T_DATA_TILE, dst + 3 * T_DATA_TILE, cur[i][1].x * sc,
+                                        cur[i][3].x * sc);
+                        } else {
+                            split_store(dst, dst + T_DATA_TILE, cur[i][0].y * sc, cur[i][2].y * sc);
+                            split_store(dst + 2 * T_DATA_TILE, dst + 3 * T_DATA_TILE, cur[i][1].y * sc,
+                                        cur[i][3].y * sc);
+                        }
+                    }
+                    if (pair == 1 && kc == n_kc - 1) {
+                        // rank-1 sums must be visible before the tile's last stage is released
+#pragma unroll
+                        for (int i = 0; i < RI; ++i) {
+                            float a = pacc[i], b = racc[i];
+#pragma unroll
+                            for (int o = 8; o; o >>= 1) {
+                                a += __shfl_xor_sync(0xffffffffu, a, o);
+                                b += __shfl_xor_sync(0xffffffffu, b, o);
+                            }
+                            const int row = bw * (2 * RI) + 2 * i + half;
+                            if (pr == 0) {
+                                rowinfo[row].y = 2.f * a;
+                                rowinfo[row].z = 2.f * b;
+                            }
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);
+                }
+            };
+            float2 bufa[RI][4], bufb[RI][4];
+            const bool even_kc = (n_kc & 1) == 0;  // buffers then alternate cleanly across tiles
             InvStrip ahead = strip;                // runs one tile ahead (prefetch of its first k-chunk)
             int64_t sig_n, c0_n;
             int ncols_n, skip_n;
             bool fresh_n;
             bool more = ahead.next(sig_n, c0_n, ncols_n, skip_n, fresh_n);
-            if (more) load_chunk(cur, sig_n, c0_n, ncols_n, 0);
+            if (more && even_kc) load_chunk(bufa, sig_n, c0_n, ncols_n, 0);
             for (int n = 0; strip.next(sig, c0, ncols, skip, fresh); ++n) {
                 const int slot = n & 1;
-                float4* rowinfo = rowinfo2 + slot * T_NF;
+                rowinfo = rowinfo2 + slot * T_NF;
                 more = ahead.next(sig_n, c0_n, ncols_n, skip_n, fresh_n);
-                mbar_wait(&scale_full[slot], (uint32_t)((n >> 1) & 1));
-                float pacc[RI], racc[RI], rscale[RI];
+                if (!even_kc) load_chunk(bufa, sig, c0, ncols, 0);
+                if (bw == 0) T_STAMP(1, n, 0);
+                T_WAITED(0, mbar_wait_relaxed(&scale_full[slot], (uint32_t)((n >> 1) & 1), 20));
+                if (bw == 0) T_STAMP(1, n, 1);
 #pragma unroll
                 for (int i = 0; i < RI; ++i) {
                     pacc[i] = racc[i] = 0.f;
                     const int row = bw * (2 * RI) + 2 * i + half;
                     rscale[i] = (row < ncols && c0 + row < p.n_frames) ? rowinfo[row].x : 0.f;
                 }
-                for (int kc = 0; kc < n_kc; ++kc) {
-                    // the next chunk's loads (of this tile, or the first of the next tile) fly
-                    // while this one is converted
-                    if (kc + 1 < n_kc) load_chunk(nxt, sig, c0, ncols, kc + 1);
-                    else if (more) load_chunk(nxt, sig_n, c0_n, ncols_n, 0);
-                    const int m0 = kc * BK + 2 * pr;   // bins 2 m0 .. 2 m0 + 3
-                    const bool dc = m0 == 0;
-                    const float dc_mul = dc ? p.dc_gain : 1.f, dc_half = dc ? 0.5f : 0.f;
-#pragma unroll
-                    for (int i = 0; i < RI; ++i) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            cur[i][e] = prep_bin<DECOMP>(cur[i][e], p.pre_scale, p.pre_expo);
-                        cur[i][0].y = dc ? 0.f : cur[i][0].y;      // Im X[0] is ignored by the c2r inverse
-                        cur[i][0].x *= dc_mul;
-                        pacc[i] += cur[i][0].x - cur[i][2].x;
-                        racc[i] += cur[i][1].y - cur[i][3].y;
-                        pacc[i] -= dc_half * cur[i][0].x;
+                for (int kc = 0; kc < n_kc; kc += 2) {
+                    // buffer a holds k-chunk kc; the loads of the chunk after it (of this tile, or the
+                    // first of the next tile) fly while it is converted
+                    if (kc + 1 < n_kc) load_chunk(bufb, sig, c0, ncols, kc + 1);
+                    convert(bufa, kc);
+                    if (kc + 1 < n_kc) {
+                        if (kc + 2 < n_kc) load_chunk(bufa, sig, c0, ncols, kc + 2);
+                        else if (more) load_chunk(bufa, sig_n, c0_n, ncols_n, 0);
+                        convert(bufb, kc + 1);
                     }
-#pragma unroll
-                    for (int pair = 0; pair < 2; ++pair, ++g) {
-                        const int s = g % T_STAGES;
-                        const uint32_t ph = (g / T_STAGES) & 1;
-                        mbar_wait(&empty_bar[s], ph ^ 1);
-                        uint8_t* sa = stages + (size_t)s * T_STAGE_BYTES + T_STAGE_BASIS;
-#pragma unroll
-                        for (int i = 0; i < RI; ++i) {
-                            const int row = bw * (2 * RI) + 2 * i + half;
-                            const float sc = rscale[i];
-                            uint8_t* dst = sa + row * (BK * 2) +
-                                           ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
-                            if (pair == 0) {
-                                split_store(dst, dst + T_DATA_TILE, cur[i][0].x * sc, cur[i][2].x * sc);
-                                split_store(dst + 2 * T_DATA_TILE, dst + 3 * T_DATA_TILE, cur[i][1].x * sc,
-                                            cur[i][3].x * sc);
-                            } else {
-                                split_store(dst, dst + T_DATA_TILE, cur[i][0].y * sc, cur[i][2].y * sc);
-                                split_store(dst + 2 * T_DATA_TILE, dst + 3 * T_DATA_TILE, cur[i][1].y * sc,
-                                            cur[i][3].y * sc);
-                            }
-                        }
-                        if (pair == 1 && kc == n_kc - 1) {
-                            // rank-1 sums must be visible before the tile's last stage is released
-#pragma unroll
-                            for (int i = 0; i < RI; ++i) {
-                                float a = pacc[i], b = racc[i];
-#pragma unroll
-                                for (int o = 8; o; o >>= 1) {
-                                    a += __shfl_xor_sync(0xffffffffu, a, o);
-                                    b += __shfl_xor_sync(0xffffffffu, b, o);
-                                }
-                                const int row = bw * (2 * RI) + 2 * i + half;
-                                if (pr == 0) {
-                                    rowinfo[row].y = 2.f * a;
-                                    rowinfo[row].z = 2.f * b;
-                                }
-                            }
-                        }
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&full_bar[s]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < RI; ++i)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) cur[i][e] = nxt[i][e];
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ri_full[slot]);
+                if (bw == 0) T_STAMP(1, n, 2);
+                if (bw == 0) T_WAIT_FLUSH(1);
             }
         }
     } else {
         // ===================== scouts: frame maxima of the next tile ==================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        T_WAIT_DECL;
         const int sw = warp - IT_SCOUT_WARP0;      // 0..7
         for (int n = 0; strip.next(sig, c0, ncols, skip, fresh); ++n) {
             const int slot = n & 1;
             float4* ri = rowinfo2 + slot * T_NF;
             const float2* xs = p.spec + sig * p.ss;
-            mbar_wait_relaxed(&scale_empty[slot], (uint32_t)(((n >> 1) & 1) ^ 1));
+            if (sw == 0) T_STAMP(0, n, 0);
+            T_WAITED(0, mbar_wait_relaxed(&scale_empty[slot], (uint32_t)(((n >> 1) & 1) ^ 1)));
+            if (sw == 0) T_STAMP(0, n, 1);
             if (FRAMES_FAST) {
-                // thread = (frame, quarter of the bins); lanes along frames
+                // thread = (frame, quarter of the 16-bin groups); lanes along frames
                 const int st = sw * 32 + lane;
-                const int row = st & (T_NF - 1), kq = st >> 6;
+                const int row = st & (T_NF - 1), part = st >> 6;       // part 0..3
                 const bool live = row < ncols && c0 + row < p.n_frames;
                 const float2* col = xs + (c0 + (live ? row : 0)) * p.sf;
                 float m = 0.f;
-                const int nb = Q / 2;              // bins per quarter (2Q bins below the Nyquist bin)
-                for (int b0 = kq * nb; b0 < (kq + 1) * nb; b0 += 16) {
+                for (int b0 = 16 * part; b0 < 2 * Q; b0 += 64) {
                     float2 v[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
@@ -953,18 +1129,17 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 }
                 // scratch rows 8.. are the scouts' (the builders use rows 0..7)
                 float* sc = scratch + 8 * T_NF;
-                sc[kq * T_NF + row] = m;
-                named_bar_sync(2, IT_SCOUT_THREADS);
-                if (kq == 0) {
+                sc[part * T_NF + row] = m;
+                T_WAITED(1, named_bar_sync(2, IT_SCOUT_THREADS));
+                if (part == 0) {
                     float ny = 0.f;
                     if (live)
                         ny = prep_bin<DECOMP>(__ldg(col + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x *
                              p.edge_gain;
-                    const float mm = fmaxf(fmaxf(sc[row], sc[T_NF + row]),
-                                           fmaxf(sc[2 * T_NF + row], sc[3 * T_NF + row]));
+                    const float mm = fmaxf(fmaxf(sc[row], sc[T_NF + row]), fmaxf(sc[2 * T_NF + row], sc[3 * T_NF + row]));
                     ri[row] = make_float4(live ? row_scale(mm) : 1.f, 0.f, 0.f, ny);
                 }
-                named_bar_sync(2, IT_SCOUT_THREADS);
+                T_WAITED(1, named_bar_sync(2, IT_SCOUT_THREADS));
             } else {
                 // warp = frame (bins contiguous), two frames in flight per warp
                 const int nj = Q / 16;             // 32-bin groups below the Nyquist bin
@@ -992,7 +1167,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                             m = fmaxf(m, abs2_finite(prep_bin<DECOMP>(v[r][j], p.pre_scale, p.pre_expo)));
 #pragma unroll
                         for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                        if (lane == 0) {
+                        if (lane == 0 && row < T_NF) {
                             const bool live = row < ncols && c0 + row < p.n_frames;
                             const float ny = prep_bin<DECOMP>(vn[r], p.pre_scale, p.pre_expo).x * p.edge_gain;
                             ri[row] = make_float4(live ? row_scale(m) : 1.f, 0.f, 0.f, live ? ny : 0.f);
@@ -1002,6 +1177,8 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&scale_full[slot]);
+            if (sw == 0) T_STAMP(0, n, 2);
+            if (sw == 0) T_WAIT_FLUSH(0);
         }
     }
     tcgen05_fence_before();

@@ -61,6 +61,9 @@ extern "C" int brv_debug_phase_times(unsigned long long* out, int n) {
 #else
 #define BRV_STAMP(i) do {} while (0)
 #endif
+#ifdef BRV_PHASE_TIMING
+extern "C" int brv_debug_t_times(unsigned long long* out, int n);
+#endif
 
 namespace {
 
@@ -2112,7 +2115,7 @@ static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool c
             prm.rows = nf;
             prm.tiles_per_signal = 0;
             prm.total_tiles = n_sig * n_frames;              // columns (frames), not tiles
-            BRV_REQUIRE(prm.total_tiles < (1LL << 40), "too many frames (%lld)", (long long)prm.total_tiles);
+            BRV_REQUIRE(prm.total_tiles < (1LL << 31), "too many frames (%lld)", (long long)prm.total_tiles);
             const int64_t want = brv_ceil_div(prm.total_tiles, 16);
             const unsigned ctas = (unsigned)(want < fp->sm_count ? want : fp->sm_count);
             if (compress)
@@ -2247,6 +2250,7 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     if ((g_brv_fold_variant == 0 || g_brv_fold_variant == 6) && !fp->odd && (fp->hq == 1 || fp->hq == 2)) {
         // transposed strip kernel: every SM walks the same number of hop blocks in <= 64-column tiles
         prm.total_tiles = n_sig * (int64_t)prm.n_blocks;     // columns (hop blocks), not tiles
+        BRV_REQUIRE(prm.total_tiles < (1LL << 31), "too many hop blocks (%lld)", (long long)prm.total_tiles);
         const int64_t want = brv_ceil_div(prm.total_tiles, 16);
         const unsigned ctas = (unsigned)(want < fp->sm_count ? want : fp->sm_count);
 #define BRV_LAUNCH_INV_T(HQ_, FF_)                                                                \
@@ -2439,3 +2443,12 @@ int brv_fold_conv_backward(const brv_stft_plan* p, const float2* X, int64_t ss, 
     prm.origin = p->frame_length - p->hop;
     return fold_inverse_launch(p, prm, p->compression != 1.0, n_sig, n_frames, out_len, st);
 }
+
+#ifdef BRV_PHASE_TIMING
+extern "C" int brv_debug_t_times(unsigned long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_brv_t_ts, sizeof(unsigned long long) * (n < 160 ? n : 160));
+}
+extern "C" int brv_debug_t_waits(unsigned long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_brv_t_wait, sizeof(unsigned long long) * (n < 32 ? n : 32));
+}
+#endif

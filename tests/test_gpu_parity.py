@@ -664,3 +664,27 @@ def test_apply_mask():
     rx, ry = O.apply_mask(x.numpy(), y.numpy(), lengths.numpy())
     assert np.array_equal(cpu(mx), rx.astype(np.float32))
     assert np.array_equal(cpu(my), ry.astype(np.float32))
+
+
+def test_criterion_workspace_reuse_across_layouts():
+    """A few-pairs / long-rows call leaves partial sums where a later many-pairs call puts its
+    ticket counters (cached workspace): the counters must be re-zeroed, or the last-CTA
+    finalise never runs and the loss is garbage."""
+    from brever_b200 import criterion as C
+    C._workspaces.clear()
+    for crit, port in ((brv.snr, P.snr), (brv.sisnr, P.sisnr)):
+        a_x, a_y = randn((8, 1, 163840), 11), randn((8, 1, 163840), 12)
+        la = torch.full((8,), 163840)
+        first = crit(a_x.to(DEV), a_y.to(DEV), la)
+        assert np.allclose(cpu(first), port(a_x, a_y, la).numpy(), atol=1e-3)
+        b_x, b_y = randn((70, 1, 16000), 13), randn((70, 1, 16000), 14)
+        lb = torch.full((70,), 16000)
+        second = crit(b_x.to(DEV), b_y.to(DEV), lb)
+        assert np.allclose(cpu(second), port(b_x, b_y, lb).numpy(), atol=1e-3)
+        # and back again, then a PIT call with S^2 pairs per item
+        again = crit(a_x.to(DEV), a_y.to(DEV), la)
+        assert torch.equal(first, again)
+    two_x, two_y = randn((32, 2, 8000), 15), randn((32, 2, 8000), 16)
+    lt = torch.full((32,), 8000)
+    pit = brv.sisnr(two_x.to(DEV), two_y.to(DEV), lt)
+    assert np.allclose(cpu(pit), P.sisnr(two_x, two_y, lt).numpy(), atol=1e-3)
