@@ -106,10 +106,10 @@ __device__ __forceinline__ void bulk_g2s_t(void* smem_dst, const void* gsrc, uin
 //   warps 12-19   operand builders: a warp owns 8 frames: per-32-sample maxima of their samples ->
 //                 per-frame power-of-two scales and rank-1 terms (no CTA-wide barrier), then
 //                 window, fold, scale, split from the staged span
-constexpr int FT_THREADS = 640;
+constexpr int FT_THREADS = 896;
 constexpr int FT_LOADER_WARP0 = 2;
 constexpr int FT_EPI_WARP0 = 4, FT_EPI_WARPS = 8;
-constexpr int FT_BUILD_WARP0 = 12, FT_BUILD_WARPS = 8;
+constexpr int FT_BUILD_WARP0 = 12, FT_BUILD_WARPS = 16;
 constexpr int FT_SPAN = (T_NF - 1) * 128 + 512 + 64;        // floats per span buffer (8640)
 constexpr int FT_BMAX = FT_SPAN / 32;                       // 270
 constexpr int FT_OFF_SPAN = T_SMEM_STAGES;
@@ -197,6 +197,9 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
     int64_t sig, t0;
     int ncols;
 
+    // register budget (72 x 896 at launch): control warpgroup 40, epilogue 80, builders 72
+    if (warp < FT_EPI_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         // ===================== TMA producer: basis k-chunks =====================
         if (elect_one()) {
@@ -208,6 +211,10 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                     const uint32_t ph = (g / T_STAGES) & 1;
                     const int kc = it >> 1, pair = it & 1;
                     T_WAITED(0, mbar_wait_relaxed(&empty_bar[s], ph ^ 1));
+#ifdef BRV_T_NO_TMA                                     // dev experiment: timing without the basis stream
+                    mbar_arrive(&full_bar[s]);
+                    (void)kc; (void)pair;
+#else
                     mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
                     uint8_t* sb = stages + (size_t)s * T_STAGE_BYTES;
 #pragma unroll
@@ -216,6 +223,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                         for (int pl = 0; pl < 2; ++pl)
                             tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
                                         &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
+#endif
                     T_WAIT_FLUSH(4);
                 }
         }
@@ -249,9 +257,15 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                             const uint64_t bl = umma_desc_sw64(a0 + (j * 2 + 1) * SUB_TILE + off);
                             const uint64_t dh = umma_desc_sw64(b0 + (j * 2) * T_DATA_TILE + off);
                             const uint64_t dl = umma_desc_sw64(b0 + (j * 2 + 1) * T_DATA_TILE + off);
+#ifndef BRV_T_NO_MMA                                    // dev experiments: MMA count
                             umma_f16(d, bh, dh, idesc, (kc | ks) != 0);
+#ifndef BRV_T_ONE_PRODUCT
                             umma_f16(d, bh, dl, idesc, 1);
                             umma_f16(d, bl, dh, idesc, 1);
+#endif
+#else
+                            (void)d; (void)bh; (void)bl; (void)dh; (void)dl; (void)idesc;
+#endif
                         }
                     }
                     umma_commit(&empty_bar[s]);
@@ -310,10 +324,10 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
             T_STAMP(0, n, 2);
             T_WAIT_FLUSH(0);
         }
-    } else if (warp < FT_EPI_WARP0) {
-        // (warp 3 idles)
+    }                                                  // (warp 3 idles)
     } else if (warp < FT_BUILD_WARP0) {
         // ===================== epilogue ========================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
         T_WAIT_DECL;
         const int e = warp - FT_EPI_WARP0;         // 0..7
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -338,19 +352,22 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
             float* obase = p.out + ((sig * p.n_frames + t0) * (int64_t)pitch + 4 * m);
             const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * T_NF);
 #pragma unroll 1
-            for (int cb = 0; cb < 32; cb += 16) {
+            for (int cb = 0; cb < 32; cb += 8) {
                 const int c0 = chalf * 32 + cb;
+#ifdef BRV_T_NO_EPI                                     // dev experiment: timing without the epilogue stores
+                if (p.n_fft > 0) break;
+#endif
                 if (c0 >= ncols) break;
-                uint32_t r0[16], r1[16], r2[16], r3[16];
-                tmem_ld16_nowait(tq + (uint32_t)(c0), r0);              // Re X[2m]
-                tmem_ld16_nowait(tq + (uint32_t)(T_NF + c0), r1);       // Re X[2m+1]
-                tmem_ld16_nowait(tq + (uint32_t)(2 * T_NF + c0), r2);   // Im X[2m]
-                tmem_ld16_nowait(tq + (uint32_t)(3 * T_NF + c0), r3);   // Im X[2m+1]
+                uint32_t r0[8], r1[8], r2[8], r3[8];
+                tmem_ld8_nowait(tq + (uint32_t)(c0), r0);              // Re X[2m]
+                tmem_ld8_nowait(tq + (uint32_t)(T_NF + c0), r1);       // Re X[2m+1]
+                tmem_ld8_nowait(tq + (uint32_t)(2 * T_NF + c0), r2);   // Im X[2m]
+                tmem_ld8_nowait(tq + (uint32_t)(3 * T_NF + c0), r3);   // Im X[2m+1]
                 float* o0 = obase + (int64_t)c0 * pitch;
                 const bool a0 = (reinterpret_cast<uintptr_t>(o0) & 15) == 0;    // c0 is even
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     if (c0 + j < ncols && valid) {
                         const float4 ri = rowinfo[c0 + j];         // scale, nyquist sum, ee[Q], oo[Q]
                         const float g0 = gb * pow2_inv(ri.x);
@@ -394,13 +411,13 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
     } else {
         // ===================== builders ========================================
         T_WAIT_DECL;
-        const int bw = warp - FT_BUILD_WARP0;      // 0..7
+        const int bw = warp - FT_BUILD_WARP0;      // 0..15
         const int half = lane >> 4;                // which of the warp's two rows per pass
         const int pr = lane & 15;                  // n pair inside the 32-wide k-chunk
         const uint32_t chunk = (uint32_t)(pr >> 2);
         const int shift = p.shift;
-        constexpr int RI = T_NF / FT_BUILD_WARPS / 2;     // row pairs per warp (4)
-        constexpr int ROWS_W = 2 * RI;                    // rows per warp (8)
+        constexpr int RI = T_NF / FT_BUILD_WARPS / 2;     // row pairs per warp (2)
+        constexpr int ROWS_W = 2 * RI;                    // rows per warp (4)
         int g = 0;
         for (int n = 0; strip.next(sig, t0, ncols); ++n) {
             const int b = n & 1;
@@ -477,6 +494,9 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                     const uint32_t ph = (g / T_STAGES) & 1;
                     T_WAITED(2, mbar_wait_relaxed(&empty_bar[s], ph ^ 1, 20));
                     uint8_t* sa = stages + (size_t)s * T_STAGE_BYTES + T_STAGE_BASIS;
+#ifdef BRV_T_NO_BUILD                                   // dev experiment: timing without the operand build
+                    if (p.n_fft < 0)
+#endif
 #pragma unroll
                     for (int i = 0; i < RI; ++i) {
                         const int row = bw * ROWS_W + 2 * i + half;

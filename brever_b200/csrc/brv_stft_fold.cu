@@ -964,6 +964,30 @@ struct FoldInvParams {
     uintptr_t spec_lo, spec_hi;
 };
 
+// The hop blocks of all signals are cut into one contiguous strip per CTA (CTA c of P owns the
+// global columns [c G / P, (c+1) G / P)), walked in tiles of <= 128 frames that never cross a
+// signal: every SM gets the same number of frames (256 fixed tiles on 148 SMs ran as 2 + 1).
+// A tile that starts inside a signal recomputes the `halo` frames before it (`skip` rows whose
+// hop blocks belong to the previous tile).
+struct TileStrip {
+    uint32_t g, g1, per_signal;
+    int halo;
+    __device__ TileStrip(int64_t total, int64_t per_signal_, int halo_, int cta, int ctas)
+        : g((uint32_t)(total * cta / ctas)), g1((uint32_t)(total * (cta + 1) / ctas)),
+          per_signal((uint32_t)per_signal_), halo(halo_) {}
+    __device__ __forceinline__ bool next(int64_t& sig, int64_t& t0, int& ncols, int& skip) {
+        if (g >= g1) return false;
+        const uint32_t s = g / per_signal, v = g - s * per_signal;
+        sig = s;
+        skip = (int)min((uint32_t)halo, v);
+        t0 = v - skip;
+        const uint32_t m = min((uint32_t)TILE_M, min(per_signal - (v - skip), g1 - g + skip));
+        ncols = (int)m;
+        g += m - skip;
+        return true;
+    }
+};
+
 template <bool DECOMP>
 __device__ __forceinline__ float2 prep_bin(float2 c, float pre_scale, float pre_expo) {
     c.x *= pre_scale;
@@ -1055,6 +1079,10 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
+    TileStrip strip(p.total_tiles, p.n_blocks, p.halo, (int)blockIdx.x, (int)gridDim.x);
+    int64_t sig, t0;
+    int ncols, skip;
+
     if (warp < INV_FIRST_BUILDER) {
     // ---- control + scout warpgroups: give registers back to the builders ----
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -1063,7 +1091,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
         if (elect_one()) {
             int g = 0;
             int n = 0;
-            for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
+            for (; strip.next(sig, t0, ncols, skip); ++n) {
                 if (n > 0) mbar_wait_relaxed(&region_free, (uint32_t)((n - 1) & 1));
                 for (int it = 0; it < n_it; ++it, ++g) {
                     const int s = g % STAGES;
@@ -1086,7 +1114,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_f16(TILE_M, Q);
             int g = 0;
-            for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x) {
+            while (strip.next(sig, t0, ncols, skip)) {
                 for (int it = 0; it < n_it; ++it, ++g) {
                     const int s = g % STAGES;
                     const uint32_t ph = (g / STAGES) & 1;
@@ -1120,7 +1148,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
         const int sw = warp - 4;                   // 0..3
         const int st = sw * 32 + lane;             // 0..127
         int n = 0;
-        for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
+        for (; strip.next(sig, t0, ncols, skip); ++n) {
             const int slot = n & 1;
             mbar_wait_relaxed(&scale_empty[slot], (uint32_t)(((n >> 1) & 1) ^ 1));
             if (n == 0) {
@@ -1132,9 +1160,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                 continue;
             }
             float4* ri = rowinfo2 + slot * TILE_M;
-            const int64_t sig = tile_id / p.tiles_per_signal;
-            const int64_t t0 = (int64_t)(tile_id % p.tiles_per_signal) * p.adv;
-            const int rows_eff = (int)max((int64_t)0, min((int64_t)TILE_M, p.n_frames - t0));
+            const int rows_eff = (int)max((int64_t)0, min((int64_t)ncols, p.n_frames - t0));
             const float2* xs = p.spec + sig * p.ss;
             if (FRAMES_FAST) {
                 // thread = frame; chunk = 16 bins x 128 frames; a thread scans only what it
@@ -1385,13 +1411,10 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
             env_reg[j] = p.no_env ? 1.f : (lane + 32 * j < H ? __ldg(p.env_per + lane + 32 * j) : 0.f);
 
         int g = 0, n = 0;
-        for (int64_t tile_id = blockIdx.x; tile_id < p.total_tiles; tile_id += gridDim.x, ++n) {
+        for (; strip.next(sig, t0, ncols, skip); ++n) {
             const int slot = n & 1;
             float4* rowinfo = rowinfo2 + slot * TILE_M;
-            const int64_t sig = tile_id / p.tiles_per_signal;
-            const int tile = (int)(tile_id % p.tiles_per_signal);
-            const int64_t t0 = (int64_t)tile * p.adv;
-            const int rows_eff = (int)max((int64_t)0, min((int64_t)TILE_M, p.n_frames - t0));
+            const int rows_eff = (int)max((int64_t)0, min((int64_t)ncols, p.n_frames - t0));
             const float2* xs = p.spec + sig * p.ss;
             BRV_STAMP(n * 8 + 0);
             mbar_wait(&scale_full[slot], (uint32_t)((n >> 1) & 1));
@@ -1752,11 +1775,9 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
 
             // ---- copy-out: finished hop blocks, * 1 / envelope, centre trim ---------------
             {
-                const int r_lo = tile == 0 ? 0 : p.halo;
                 float* ys = p.y + sig * p.out_len;
-                for (int r = r_lo + bw; r < TILE_M; r += BUILDERS) {
+                for (int r = skip + bw; r < ncols; r += BUILDERS) {
                     const int64_t u = t0 + r;
-                    if (u >= p.n_blocks) break;
                     const float* src = orow + r * pitch;
                     const int qq = r >> 5, lr = r & 31;
                     const float* sp = (qq > 0 && lr < p.halo) ? spill + (qq * 3 + lr) * H : nullptr;
@@ -2269,7 +2290,11 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
         BRV_LAUNCH_CHECK("istft_t_kernel");
         return BRV_OK;
     }
-    const unsigned grid = (unsigned)(prm.total_tiles < fp->sm_count ? prm.total_tiles : fp->sm_count);
+    // one strip of hop blocks per CTA (TileStrip): at least 32 columns each
+    prm.total_tiles = n_sig * (int64_t)prm.n_blocks;         // columns (hop blocks), not tiles
+    BRV_REQUIRE(prm.total_tiles < (1LL << 31), "too many hop blocks (%lld)", (long long)prm.total_tiles);
+    const int64_t want_ctas = brv_ceil_div(prm.total_tiles, 32);
+    const unsigned grid = (unsigned)(want_ctas < fp->sm_count ? want_ctas : fp->sm_count);
     {   // the bytes the (signal, frame, bin) view itself covers: bulk row copies stay inside them
         const int64_t f_in = p->n_fft / 2 + 1;
         // (16 KB chunks only: with the 8 KB chunks of n_fft = 256 three copies in flight do not

@@ -9,3 +9,5 @@ grep -c "ok " gpurun_out/t_fwd.log gpurun_out/t_inv.log; grep -h "BAD\|Error\|er
 cat gpurun_out/t_bench.log | tail -12
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_t.log 2>&1; echo "pytest rc $?"
 tail -5 gpurun_out/pytest_t.log
+BRV_TC_VARIANT=4 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_v4.log 2>&1; echo "pytest (variant 4) rc $?"
+tail -3 gpurun_out/pytest_v4.log
