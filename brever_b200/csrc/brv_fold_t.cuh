@@ -220,9 +220,10 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
-                        for (int pl = 0; pl < 2; ++pl)
+                        for (int pl = 0; pl < 2; ++pl) {
                             tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
                                         &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
+                        }
 #endif
                     T_WAIT_FLUSH(4);
                 }

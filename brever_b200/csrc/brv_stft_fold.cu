@@ -939,6 +939,8 @@ struct FoldInvParams {
     float pre_scale, pre_expo;   // 1 / scale_factor, 1 / c - 1
     float* y;                    // (sig, out_len)
     int64_t out_len;
+    int64_t total_cols;          // n_signals * n_blocks (strip scheduling)
+    int strips;                  // one strip of hop blocks per CTA instead of fixed tiles
     const float* env_per;        // hop: 1 / overlap-added w^2 of interior hop blocks (periodic)
     const float* wsq;            // n_fft: squared window (edge hop blocks are summed on the fly)
     int no_env;                  // gradient / ConvSTFT use: no division by the envelope
@@ -972,10 +974,27 @@ struct FoldInvParams {
 struct TileStrip {
     uint32_t g, g1, per_signal;
     int halo;
-    __device__ TileStrip(int64_t total, int64_t per_signal_, int halo_, int cta, int ctas)
+    // fixed tiling (small launches: measured faster there): tile ids cta, cta + ctas, ... of
+    // `tiles_per_signal` tiles of TILE_M - halo new columns each
+    uint32_t tile_id, n_tiles, stride;
+    int tiles_per_signal;
+    __device__ TileStrip(int64_t total, int64_t per_signal_, int halo_, int tiles_per_signal_, int64_t n_tiles_,
+                         int cta, int ctas)
         : g((uint32_t)(total * cta / ctas)), g1((uint32_t)(total * (cta + 1) / ctas)),
-          per_signal((uint32_t)per_signal_), halo(halo_) {}
+          per_signal((uint32_t)per_signal_), halo(halo_), tile_id((uint32_t)cta), n_tiles((uint32_t)n_tiles_),
+          stride((uint32_t)ctas), tiles_per_signal(tiles_per_signal_) {}
     __device__ __forceinline__ bool next(int64_t& sig, int64_t& t0, int& ncols, int& skip) {
+        if (tiles_per_signal > 0) {
+            if (tile_id >= n_tiles) return false;
+            const uint32_t s = tile_id / (uint32_t)tiles_per_signal;
+            const uint32_t tile = tile_id - s * (uint32_t)tiles_per_signal;
+            sig = s;
+            t0 = (int64_t)tile * (TILE_M - halo);
+            skip = tile ? halo : 0;
+            ncols = (int)min((uint32_t)TILE_M, per_signal - (uint32_t)t0);
+            tile_id += stride;
+            return true;
+        }
         if (g >= g1) return false;
         const uint32_t s = g / per_signal, v = g - s * per_signal;
         sig = s;
@@ -1079,7 +1098,8 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    TileStrip strip(p.total_tiles, p.n_blocks, p.halo, (int)blockIdx.x, (int)gridDim.x);
+    TileStrip strip(p.total_cols, p.n_blocks, p.halo, p.strips ? 0 : p.tiles_per_signal, p.total_tiles,
+                    (int)blockIdx.x, (int)gridDim.x);
     int64_t sig, t0;
     int ncols, skip;
 
@@ -2115,6 +2135,20 @@ void brv_fold_plan_free(brv_stft_plan* p) {
     p->fold = nullptr;
 }
 
+// Transposed strip kernel (brv_fold_t.cuh): every SM walks the same number of frames in <= 64-frame
+// tiles, the epilogue of a tile runs under the build + MMA of the next one.  Measured (B200):
+// 128 x 8 s at 510 / 128 compressed 210 -> 181 us, 2048 x 4 s at 256 / 128 625 -> 530 us, but
+// 64 x 4 s at 512 / 128 40 -> 44 us: with only a few tiles per SM its longer pipeline fill
+// loses to one CTA per tile.  Variant 5 forces it, variant 4 disables it.
+static bool fold_forward_uses_t(const brv_stft_plan* p, int64_t n_sig, int64_t n_frames, int origin) {
+    const FoldPlan* fp = (const FoldPlan*)p->fold;
+    if (origin < 0) origin = p->n_fft / 2;
+    const int shift = p->hop % 4 == 0 ? (4 - (origin & 3)) & 3 : 0;
+    if (ft_tile_frames(p->n_fft, p->hop, shift) < 16) return false;
+    return g_brv_fold_variant == 5 ||
+           (g_brv_fold_variant == 0 && n_sig * n_frames >= 512LL * fp->sm_count);
+}
+
 static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool compress,
                                int64_t n_sig, int64_t n_frames, cudaStream_t st) {
     const FoldPlan* fp = (const FoldPlan*)p->fold;
@@ -2129,10 +2163,9 @@ static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool c
     prm.shift = p->hop % 4 == 0 ? (4 - (prm.origin & 3)) & 3 : 0;
     prm.tmem_cols = fp->tmem_cols;
     prm.basis_scale_inv = fp->fwd.scale_inv;
-    if (g_brv_fold_variant == 0 || g_brv_fold_variant == 5) {
-        // transposed strip kernel: every SM walks the same number of frames in <= 64-frame tiles
+    if (fold_forward_uses_t(p, n_sig, n_frames, prm.origin)) {
         const int nf = ft_tile_frames(p->n_fft, p->hop, prm.shift);
-        if (nf >= 16) {
+        {
             prm.rows = nf;
             prm.tiles_per_signal = 0;
             prm.total_tiles = n_sig * n_frames;              // columns (frames), not tiles
@@ -2268,8 +2301,9 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     prm.wsq = p->window_sq;
     prm.total_tiles = n_sig * prm.tiles_per_signal;
     const bool frames_fast = prm.sb != 1;
-    if ((g_brv_fold_variant == 0 || g_brv_fold_variant == 6) && !fp->odd && (fp->hq == 1 || fp->hq == 2)) {
-        // transposed strip kernel: every SM walks the same number of hop blocks in <= 64-column tiles
+    if (g_brv_fold_variant == 6 && !fp->odd && (fp->hq == 1 || fp->hq == 2)) {
+        // transposed strip kernel (on request only: measured slower than the one-tile-per-TMEM kernel,
+        // 70 vs 60 us on 64 x 4 s at 512 / 128; see DESIGN.md 4.2 for the ablation that explains why)
         prm.total_tiles = n_sig * (int64_t)prm.n_blocks;     // columns (hop blocks), not tiles
         BRV_REQUIRE(prm.total_tiles < (1LL << 31), "too many hop blocks (%lld)", (long long)prm.total_tiles);
         const int64_t want = brv_ceil_div(prm.total_tiles, 16);
@@ -2290,11 +2324,13 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
         BRV_LAUNCH_CHECK("istft_t_kernel");
         return BRV_OK;
     }
-    // one strip of hop blocks per CTA (TileStrip): at least 32 columns each
-    prm.total_tiles = n_sig * (int64_t)prm.n_blocks;         // columns (hop blocks), not tiles
-    BRV_REQUIRE(prm.total_tiles < (1LL << 31), "too many hop blocks (%lld)", (long long)prm.total_tiles);
-    const int64_t want_ctas = brv_ceil_div(prm.total_tiles, 32);
-    const unsigned grid = (unsigned)(want_ctas < fp->sm_count ? want_ctas : fp->sm_count);
+    // large launches: one strip of hop blocks per CTA (TileStrip; cfg5-size: 5 % faster); small
+    // ones keep the fixed tiles (measured: strips cost 60 -> 73 us on 256 tiles)
+    prm.total_cols = n_sig * (int64_t)prm.n_blocks;
+    BRV_REQUIRE(prm.total_cols < (1LL << 31) && prm.total_tiles < (1LL << 31), "too many hop blocks (%lld)",
+                (long long)prm.total_cols);
+    prm.strips = prm.total_tiles >= 8LL * fp->sm_count ? 1 : 0;
+    const unsigned grid = (unsigned)(prm.total_tiles < fp->sm_count ? prm.total_tiles : fp->sm_count);
     {   // the bytes the (signal, frame, bin) view itself covers: bulk row copies stay inside them
         const int64_t f_in = p->n_fft / 2 + 1;
         // (16 KB chunks only: with the 8 KB chunks of n_fft = 256 three copies in flight do not
@@ -2385,7 +2421,7 @@ int brv_fold_istft_grad(const brv_stft_plan* p, const float* gy, int64_t n_sig, 
                         int64_t out_len, float2* gX, cudaStream_t st) {
     const FoldPlan* fp = (const FoldPlan*)p->fold;
     FoldFwdParams prm = {};
-    if (g_brv_fold_variant == 0 || g_brv_fold_variant == 5) {
+    if (fold_forward_uses_t(p, n_sig, n_frames, -1)) {
         prm.grad_env = 1;                          // the transposed kernel sums the envelope itself
         prm.env_per = fp->env_per;
         prm.wsq = p->window_sq;

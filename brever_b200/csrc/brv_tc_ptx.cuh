@@ -48,6 +48,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 64) {
     const uint32_t addr = smem_u32(bar);
     long long start = 0;
+#ifdef BRV_WAIT_HINT
+    // try_wait with a suspend-time hint: the hardware parks the thread until the phase flips (or
+    // the hint expires), so a waiting warp issues a handful of instructions per wake-up instead
+    // of a try_wait / nanosleep loop (polling was 20 - 40 % of all issued instructions)
+    const uint32_t hint = ns * 64u;
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"(hint)
+            : "memory");
+        if (ok) return;
+        if ((spins & 255) == 255) {                          // never hang the device
+            if (start == 0) start = clock64();
+            else if (clock64() - start > 4000000000LL) __trap();
+        }
+    }
+#else
     for (uint32_t spins = 0;; ++spins) {
         uint32_t ok;
         asm volatile(
@@ -64,6 +85,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             else if (clock64() - start > 4000000000LL) __trap();
         }
     }
+#endif
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
