@@ -9,7 +9,15 @@ N=1 the default workload is BASELINE.json configs[1]: the DCCRN-style complex
 STFT (512-pt, hop 128) -> iSTFT round trip + SI-SNR loss on a batch of 64 x 4 s
 at 16 kHz.  With N > 1 every rank processes its own batch of that size (weak
 scaling, utterances sharded by rank, no collective on the data path) and the
-only NCCL traffic is the final all-reduce of the mean metric.
+only NCCL traffic is the final all-reduce of the mean metric; `--scaling strong`
+shards the workload's fixed global batch instead.
+
+Besides the headline the same JSON line carries (skip with --no-extras):
+  workloads  : (N = 1) all five BASELINE.json configs measured in this run
+  torch_gpu_baseline : (N = 1) the reference's torch.stft / istft calls on the same GPU
+  strong_scaling : (N > 1) cfg5 (1024 x 2ch x 4 s) and cfg3 (256 x 4 s) at their fixed
+               global batch, sharded with brever_b200.distributed.shard_bounds
+  cpu_baseline_1thread : the CPU reference on one core
 
 Prints ONE JSON line on rank 0 (see the contract in the task statement):
   value      : audio-seconds / second, inputs resident in HBM, CUDA-event timed
@@ -305,23 +313,26 @@ def time_stages(pipe, sets, reps, only=None):
     return out
 
 
-def run_ours(args, rank, world, device):
+def measure_workload(name, wl, device, rank, world, steps, warmup, use_graph=True, with_e2e=True,
+                     global_audio_s=None, seed_base=1000):
+    """One workload through the public API on this rank's GPU: device-timed steps (max over
+    ranks), per-stage times, the roofline block and the end-to-end (host buffers) figure.
+    `global_audio_s`: audio-seconds all ranks process per step (default: world x this rank's)."""
     import torch.distributed as dist
     from brever_b200 import _lib, graphs
-    wl = WORKLOADS[args.workload]
     peaks = load_peaks()
-    sampler = ClockSampler(device.index)
-    sampler.start()
-    pipe = Pipeline(args.workload, wl, device)
+    pipe = Pipeline(name, wl, device)
     work, n_frames = stage_work(wl)
-    audio_s = wl['batch'] * wl['seconds']            # per rank per step
+    audio_s = wl['batch'] * wl['seconds']            # this rank, per step
+    if global_audio_s is None:
+        global_audio_s = world * audio_s
 
     # rotating input sets so that a step never finds its inputs in L2
     set_bytes = sum(work[s]['bytes'] for s in pipe.stage_names)
     n_sets = max(2, min(8, int(2.2 * 126e6 / max(set_bytes, 1)) + 1))
     sets = []
     for i in range(n_sets):
-        mix, fg = make_batch(wl, 1000 + rank * 16 + i)
+        mix, fg = make_batch(wl, seed_base + rank * 16 + i)
         sets.append((mix.to(device), fg.to(device)))
     torch.cuda.synchronize()
 
@@ -337,7 +348,6 @@ def run_ours(args, rank, world, device):
         total.add_(loss.mean())                      # running metric (training.py:369-373)
         return loss
 
-    use_graph = not args.no_graph
     lib = _lib.lib()
     if use_graph:
         # one captured step per input set: a replay is ONE host call for the whole chain
@@ -354,7 +364,7 @@ def run_ours(args, rank, world, device):
         def run(i):
             return full_step(*sets[i % n_sets])
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         run(i)
     barrier()
     total.zero_()
@@ -362,25 +372,23 @@ def run_ours(args, rank, world, device):
     torch.cuda.synchronize()
     t_begin = time.perf_counter()
     start.record()
-    for i in range(args.steps):
+    for i in range(steps):
         run(i)
     if world > 1:   # the one collective: final metric all-reduce (training.py:369-373)
         dist.all_reduce(total)
     stop.record()
     barrier()
     t_end = time.perf_counter()
-    clocks = sampler.stop(t_begin, t_end)
     elapsed_ms = start.elapsed_time(stop)
     t = torch.tensor([elapsed_ms], device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t)
-    ms_per_step = elapsed_ms / args.steps
-    value = world * audio_s / (ms_per_step * 1e-3)
-    mean_loss = float(total) / (args.steps * world)
+    ms_per_step = float(t) / steps
+    value = global_audio_s / (ms_per_step * 1e-3)
+    mean_loss = float(total) / (steps * world)
 
     # per-stage device time, each stage isolated (CUDA events around graph replays)
-    stage_ms = time_stages(pipe, sets, reps=max(5, min(args.steps, 20)))
+    stage_ms = time_stages(pipe, sets, reps=max(5, min(steps, 20)))
     dominant = max(stage_ms, key=stage_ms.get)
     w = work[dominant]
     if w['flops'] > 0:
@@ -397,9 +405,11 @@ def run_ours(args, rank, world, device):
         roofline = dict(bound='hbm', kernel=dominant, achieved=round(achieved, 1),
                         peak=peaks['hbm'], unit='GB/s', frac=round(achieved / peaks['hbm'], 4),
                         traffic=None, peak_source=peaks['source'])
-    try:    # DRAM traffic of the dominant kernel from the committed ncu capture, if there is one
-        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
-            roofline['traffic'] = json.load(f).get(args.workload, {}).get(dominant)
+    try:    # DRAM traffic of the dominant kernel from the committed ncu capture of this round
+        with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as f:
+            tr = json.load(f)
+        roofline['traffic'] = tr.get(name, {}).get(dominant)
+        roofline['traffic_source'] = tr.get('_source')
     except (OSError, ValueError):
         pass
     roofline['stage_ms'] = {k: round(v, 4) for k, v in stage_ms.items()}
@@ -410,9 +420,16 @@ def run_ours(args, rank, world, device):
     tot_bytes = sum(work[s]['bytes'] for s in pipe.stage_names)
     tot_flops = sum(work[s]['flops'] for s in pipe.stage_names)
     t_roof = max(tot_bytes / (peaks['hbm'] * 1e9), tot_flops / (peaks['bf16'] / 3 * 1e12))
+    local_ms = ms_per_step                      # every rank runs the same amount of work
     roofline['chain'] = {'alg_bytes': tot_bytes, 'alg_flops': tot_flops,
                          'roofline_ms': round(t_roof * 1e3, 4),
-                         'frac': round(t_roof * 1e3 / ms_per_step, 4)}
+                         'frac': round(t_roof * 1e3 / local_ms, 4)}
+    res = {'ms_per_step': round(ms_per_step, 4), 'value': round(value, 1), 'unit': 'audio-s/s',
+           'launches_per_step': int(launches_per_step), 'mean_loss_db': round(mean_loss, 4),
+           'frames': n_frames, 'n_sets': n_sets, 'roofline': roofline,
+           '_t': (t_begin, t_end), '_pipe': (pipe, sets, full_step)}
+    if not with_e2e:
+        return res
 
     # ---- end to end: pinned host buffers, H2D + D2H inside the timed region ----
     # mixture and target of a step travel as ONE pinned buffer / one H2D copy (they are
@@ -435,10 +452,10 @@ def run_ours(args, rank, world, device):
     else:
         e2e_steps = [lambda b=b: full_step(*dev_bufs[b]) for b in range(2)]
 
-    def e2e_loop(steps):
+    def e2e_loop(n):
         main = torch.cuda.current_stream(device)
-        for i in range(steps + 1):
-            if i < steps:                  # stage the next step's inputs
+        for i in range(n + 1):
+            if i < n:                      # stage the next step's inputs
                 b = i % 2
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(consumed[b])
@@ -454,47 +471,124 @@ def run_ours(args, rank, world, device):
 
     for ev in consumed:
         ev.record(torch.cuda.current_stream(device))
-    e2e_loop(max(2, args.warmup))
+    e2e_loop(max(2, warmup))
     barrier()
     t0 = time.perf_counter()
-    e2e_loop(args.steps)
+    e2e_loop(steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * audio_s * args.steps / float(t)
+    e2e_value = global_audio_s * steps / float(t)
     # what the link alone allows: the same H2D copies with no compute behind them
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         dev_flat[i % 2].copy_(host[i % 2], non_blocking=True)
     torch.cuda.synchronize()
-    h2d_only_s = (time.perf_counter() - t0) / args.steps
+    h2d_only_s = (time.perf_counter() - t0) / steps
+    rates = torch.tensor([h2d / h2d_only_s / 1e9], device=device)
+    if world > 1:
+        gathered = [torch.zeros_like(rates) for _ in range(world)]
+        dist.all_gather(gathered, rates)
+        rates = torch.cat(gathered)
+    res['e2e'] = {'value': round(e2e_value, 1), 'unit': 'audio-s/s',
+                  'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                  'h2d_only_ms_per_step': round(h2d_only_s * 1e3, 4),
+                  'h2d_gb_per_s': round(h2d / h2d_only_s / 1e9, 1),
+                  'h2d_gb_per_s_per_rank': [round(float(r), 1) for r in rates],
+                  'note': 'one pinned host -> device copy of mixture+target per step, double-buffered on a copy stream; '
+                          'loss read back every step; h2d_only_* = the same copies with no compute (the PCIe bound)'}
+    return res
 
+
+def torch_gpu_baseline(wl, device, steps):
+    """The reference's own library calls for the cfg2 chain (torch.stft / torch.istft -> cuFFT,
+    elementwise SI-SNR; brever/modules/stft.py:59-138, criterion.py:41-72 with one source) on
+    CUDA tensors of the same B200: the existing-library bar."""
+    eps = torch.finfo(torch.float32).eps
+    N, H = wl['frame_length'], wl['hop']
+    window = torch.hann_window(N, periodic=True, device=device)
+    norm = window.pow(2).sum().sqrt()
+    mix, fg = make_batch(wl, 1000)
+    mix, fg = mix.to(device), fg.to(device)
+    lengths = torch.full((wl['batch'],), mix.shape[-1], dtype=torch.int64, device=device)
+
+    def step():
+        spec = torch.stft(mix, n_fft=N, hop_length=H, win_length=N, window=window, center=True,
+                          pad_mode='constant', normalized=False, onesided=True, return_complex=True) / norm
+        y = torch.istft(spec * norm, n_fft=N, hop_length=H, win_length=N, window=window, center=True,
+                        normalized=False, onesided=True, return_complex=False)[..., :mix.shape[-1]]
+        mask = (torch.arange(mix.shape[-1], device=device)[None] < lengths[:, None]).float()
+        a, b = y * mask, fg * mask
+        a = (a - a.sum(-1, keepdim=True) / lengths[:, None]) * mask
+        b = (b - b.sum(-1, keepdim=True) / lengths[:, None]) * mask
+        proj = (a * b).sum(-1, keepdim=True) * b / b.pow(2).sum(-1, keepdim=True)
+        noise = a - proj
+        return -10 * torch.log10(proj.pow(2).sum(-1) / (noise.pow(2).sum(-1) + eps) + eps)
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {'value': round(wl['batch'] * wl['seconds'] / (ms * 1e-3), 1), 'unit': 'audio-s/s',
+            'ms_per_step': round(ms, 4),
+            'what': f'torch {torch.__version__} torch.stft / torch.istft (cuFFT) + elementwise SI-SNR on the same GPU, '
+                    'eager launches, same inputs and shapes as the headline workload'}
+
+
+# global batches of the fixed-batch (strong-scaling) configs of BASELINE.json
+STRONG = {'cfg5': 1024, 'cfg3': 256}
+
+
+def run_ours(args, rank, world, device):
+    from brever_b200 import distributed
+    wl = WORKLOADS[args.workload]
+    sampler = ClockSampler(device.index)
+    sampler.start()
+    use_graph = not args.no_graph
+    strong = args.scaling == 'strong'
+    if strong:
+        # fixed global batch, utterances sharded by rank (brever/batching.py:279-290)
+        lo, hi = distributed.shard_bounds(wl['batch'], rank, world)
+        wl = dict(wl, batch=hi - lo)
+        global_audio = WORKLOADS[args.workload]['batch'] * wl['seconds']
+    else:
+        global_audio = None
+    res = measure_workload(args.workload, wl, device, rank, world, args.steps, args.warmup,
+                           use_graph=use_graph, global_audio_s=global_audio)
+    t_begin, t_end = res.pop('_t')
+    pipe, sets, full_step = res.pop('_pipe')
+    clocks = sampler.stop(t_begin, t_end)
+    n_sets = res['n_sets']
+    base_wl = WORKLOADS[args.workload]
     out = {
         'metric': 'audio-seconds/sec (STFT->iSTFT->SI-SNR front-end)',
-        'value': round(value, 1), 'unit': 'audio-s/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms_per_step, 4),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'value': res['value'], 'unit': 'audio-s/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': res['ms_per_step'],
+        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f"{args.workload}: {wl['desc']}",
+        'config': {'workload': f"{args.workload}: {base_wl['desc']}",
                    'per_gpu_batch': wl['batch'], 'seconds': wl['seconds'], 'fs': FS,
                    'frame_length': wl['frame_length'], 'hop_length': wl['hop'],
-                   'frames': n_frames, 'parallelism': f'dp{world} (utterances sharded by rank)',
+                   'frames': res['frames'],
+                   'parallelism': f'dp{world} (utterances sharded by rank' +
+                                  (f', fixed global batch {base_wl["batch"]})' if strong else ', fixed per-GPU batch)'),
                    'l2': f'{n_sets} rotating input sets (> 2x L2) so steps never hit L2-resident inputs',
                    'launch': 'one CUDA-graph replay per step (brever_b200.graphs.capture of the public API calls)'
                              if use_graph else 'eager Python launches',
                    'stft_path': os.environ.get('BRV_FORCE_GENERIC', '0') == '1' and 'generic' or 'default'},
-        'e2e': {'value': round(e2e_value, 1), 'unit': 'audio-s/s',
-                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'h2d_only_ms_per_step': round(h2d_only_s * 1e3, 4),
-                'h2d_gb_per_s': round(h2d / h2d_only_s / 1e9, 1),
-                'note': 'one pinned host -> device copy of mixture+target per step, double-buffered on a copy stream; '
-                        'loss read back every step; h2d_only_* = the same copies with no compute (the PCIe bound)'},
-        'gpu_launches': int(launches_per_step * args.steps),
-        'mean_loss_db': round(mean_loss, 4),
-        'roofline': roofline,
+        'e2e': res['e2e'],
+        'gpu_launches': int(res['launches_per_step'] * args.steps),
+        'mean_loss_db': res['mean_loss_db'],
+        'roofline': res['roofline'],
         'clocks': clocks,
     }
     if use_graph and args.eager_compare:
@@ -509,21 +603,74 @@ def run_ours(args, rank, world, device):
         e1.record()
         torch.cuda.synchronize()
         out['eager_ms_per_step'] = round(e0.elapsed_time(e1) / args.steps, 4)
+    del pipe, sets, full_step
+    torch.cuda.empty_cache()
+
+    if world == 1 and not args.no_extras:
+        # every BASELINE.json config in the same run (lighter settings), so that K2 (mel /
+        # features, cfg1) and the 60 % target are measured by whoever runs this file
+        sub_steps = max(10, min(args.steps, 20))
+        table = {args.workload: {k: res[k] for k in ('ms_per_step', 'value', 'launches_per_step')} |
+                 {'chain_frac': res['roofline']['chain']['frac'], 'dominant': res['roofline']['kernel'],
+                  'dominant_frac': res['roofline']['frac'], 'stage_ms': res['roofline']['stage_ms'],
+                  'e2e': res['e2e']['value']}}
+        for name in sorted(WORKLOADS):
+            if name in table:
+                continue
+            r = measure_workload(name, WORKLOADS[name], device, rank, world, sub_steps, 3,
+                                 use_graph=use_graph)
+            r.pop('_t'), r.pop('_pipe')
+            table[name] = {'ms_per_step': r['ms_per_step'], 'value': r['value'],
+                           'launches_per_step': r['launches_per_step'],
+                           'chain_frac': r['roofline']['chain']['frac'],
+                           'dominant': r['roofline']['kernel'], 'dominant_frac': r['roofline']['frac'],
+                           'dominant_bound': r['roofline']['bound'],
+                           'stage_ms': r['roofline']['stage_ms'], 'e2e': r['e2e']['value'],
+                           'desc': WORKLOADS[name]['desc']}
+            torch.cuda.empty_cache()
+        out['workloads'] = table
+        out['workloads_note'] = (f'all five BASELINE.json configs on this GPU in this run; {sub_steps} timed steps '
+                                 'each besides the headline workload; chain_frac = step time against '
+                                 'max(bytes / HBM, flops / (bf16 / 3)) of SURVEY 8d')
+        if args.workload == 'cfg2':
+            out['torch_gpu_baseline'] = torch_gpu_baseline(WORKLOADS['cfg2'], device, sub_steps)
+    if world > 1 and not args.no_extras and not strong:
+        # the fixed-batch configs of north_star, sharded with brever_b200.distributed
+        block = {}
+        for name, gbatch in STRONG.items():
+            lo, hi = distributed.shard_bounds(gbatch, rank, world)
+            swl = dict(WORKLOADS[name], batch=hi - lo)
+            r = measure_workload(name, swl, device, rank, world, max(10, min(args.steps, 20)), 3,
+                                 use_graph=use_graph, with_e2e=False,
+                                 global_audio_s=gbatch * swl['seconds'])
+            r.pop('_t'), r.pop('_pipe')
+            block[name] = {'global_batch': gbatch, 'per_gpu_batch': hi - lo, 'ms_per_step': r['ms_per_step'],
+                           'value': r['value'], 'chain_frac': r['roofline']['chain']['frac']}
+            torch.cuda.empty_cache()
+        out['strong_scaling'] = block
+        out['strong_scaling_note'] = ('fixed global batch (cfg5: 1024 x 2ch x 4 s, cfg3: 256 x 4 s) sharded by rank with '
+                                      'brever_b200.distributed.shard_bounds; value = global audio-s / max-over-ranks step time; '
+                                      'compare with workloads.cfg5 / cfg3 of the 1-GPU line')
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_reference(args.workload, budget_s=15.0)
+        one = cpu_reference(args.workload, budget_s=6.0, threads=1)
+        out['cpu_baseline_1thread'] = {k: one[k] for k in ('value', 'unit', 'cores', 'sample')}
+    if world > 1:
+        out['vs_reference_note'] = ('the reference arm runs ONE batch slice on rank 0 host cores; at N GPUs the whole-job '
+                                    'value covers N batches (weak scaling), so value / reference grows with N by construction')
     return out
 
 
 # --------------------------------------------------------------------------- #
 # reference arm: the reference's CPU implementation on this host's cores      #
 # --------------------------------------------------------------------------- #
-def cpu_reference(workload, budget_s=15.0, steps=None, warmup=1):
+def cpu_reference(workload, budget_s=15.0, steps=None, warmup=1, threads=None):
     """Times oracle/torch_port.py (the reference's exact torch calls, float32 CPU,
     all host threads) on a bounded slice of the workload."""
     from oracle import tf_oracle as O
     from oracle import torch_port as P
     wl = WORKLOADS[workload]
-    threads = os.cpu_count() or 1
+    threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     win = torch.from_numpy(O.get_window('hann', wl['frame_length']))
     kw = dict(frame_length=wl['frame_length'], hop_length=wl['hop'], **wl['kw'])
@@ -580,6 +727,7 @@ def run_reference(args, rank, world):
         return None
     base = cpu_reference(args.workload, budget_s=60.0, steps=args.steps, warmup=args.warmup)
     wl = WORKLOADS[args.workload]
+    _, n_frames = stage_work(wl)
     return {
         'impl': 'reference',
         'metric': 'audio-seconds/sec (STFT->iSTFT->SI-SNR front-end)',
@@ -588,7 +736,9 @@ def run_reference(args, rank, world):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f"{args.workload}: {wl['desc']}", 'per_gpu_batch': wl['batch'],
                    'seconds': wl['seconds'], 'fs': FS, 'frame_length': wl['frame_length'],
-                   'hop_length': wl['hop'],
+                   'hop_length': wl['hop'], 'frames': n_frames,
+                   'parallelism': 'host CPU cores of rank 0 (no GPU)', 'l2': 'n/a (CPU arm)',
+                   'launch': 'eager torch CPU calls', 'stft_path': 'reference (torch.stft / torch.istft, MKL FFT)',
                    'note': 'reference CPU path (torch.stft/istft + criterion, brever call sequence) on host cores; each step is a bounded batch slice'},
         'cpu_baseline': base,
         'e2e': {'value': base['value'], 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0,
@@ -604,6 +754,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: every rank runs the full per-GPU batch; strong: the fixed global batch of the '
+                         'workload is sharded over the ranks (brever_b200.distributed.shard_bounds)')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip the per-config table (N = 1), the torch-on-GPU baseline and the strong-scaling block (N > 1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly from Python instead of replaying CUDA graphs')
     ap.add_argument('--no-eager-compare', dest='eager_compare', action='store_false',

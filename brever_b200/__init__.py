@@ -8,7 +8,7 @@ Drop-in replacements for the hot-path classes of philgzl/brever:
 backed by hand-written CUDA kernels behind a C ABI (include/brever_b200.h).
 CUDA tensors only; there is no CPU fallback.
 """
-from . import criterion, ffnn, modules
+from . import criterion, ffnn, metrics, modules
 from .criterion import (CriterionRegistry, MultiResYuLoss, apply_mask, init_criterion, mse,
                         sisnr, snr)
 from .modules import STFT, ConvSTFT, FeatureExtractor, MelFilterbank
@@ -17,4 +17,4 @@ from .registry import Registry
 __version__ = '0.1.0'
 __all__ = ['STFT', 'ConvSTFT', 'MelFilterbank', 'FeatureExtractor', 'CriterionRegistry',
            'init_criterion', 'sisnr', 'snr', 'mse', 'MultiResYuLoss', 'apply_mask', 'Registry',
-           'criterion', 'ffnn', 'modules']
+           'criterion', 'ffnn', 'metrics', 'modules']

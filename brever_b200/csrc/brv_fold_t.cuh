@@ -111,12 +111,12 @@ constexpr int FT_LOADER_WARP0 = 2;
 constexpr int FT_EPI_WARP0 = 4, FT_EPI_WARPS = 8;
 constexpr int FT_BUILD_WARP0 = 12, FT_BUILD_WARPS = 16;
 constexpr int FT_SPAN = (T_NF - 1) * 128 + 512 + 64;        // floats per span buffer (8640)
-constexpr int FT_BMAX = FT_SPAN / 32;                       // 270
+constexpr int FT_BMAX_W = 72;                               // per-builder-warp maxima (<= (3 H + N) / 32 + 2)
 constexpr int FT_OFF_SPAN = T_SMEM_STAGES;
 constexpr int FT_OFF_WTAB = FT_OFF_SPAN + 2 * FT_SPAN * 4;
 constexpr int FT_OFF_ROWINFO = FT_OFF_WTAB + SMEM_WTAB;      // 2 slots x 64 float4
 constexpr int FT_OFF_BMAX = FT_OFF_ROWINFO + 2 * T_NF * 16;
-constexpr int FT_SMEM_BYTES = 1024 + FT_OFF_BMAX + 2 * FT_BMAX * 4 + 32;
+constexpr int FT_SMEM_BYTES = 1024 + FT_OFF_BMAX + FT_BUILD_WARPS * FT_BMAX_W * 4 + 32;
 static_assert(FT_SMEM_BYTES <= 227 * 1024, "transposed forward kernel shared memory");
 
 // frames per tile for a given geometry: the tile's span must fit one span buffer
@@ -164,7 +164,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
     float* span2 = reinterpret_cast<float*>(stages + FT_OFF_SPAN);
     float4* wtab = reinterpret_cast<float4*>(stages + FT_OFF_WTAB);
     float4* rowinfo2 = reinterpret_cast<float4*>(stages + FT_OFF_ROWINFO);
-    uint32_t* bmax2 = reinterpret_cast<uint32_t*>(stages + FT_OFF_BMAX);
+    uint32_t* bmax_all = reinterpret_cast<uint32_t*>(stages + FT_OFF_BMAX);
 
     const int N = p.n_fft, H = p.hop, Q = p.q, Hf = N / 2;
     const int n_kc = Q / BK;
@@ -424,16 +424,16 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
             const int b = n & 1;
             const float* span = span2 + b * FT_SPAN;
             float4* rowinfo = rowinfo2 + b * T_NF;
-            uint32_t* bmax = bmax2 + b * FT_BMAX;
             if (bw == 0) T_STAMP(1, n, 0);
             const uint32_t kph = (uint32_t)((n >> 1) & 1);
-            T_WAITED(0, mbar_wait_relaxed(&span_landed[b], kph, 20));
-            T_WAITED(1, mbar_wait_relaxed(&ri_empty[b], kph ^ 1, 20));
+            mbar_wait_relaxed(&span_landed[b], kph, 20);
+            mbar_wait_relaxed(&ri_empty[b], kph ^ 1, 20);
             if (bw == 0) T_STAMP(1, n, 1);
             if (bw * ROWS_W < ncols) {
                 // ---- this warp's frames: per-32-sample maxima of the samples they cover (the
-                //      neighbouring warps scan the overlap again and store the same values),
-                //      then the per-frame scale and rank-1 terms ---------------------------
+                //      neighbouring warps scan the overlap again into their own tables), then
+                //      the per-frame scale and rank-1 terms ----------------------------------
+                uint32_t* bmax = bmax_all + bw * FT_BMAX_W - (((bw * ROWS_W * H + shift) & ~31) >> 5);
                 const int rows_w = min(ROWS_W, ncols - bw * ROWS_W);
                 const int s_lo = (bw * ROWS_W * H + shift) & ~31;
                 const int s_hi = ((bw * ROWS_W + rows_w - 1) * H + shift + N + 31) & ~31;   // whole blocks (<= span_pad)
@@ -476,6 +476,9 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                 frow[i] = span + shift + (row < ncols ? row : 0) * H;
             }
             for (int kc = 0; kc < n_kc; ++kc) {
+#ifdef BRV_PHASE_TIMING
+                const long long tf0_ = clock64();
+#endif
                 const int n0 = kc * BK + 2 * pr;
                 const float4 w0 = wtab[n0], w1 = wtab[n0 + 1];
                 float sp0[RI], sp1[RI], rp0[RI], rp1[RI], sm0[RI], sm1[RI], rm0[RI], rm1[RI];
@@ -489,11 +492,17 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                     sp0[i] = a0 + d0; sp1[i] = a1 + d1; rp0[i] = b0 + c0; rp1[i] = b1 + c1;
                     sm0[i] = a0 - d0; sm1[i] = a1 - d1; rm0[i] = b0 - c0; rm1[i] = b1 - c1;
                 }
+#ifdef BRV_PHASE_TIMING
+                t_wacc_[0] += clock64() - tf0_;            // (timing build: kind 0 = window + fold part)
+#endif
 #pragma unroll
                 for (int pair = 0; pair < 2; ++pair, ++g) {
                     const int s = g % T_STAGES;
                     const uint32_t ph = (g / T_STAGES) & 1;
                     T_WAITED(2, mbar_wait_relaxed(&empty_bar[s], ph ^ 1, 20));
+#ifdef BRV_PHASE_TIMING
+                    const long long ts0_ = clock64();
+#endif
                     uint8_t* sa = stages + (size_t)s * T_STAGE_BYTES + T_STAGE_BASIS;
 #ifdef BRV_T_NO_BUILD                                   // dev experiment: timing without the operand build
                     if (p.n_fft < 0)
@@ -529,9 +538,16 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                             if (pr == 0 && row < ncols) rowinfo[row].y = v;
                         }
                     }
+#ifdef BRV_PHASE_TIMING
+                    const long long ts1_ = clock64();
+                    t_wacc_[1] += ts1_ - ts0_;                 // (kind 1 = split + store loop)
+#endif
                     fence_proxy_async();                           // generic -> async proxy
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full_bar[s]);
+#ifdef BRV_PHASE_TIMING
+                    t_wacc_[3] += clock64() - ts1_;            // (kind 3 = fence + arrive)
+#endif
                 }
             }
             __syncwarp();

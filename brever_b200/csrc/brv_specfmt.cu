@@ -1,0 +1,187 @@
+// Spectrogram representations around the STFT pair, one pass each (HBM-bound elementwise):
+//   split: complex64 X -> two real planes      join: two real planes -> complex64 X
+//   mode 0  (Re X, Im X)                   STFT.forward(return_type='real_imag')   stft.py:91-94
+//   mode 1  (|X|, angle X)                 return_type='mag_phase' / input_type     stft.py:95-110
+//   mode 2  (log1p(|X| + eps), angle X)    MetricGAN-OKD's stft / istft wrappers    metricganokd.py:185-195
+// and their adjoints (torch convention: the gradient of a complex tensor is dL/dRe + i dL/dIm).
+// The planes are elementwise images of X's memory: the caller passes the dense buffers, so the
+// (F, T) views with strides (1, F) the reference's `.abs()` / `.angle()` return come for free.
+#include <math.h>
+
+#include "brv_common.cuh"
+
+namespace {
+
+constexpr int SF_THREADS = 256;
+constexpr int SF_PER_THREAD = 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(SF_THREADS)
+spec_split_kernel(const float2* __restrict__ X, int64_t n, float eps, float* __restrict__ a,
+                  float* __restrict__ b) {
+    const int64_t base = ((int64_t)blockIdx.x * SF_THREADS + threadIdx.x) * SF_PER_THREAD;
+    if (base + SF_PER_THREAD <= n) {
+        // two 16-byte loads, two 16-byte stores per plane pair
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(X + base));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(X + base + 2));
+        const float re[4] = {v0.x, v0.z, v1.x, v1.z}, im[4] = {v0.y, v0.w, v1.y, v1.w};
+        float oa[4], ob[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (MODE == 0) {
+                oa[i] = re[i];
+                ob[i] = im[i];
+            } else {
+                const float m = hypotf(re[i], im[i]);
+                oa[i] = MODE == 1 ? m : log1pf(m + eps);
+                ob[i] = atan2f(im[i], re[i]);
+            }
+        }
+        *reinterpret_cast<float4*>(a + base) = make_float4(oa[0], oa[1], oa[2], oa[3]);
+        *reinterpret_cast<float4*>(b + base) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+    } else {
+        for (int64_t i = base; i < n; ++i) {
+            const float2 v = __ldg(X + i);
+            if (MODE == 0) {
+                a[i] = v.x;
+                b[i] = v.y;
+            } else {
+                const float m = hypotf(v.x, v.y);
+                a[i] = MODE == 1 ? m : log1pf(m + eps);
+                b[i] = atan2f(v.y, v.x);
+            }
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ float2 join_one(float a, float b) {
+    if (MODE == 0) return make_float2(a, b);
+    const float m = MODE == 1 ? a : expm1f(a);
+    float s, c;
+    sincosf(b, &s, &c);
+    return make_float2(m * c, m * s);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SF_THREADS)
+spec_join_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                 float2* __restrict__ X) {
+    const int64_t base = ((int64_t)blockIdx.x * SF_THREADS + threadIdx.x) * SF_PER_THREAD;
+    if (base + SF_PER_THREAD <= n && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+        const float4 va = __ldg(reinterpret_cast<const float4*>(a + base));
+        const float4 vb = __ldg(reinterpret_cast<const float4*>(b + base));
+        const float2 x0 = join_one<MODE>(va.x, vb.x), x1 = join_one<MODE>(va.y, vb.y);
+        const float2 x2 = join_one<MODE>(va.z, vb.z), x3 = join_one<MODE>(va.w, vb.w);
+        *reinterpret_cast<float4*>(X + base) = make_float4(x0.x, x0.y, x1.x, x1.y);
+        *reinterpret_cast<float4*>(X + base + 2) = make_float4(x2.x, x2.y, x3.x, x3.y);
+    } else {
+        for (int64_t i = base; i < n && i < base + SF_PER_THREAD; ++i) X[i] = join_one<MODE>(__ldg(a + i), __ldg(b + i));
+    }
+}
+
+// gX from (ga, gb): mode 1 / 2 need X itself (|X| = 0 gets a zero gradient, as torch's sgn does)
+template <int MODE>
+__global__ void __launch_bounds__(SF_THREADS)
+spec_split_grad_kernel(const float* __restrict__ ga, const float* __restrict__ gb,
+                       const float2* __restrict__ X, int64_t n, float eps, float2* __restrict__ gX) {
+    for (int64_t i = ((int64_t)blockIdx.x * SF_THREADS + threadIdx.x); i < n;
+         i += (int64_t)gridDim.x * SF_THREADS) {
+        const float da = ga ? __ldg(ga + i) : 0.f, db = gb ? __ldg(gb + i) : 0.f;
+        if (MODE == 0) {
+            gX[i] = make_float2(da, db);
+            continue;
+        }
+        const float2 v = __ldg(X + i);
+        const float m2 = v.x * v.x + v.y * v.y;
+        if (!(m2 > 0.f)) {
+            gX[i] = make_float2(0.f, 0.f);
+            continue;
+        }
+        const float m = sqrtf(m2);
+        const float dm = MODE == 1 ? da : da / (1.f + m + eps);
+        gX[i] = make_float2(dm * v.x / m - db * v.y / m2, dm * v.y / m + db * v.x / m2);
+    }
+}
+
+// (ga, gb) from gX: X = m(a) e^{i b}
+template <int MODE>
+__global__ void __launch_bounds__(SF_THREADS)
+spec_join_grad_kernel(const float2* __restrict__ gX, const float* __restrict__ a,
+                      const float* __restrict__ b, int64_t n, float* __restrict__ ga,
+                      float* __restrict__ gb) {
+    for (int64_t i = ((int64_t)blockIdx.x * SF_THREADS + threadIdx.x); i < n;
+         i += (int64_t)gridDim.x * SF_THREADS) {
+        const float2 g = __ldg(gX + i);
+        if (MODE == 0) {
+            ga[i] = g.x;
+            gb[i] = g.y;
+            continue;
+        }
+        const float av = __ldg(a + i);
+        const float m = MODE == 1 ? av : expm1f(av);
+        float s, c;
+        sincosf(__ldg(b + i), &s, &c);
+        const float dm = g.x * c + g.y * s;
+        ga[i] = MODE == 1 ? dm : dm * expf(av);
+        gb[i] = m * (g.y * c - g.x * s);
+    }
+}
+
+unsigned blocks_vec(int64_t n) { return (unsigned)brv_ceil_div(n, (int64_t)SF_THREADS * SF_PER_THREAD); }
+unsigned blocks_loop(int64_t n) {
+    const int64_t b = brv_ceil_div(n, SF_THREADS);
+    return (unsigned)(b < 148 * 16 ? b : 148 * 16);
+}
+
+}  // namespace
+
+#define BRV_MODE_SWITCH(KERNEL, GRID, ...)                                             \
+    switch (mode) {                                                                    \
+        case 0: KERNEL<0><<<GRID, SF_THREADS, 0, (cudaStream_t)stream>>>(__VA_ARGS__); break; \
+        case 1: KERNEL<1><<<GRID, SF_THREADS, 0, (cudaStream_t)stream>>>(__VA_ARGS__); break; \
+        default: KERNEL<2><<<GRID, SF_THREADS, 0, (cudaStream_t)stream>>>(__VA_ARGS__); break; \
+    }
+
+extern "C" int brv_spec_split(const void* X, int64_t n, int mode, float eps, float* a, float* b,
+                              void* stream) {
+    BRV_REQUIRE(n >= 0 && mode >= 0 && mode <= 2, "bad spectrogram split arguments");
+    if (n == 0) return BRV_OK;
+    BRV_REQUIRE(X && a && b, "null pointer argument");
+    BRV_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(a) |
+                  reinterpret_cast<uintptr_t>(b)) & 15) == 0, "spectrogram planes must be 16-byte aligned");
+    BRV_MODE_SWITCH(spec_split_kernel, blocks_vec(n), (const float2*)X, n, eps, a, b)
+    BRV_LAUNCH_CHECK("spec_split_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_spec_join(const float* a, const float* b, int64_t n, int mode, void* X,
+                             void* stream) {
+    BRV_REQUIRE(n >= 0 && mode >= 0 && mode <= 2, "bad spectrogram join arguments");
+    if (n == 0) return BRV_OK;
+    BRV_REQUIRE(X && a && b, "null pointer argument");
+    BRV_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0, "spectrogram must be 16-byte aligned");
+    BRV_MODE_SWITCH(spec_join_kernel, blocks_vec(n), a, b, n, (float2*)X)
+    BRV_LAUNCH_CHECK("spec_join_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_spec_split_grad(const float* ga, const float* gb, const void* X, int64_t n,
+                                   int mode, float eps, void* gX, void* stream) {
+    BRV_REQUIRE(n >= 0 && mode >= 0 && mode <= 2, "bad spectrogram split arguments");
+    if (n == 0) return BRV_OK;
+    BRV_REQUIRE(gX && (mode == 0 || X), "null pointer argument");
+    BRV_MODE_SWITCH(spec_split_grad_kernel, blocks_loop(n), ga, gb, (const float2*)X, n, eps, (float2*)gX)
+    BRV_LAUNCH_CHECK("spec_split_grad_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_spec_join_grad(const void* gX, const float* a, const float* b, int64_t n, int mode,
+                                  float* ga, float* gb, void* stream) {
+    BRV_REQUIRE(n >= 0 && mode >= 0 && mode <= 2, "bad spectrogram join arguments");
+    if (n == 0) return BRV_OK;
+    BRV_REQUIRE(gX && ga && gb && (mode == 0 || (a && b)), "null pointer argument");
+    BRV_MODE_SWITCH(spec_join_grad_kernel, blocks_loop(n), (const float2*)gX, a, b, n, ga, gb)
+    BRV_LAUNCH_CHECK("spec_join_grad_kernel");
+    return BRV_OK;
+}

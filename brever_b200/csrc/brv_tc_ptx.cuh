@@ -42,6 +42,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+#ifndef BRV_WAIT_NAP_MAX
+#define BRV_WAIT_NAP_MAX 256u
+#endif
 // Wait used by the roles that are NOT on the critical path of the CUDA cores (TMA producer,
 // MMA issuer, epilogue / scout warps waiting for work): backs off with nanosleep so the
 // polling does not take issue slots from the warps that do the arithmetic.
@@ -69,6 +72,10 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         }
     }
 #else
+    // exponential back-off: a short wait is answered at once, a long one (a role that is a tile
+    // ahead of its producer) polls a few times per microsecond instead of every ~100 ns --
+    // ~20 waiting warps polling at the short period took a quarter of the SM's issue slots
+    uint32_t nap = ns;
     for (uint32_t spins = 0;; ++spins) {
         uint32_t ok;
         asm volatile(
@@ -79,8 +86,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             : "r"(addr), "r"(parity)
             : "memory");
         if (ok) return;
-        __nanosleep(ns);
-        if ((spins & 1023) == 1023) {                        // never hang the device
+        __nanosleep(nap);
+        nap = min(nap * 2u, BRV_WAIT_NAP_MAX);
+        if ((spins & 255) == 255) {                          // never hang the device
             if (start == 0) start = clock64();
             else if (clock64() - start > 4000000000LL) __trap();
         }

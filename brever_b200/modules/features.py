@@ -129,6 +129,7 @@ class FeatureExtractor:
             raise ValueError(f'input must be 4 dimensional, got {x.ndim}')
         if x.dtype != torch.complex64:
             x = x.to(torch.complex64)
+        x = x.resolve_conj().resolve_neg()   # raw pointers below: no lazy conj / neg bits
         batch, channels, bins, frames = x.shape
         fb = self.mel_fb
         vals, cols, rowptr, n_mel, n_in = fb.csr('forward', x.device)
@@ -187,6 +188,7 @@ class FeatureExtractor:
                 raise ValueError(f'input must be 4 dimensional, got {x.ndim}')
             if x.dtype != torch.complex64:
                 x = x.to(torch.complex64)
+            x = x.resolve_conj().resolve_neg()   # raw pointers below: no lazy conj / neg bits
             batch, channels, bins, frames = x.shape
             src, strides = x, (x.stride(0), x.stride(1), x.stride(2), x.stride(3))
         else:
@@ -227,6 +229,7 @@ class FeatureExtractor:
             raise ValueError(f'input must be 4 dimensional, got {x.ndim}')
         if x.dtype != torch.complex64:
             x = x.to(torch.complex64)
+        x = x.resolve_conj().resolve_neg()   # raw pointers below: no lazy conj / neg bits
         batch, channels, bins, frames = x.shape
         if channels < 2:
             raise IndexError('index 1 is out of bounds for dimension 1 with size 1')

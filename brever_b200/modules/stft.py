@@ -22,6 +22,7 @@ import scipy.signal
 import torch
 
 from .. import _lib
+from . import specfmt
 
 
 def _fft_freqs(fs, n_fft):
@@ -168,7 +169,7 @@ class STFT:
 
     def _forward_grad_raw(self, grad, samples):
         n_sig, bins, frames = grad.shape
-        grad = grad.to(torch.complex64)
+        grad = grad.to(torch.complex64).resolve_conj().resolve_neg()   # raw pointers below: no lazy bits
         gx = torch.empty((n_sig, samples), dtype=torch.float32, device=grad.device)
         if n_sig:
             lib = _lib.lib()
@@ -187,7 +188,7 @@ class STFT:
         n_sig, bins, frames = spec3d.shape
         if bins != self.n_bins:
             raise RuntimeError(f'expected {self.n_bins} frequency bins, got {bins}')
-        spec3d = spec3d.to(torch.complex64)
+        spec3d = spec3d.to(torch.complex64).resolve_conj().resolve_neg()   # raw pointers below
         out_len = self.hop_length * (frames - 1) + self.n_fft - 2 * (self.n_fft // 2)
         y = torch.empty((n_sig, out_len), dtype=torch.float32, device=spec3d.device)
         lib = _lib.lib()
@@ -242,17 +243,19 @@ class STFT:
             spec = spec.to(torch.complex128)
         if return_type == 'complex':
             return spec
-        if return_type == 'real_imag':
-            return spec.real, spec.imag
-        return spec.abs(), spec.angle()
+        if spec.dtype != torch.complex64:          # float64 callers: torch ops on the cast result
+            return (spec.real, spec.imag) if return_type == 'real_imag' else (spec.abs(), spec.angle())
+        # one fused pass (brv_spec_split) instead of the reference's eager .abs() / .angle()
+        return specfmt.split(spec, return_type)
 
     def backward(self, x, input_type='complex'):
-        if input_type == 'real_imag':
-            real, imag = x
-            x = torch.complex(real, imag)
-        elif input_type == 'mag_phase':
-            mag, phase = x
-            x = torch.polar(mag, phase)
+        if input_type in ('real_imag', 'mag_phase'):
+            a, b = x
+            _lib.require_cuda(a, 'STFT.backward input')
+            if a.dtype == torch.float64:
+                x = torch.complex(a, b) if input_type == 'real_imag' else torch.polar(a, b)
+            else:
+                x = specfmt.join(a, b, input_type)     # one fused pass (brv_spec_join)
         elif input_type != 'complex':
             raise ValueError('input_type must be complex, real_imag or '
                              f'mag_phase, got {input_type}')
@@ -373,7 +376,7 @@ class ConvSTFT:
         if not x.is_complex():
             raise RuntimeError('ConvSTFT.backward input must be complex')
         lead = x.shape[:-2]
-        spec3d = x.reshape(-1, *x.shape[-2:]).to(torch.complex64)
+        spec3d = x.reshape(-1, *x.shape[-2:]).to(torch.complex64).resolve_conj().resolve_neg()
         n_sig, bins, frames = spec3d.shape
         if bins != self.frame_length // 2 + 1:
             raise RuntimeError(f'expected {self.frame_length // 2 + 1} frequency bins, got {bins}')

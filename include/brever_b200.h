@@ -109,9 +109,10 @@ int brv_stft_forward_grad(const brv_stft_plan* plan, const void* gX,
  * y : (n_signals, hop*(T-1)) float32 contiguous.
  * /scale, |X|^(1/c), *sqrt(sum w^2), inverse real DFT (imag of DC/Nyquist
  * ignored), window, overlap-add, / overlap-added w^2, centre trim — fused.
- * Returns BRV_ERR_NOLA where torch.istft raises.  X is NOT modified (the
- * reference's in-place `x /= scale`, stft.py:114, is applied by the Python
- * mirror when the caller relies on it).                                      */
+ * Returns BRV_ERR_NOLA where torch.istft raises.  X is NOT modified: the
+ * reference divides a complex input by scale_factor in place (stft.py:114);
+ * neither this entry point nor the Python mirror reproduce that side effect
+ * ("Deliberate differences").                                     */
 int brv_istft_forward(const brv_stft_plan* plan, const void* X,
                       int64_t stride_signal, int64_t stride_bin,
                       int64_t stride_frame, int64_t n_signals, int64_t n_frames,
@@ -311,6 +312,23 @@ int brv_criterion_backward(const float* x, const float* y, const int64_t* length
  * themselves: out[b, ..., n] = n < lengths[b] ? x[b, ..., n] : 0.            */
 int brv_apply_mask(const float* x, const int64_t* lengths, int64_t n_batch,
                    int64_t inner, int64_t length, float* out, void* stream);
+
+/* ---- spectrogram representations (stft.py:91-110, metricganokd.py:185-195) -----
+ * One elementwise pass over n complex64 values and two float32 planes of the same
+ * memory order.  mode 0: (Re, Im) -- return_type / input_type 'real_imag';
+ * mode 1: (|X|, angle X) -- 'mag_phase'; mode 2: (log1p(|X| + eps), angle X) and
+ * X = expm1(a) e^{i b} -- MetricGAN-OKD's stft / istft wrappers.  X, a, b 16-byte
+ * aligned for split; the *_grad entries are the adjoints (gradient of a complex
+ * tensor = dL/dRe + i dL/dIm; |X| = 0 gets a zero gradient; ga / gb nullable in
+ * split_grad).                                                                    */
+int brv_spec_split(const void* X, int64_t n, int mode, float eps, float* a, float* b,
+                   void* stream);
+int brv_spec_join(const float* a, const float* b, int64_t n, int mode, void* X,
+                  void* stream);
+int brv_spec_split_grad(const float* ga, const float* gb, const void* X, int64_t n,
+                        int mode, float eps, void* gX, void* stream);
+int brv_spec_join_grad(const void* gX, const float* a, const float* b, int64_t n, int mode,
+                       float* ga, float* gb, void* stream);
 
 #ifdef __cplusplus
 }

@@ -204,3 +204,38 @@ def test_static_normalizer_state_dict_matches_reference_layout():
     assert sd['mean'].shape == (384, 1) and sd['std'].shape == (384, 1)
     front = brv.ffnn.FFNNFrontEnd()
     assert front.input_size == 384
+
+
+def test_metric_wrappers_mirror_reference_checks():
+    """brever/metrics.py:112-150: registry names, `_check_input` shapes / defaults / errors.  When
+    the reference tree is present its own `_check_input` source is executed next to ours."""
+    import ast
+    import os
+    import torch
+    from brever_b200 import metrics as M
+    assert set(M.MetricRegistry.keys()) == {'snr', 'sisnr'}
+    x, y = torch.zeros(3, 50), torch.zeros(3, 50)
+    fx, fy, lengths, unbatched = M._check_input(x, y, None)
+    assert fx.shape == (3, 1, 50) and fy.shape == (3, 1, 50) and not unbatched
+    assert lengths.tolist() == [50, 50, 50]
+    fx, _, lengths, unbatched = M._check_input(x[0], y[0], None)
+    assert fx.shape == (1, 1, 50) and unbatched and lengths.tolist() == [50]
+    cases = [(x, y[:2], None), (x[None], y[None], None), (x, y, [50, 50]), (x, y, [50, 51, 2])]
+    for a, b, ln in cases:
+        with pytest.raises(ValueError):
+            M._check_input(a, b, ln)
+    ref_path = '/root/reference/brever/metrics.py'
+    if os.path.exists(ref_path):
+        tree = ast.parse(open(ref_path).read())
+        fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == '_check_input'][0]
+        ns = {'torch': torch}
+        exec(compile(ast.Module([fn], []), ref_path, 'exec'), ns)
+        for a, b, ln in cases:
+            with pytest.raises(ValueError) as e_ref:
+                ns['_check_input'](a, b, ln)
+            with pytest.raises(ValueError) as e_new:
+                M._check_input(a, b, ln)
+            assert str(e_ref.value) == str(e_new.value)
+        for a, b, ln in [(x, y, None), (x[0], y[0], None), (x, y, torch.tensor([50, 10, 3]))]:
+            r, n = ns['_check_input'](a, b, ln), M._check_input(a, b, ln)
+            assert r[0].shape == n[0].shape and r[3] == n[3] and list(r[2]) == list(n[2])

@@ -688,3 +688,89 @@ def test_criterion_workspace_reuse_across_layouts():
     lt = torch.full((32,), 8000)
     pit = brv.sisnr(two_x.to(DEV), two_y.to(DEV), lt)
     assert np.allclose(cpu(pit), P.sisnr(two_x, two_y, lt).numpy(), atol=1e-3)
+
+
+def test_return_and_input_types_fused():
+    """stft.py:91-110 `return_type` / `input_type` and MetricGAN-OKD's log1p / expm1 wrappers
+    (metricganokd.py:185-195) through brv_spec_split / brv_spec_join: values, strides and
+    gradients against the eager torch ops the reference runs."""
+    from brever_b200.modules import specfmt
+    stft = brv.STFT(512, 128)
+    x = randn((2, 3, 3000), 5).to(DEV)
+    spec = stft(x)
+    re, im = stft(x, return_type='real_imag')
+    assert torch.equal(re, spec.real) and torch.equal(im, spec.imag)
+    mag, ph = stft(x, return_type='mag_phase')
+    assert mag.shape == spec.shape and mag.stride() == spec.abs().stride()
+    assert torch.allclose(mag, spec.abs(), rtol=2e-6, atol=0)
+    assert torch.allclose(ph, spec.angle(), rtol=0, atol=2e-6)
+    y = stft.backward(spec)
+    assert torch.allclose(stft.backward((mag, ph), input_type='mag_phase'), y, atol=2e-6)
+    assert torch.equal(stft.backward((re, im), input_type='real_imag'), y)
+    # planes in the layout a network produces (bin-major contiguous) go through as well
+    assert torch.allclose(stft.backward((mag.contiguous(), ph.contiguous()), input_type='mag_phase'), y, atol=2e-6)
+    eps = 1e-7
+    a, b = specfmt.split(spec, 'log1p_mag_phase', eps)
+    assert torch.allclose(a, torch.log1p(spec.abs() + eps), rtol=2e-6, atol=1e-7)
+    back = specfmt.join(a, b, 'log1p_mag_phase')
+    ref = torch.expm1(a) * torch.exp(1j * b)
+    assert rel_err(cpu(back), cpu(ref))[0] < 2e-6
+    with pytest.raises(ValueError):
+        specfmt.split(spec, 'polar')
+    # gradients against torch autograd through the reference's eager ops
+    for kind in ('real_imag', 'mag_phase', 'log1p_mag_phase'):
+        X = crandn((2, 40, 30), 3).to(DEV)
+        w1, w2 = randn((2, 40, 30), 4).to(DEV), randn((2, 40, 30), 6).to(DEV)
+
+        def ref_split(X):
+            if kind == 'real_imag':
+                return X.real, X.imag
+            m = X.abs()
+            return (torch.log1p(m + eps) if kind == 'log1p_mag_phase' else m), X.angle()
+        Xa, Xb = X.clone().requires_grad_(True), X.clone().requires_grad_(True)
+        pa = specfmt.split(Xa, kind, eps)
+        (pa[0] * w1 + pa[1] * w2).sum().backward()
+        pb = ref_split(Xb)
+        (pb[0] * w1 + pb[1] * w2).sum().backward()
+        assert rel_err(cpu(Xa.grad), cpu(Xb.grad))[0] < 1e-5, kind
+        m0, p0 = randn((2, 40, 30), 8).abs().to(DEV) + 0.1, randn((2, 40, 30), 9).to(DEV)
+        W = crandn((2, 40, 30), 10).to(DEV)
+        outs = []
+        for fn in ('ours', 'torch'):
+            m, p = m0.clone().requires_grad_(True), p0.clone().requires_grad_(True)
+            if fn == 'ours':
+                Z = specfmt.join(m, p, kind)
+            elif kind == 'real_imag':
+                Z = torch.complex(m, p)
+            else:
+                Z = torch.polar(torch.expm1(m) if kind == 'log1p_mag_phase' else m, p)
+            (Z * W).real.sum().backward()
+            outs.append((m.grad, p.grad))
+        assert rel_err(cpu(outs[0][0]), cpu(outs[1][0]))[0] < 1e-5, kind
+        assert rel_err(cpu(outs[0][1]), cpu(outs[1][1]))[0] < 1e-5, kind
+
+
+def test_lazy_conjugate_inputs_are_resolved():
+    """A lazily conjugated spectrogram (conj bit set, memory un-conjugated) must be read as its
+    conjugate: raw data pointers go to the kernels."""
+    stft = brv.STFT(256, 64)
+    spec = crandn((2, 129, 50), 12).to(DEV)
+    lazy = spec.conj()
+    assert lazy.is_conj()
+    assert torch.equal(stft.backward(lazy), stft.backward(lazy.resolve_conj()))
+    fe = brv.FeatureExtractor(features=['logfbe'], mel_fb=brv.MelFilterbank(n_fft=256))
+    four = crandn((1, 2, 129, 20), 13).to(DEV)
+    assert torch.equal(fe(four.conj()), fe(four.conj().resolve_conj()))
+
+
+def test_metric_wrappers():
+    """brever/metrics.py:112-123: negated criteria, default lengths, .item() for 1-D input."""
+    x, y = randn((4, 3000), 21), randn((4, 3000), 22)
+    lengths = torch.tensor([3000, 2500, 100, 3000])
+    for name, port in (('snr', P.snr), ('sisnr', P.sisnr)):
+        fn = brv.metrics.MetricRegistry.get(name)
+        out = fn(x.to(DEV), y.to(DEV), lengths)
+        ref = -port(x[:, None], y[:, None], lengths)
+        assert out.shape == (4,) and np.allclose(cpu(out), ref.numpy(), atol=5e-5)
+        one = fn(x[0].to(DEV), y[0].to(DEV))
+        assert isinstance(one, float) and abs(one - float(ref[0])) < 5e-5

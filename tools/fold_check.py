@@ -91,7 +91,7 @@ def check_inverse():
 
 def bench():
     # variant 0: transposed strip kernels; 4: one-tile-per-TMEM kernels; 1: dense contraction
-    variants = [int(v) for v in os.environ.get('FOLD_CHECK_VARIANTS', '0,4').split(',')]
+    variants = [int(v) for v in os.environ.get("FOLD_CHECK_VARIANTS", "0,4").split(",")]
     for name, shape, kw in [('cfg2', (64, 64000), dict(frame_length=512, hop_length=128)),
                             ('cfg1', (32, 64000), dict(frame_length=512, hop_length=256)),
                             ('cfg4', (128, 128000), dict(frame_length=510, hop_length=128, normalized=False,

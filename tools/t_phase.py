@@ -27,7 +27,7 @@ def stamps():
 
 
 WAITS = {0: ('loader/scout', ['slot/span empty', 'scout bar', '', '']),
-         1: ('builder', ['span/scale ready', 'ri_empty', 'stage empty', 'builder bar']),
+         1: ('builder', ['fwd: window+fold | inv: scale ready', 'fwd: split+store', 'stage empty', 'fwd: fence+arrive | inv: bar']),
          2: ('mma', ['tmem_empty', 'stage full', '', '']),
          3: ('epilogue', ['ri_full', 'tmem_full', 'epilogue bar', '']),
          4: ('tma', ['stage empty', '', '', ''])}
@@ -79,6 +79,7 @@ def main():
                              (512, 64000))]:
         stft = brv.STFT(**kw)
         x = 0.05 * torch.randn(*shape, device=dev)
+        _lib.lib().brv_set_tc_variant(int(os.environ.get('T_PHASE_VARIANT', '0')))
         for _ in range(3):
             spec = stft(x)
             stft.backward(spec)
