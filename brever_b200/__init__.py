@@ -8,13 +8,14 @@ Drop-in replacements for the hot-path classes of philgzl/brever:
 backed by hand-written CUDA kernels behind a C ABI (include/brever_b200.h).
 CUDA tensors only; there is no CPU fallback.
 """
-from . import criterion, ffnn, metrics, modules
+from . import criterion, ffnn, manner, metrics, modules, transforms
 from .criterion import (CriterionRegistry, MultiResYuLoss, apply_mask, init_criterion, mse,
                         sisnr, snr)
 from .modules import STFT, ConvSTFT, FeatureExtractor, MelFilterbank
 from .registry import Registry
+from .transforms import transform_batched
 
 __version__ = '0.1.0'
 __all__ = ['STFT', 'ConvSTFT', 'MelFilterbank', 'FeatureExtractor', 'CriterionRegistry',
            'init_criterion', 'sisnr', 'snr', 'mse', 'MultiResYuLoss', 'apply_mask', 'Registry',
-           'criterion', 'ffnn', 'metrics', 'modules']
+           'criterion', 'ffnn', 'manner', 'metrics', 'modules', 'transforms', 'transform_batched']

@@ -77,6 +77,11 @@ PROTOTYPES = {
                                _i64, _i64, _i64, _ptr, _ptr]),
     'brv_mag_l1_forward': (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _sz, _ptr]),
     'brv_mag_l1_backward': (_int, [_ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr]),
+    'brv_stft_plan_set_framing': (_int, [_ptr, _int, _int]),
+    'brv_reflect_pad': (_int, [_ptr, _i64, _i64, _i64, _i64, _int, _int, _ptr, _ptr]),
+    'brv_reflect_pad_grad': (_int, [_ptr, _i64, _i64, _i64, _int, _int, _ptr, _ptr]),
+    'brv_mrstft_forward': (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr]),
+    'brv_mrstft_backward': (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr]),
     'brv_spec_split': (_int, [_ptr, _i64, _int, _f32, _ptr, _ptr, _ptr]),
     'brv_spec_join': (_int, [_ptr, _ptr, _i64, _int, _ptr, _ptr]),
     'brv_spec_split_grad': (_int, [_ptr, _ptr, _ptr, _i64, _int, _f32, _ptr, _ptr]),

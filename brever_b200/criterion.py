@@ -334,8 +334,8 @@ class MultiResYuLoss:
     kernels; the time-domain and spectral L1 sums are fused reductions (``brv_l1_forward``,
     ``brv_mag_l1_forward``), so no magnitude or difference tensor is materialised.  The
     gradient flows back through ``brv_mag_l1_backward`` into the STFT gradient kernel.
-    With ``scale_invariant=True`` the loss value is supported but not its gradient (the
-    derivative of the scaling factor is not implemented; no reference model enables it).
+    With ``scale_invariant=True`` the scaling factor comes from the fused moment kernel
+    without gradients, and from a few broadcast ops kept in the autograd graph with them.
     """
 
     def __init__(self, frame_lengths=[512], hop_lengths=None, time_domain_weight=0.5,
@@ -359,10 +359,14 @@ class MultiResYuLoss:
         x3, y3 = _rows(x), _rows(y)
         batch, rows, length = x3.shape
         scale = None
-        if self.scale_invariant:
-            if torch.is_grad_enabled() and x.requires_grad:
-                raise NotImplementedError(
-                    'gradient of the scale-invariant MultiResYuLoss is not implemented')
+        if self.scale_invariant and torch.is_grad_enabled() and x.requires_grad:
+            # the scaling factor depends on the estimate (criterion.py:207-211): keep it in the
+            # autograd graph -- d(a x)/dx = a g + <g, x> (y - 2 a x) / (sum x^2 + eps) comes out
+            # of these few broadcast ops on the masked rows; the L1 / STFT terms below see a x
+            xm, ym = apply_mask(x3, y3, lengths)
+            a = (xm * ym).sum(-1, keepdim=True) / (xm.pow(2).sum(-1, keepdim=True) + eps)
+            x3 = a * xm
+        elif self.scale_invariant:
             _, mom = _moments(x3, y3, lengths, True) if rows == 1 else (None, None)
             if mom is None:     # pairwise moments are S x S: take the matched pairs directly
                 xm, ym = apply_mask(x3, y3, lengths)

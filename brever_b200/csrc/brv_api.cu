@@ -142,6 +142,8 @@ extern "C" int brv_istft_forward(const brv_stft_plan* p, const void* X, int64_t 
                                  void* workspace, size_t workspace_bytes, void* stream) {
     BRV_REQUIRE(p && X, "null pointer argument");
     BRV_REQUIRE(n_signals >= 0 && n_frames >= 1, "bad shape");
+    if (!p->center)
+        return brv_fail(BRV_ERR_UNSUPPORTED, "the inverse transform is implemented for center=True plans only");
     int64_t out_len = 0;
     int rc = brv_istft_geometry(p, n_frames, &out_len);
     if (rc != BRV_OK) return rc;
@@ -171,6 +173,8 @@ extern "C" int brv_istft_forward_grad(const brv_stft_plan* p, const float* gy, i
                                       int64_t n_frames, void* gX, void* workspace,
                                       size_t workspace_bytes, void* stream) {
     BRV_REQUIRE(p && gy && gX, "null pointer argument");
+    if (!p->center)
+        return brv_fail(BRV_ERR_UNSUPPORTED, "the inverse transform is implemented for center=True plans only");
     if (p->compression != 1.0)
         return brv_fail(BRV_ERR_UNSUPPORTED,
                         "gradient of the decompressing iSTFT (compression_factor != 1) is not "

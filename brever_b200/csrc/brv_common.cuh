@@ -41,6 +41,8 @@ struct brv_stft_plan {
     int n_bins;       // bins produced by the forward transform (N/2+1 or N)
     int n_bins_inv;   // bins consumed by the inverse (always N/2+1)
     int normalized, onesided;
+    int center;       // frames start n_fft/2 before t*hop (torch.stft center=True) or at t*hop
+    int pad_frames;   // right-pad to whole frames first (STFT.pad, stft.py:140-144) or floor framing
     double compression, scale, norm;  // norm = sqrt(sum w^2) or 1
     int device;
     std::vector<double> window;       // zero-padded, centred, n_fft points
@@ -60,6 +62,7 @@ struct brv_stft_plan {
 };
 
 int brv_check_nola(const brv_stft_plan* p, int64_t n_frames);
+static inline int brv_left(const brv_stft_plan* p) { return p->center ? p->n_fft / 2 : 0; }
 
 // simt (generic) path, brv_stft_simt.cu
 int brv_simt_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig,

@@ -293,6 +293,85 @@ __global__ void mag_l1_grad_kernel(const float2* __restrict__ X, const float2* _
     }
 }
 
+// MANNER's multi-resolution STFT loss (models/manner/stft_loss.py:22-77) on two spectrograms of the
+// same resolution: with m(.) = sqrt(max(re^2 + im^2, 1e-7)) the per-signal sums
+//   s0 = sum (m(Y) - m(X))^2   s1 = sum m(Y)^2   s2 = sum |log m(Y) - log m(X)|
+// (spectral convergence = sqrt(s0 / s1), log-magnitude = s2 / n); double accumulation.
+constexpr float MR_CLAMP = 1e-7f;
+__global__ void __launch_bounds__(CR_THREADS)
+mrstft_sums_kernel(const float2* __restrict__ X, const float2* __restrict__ Y, int64_t n_elems,
+                   double* __restrict__ sums) {
+    const int64_t sig = blockIdx.y;
+    const float2* xp = X + sig * n_elems;
+    const float2* yp = Y + sig * n_elems;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int64_t i0 = (int64_t)blockIdx.x * (4 * CR_THREADS); i0 < n_elems;
+         i0 += (int64_t)gridDim.x * (4 * CR_THREADS)) {
+        float2 a[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * CR_THREADS + threadIdx.x;
+            a[u] = i < n_elems ? __ldcs(xp + i) : make_float2(0.f, 0.f);
+            c[u] = i < n_elems ? __ldcs(yp + i) : make_float2(0.f, 0.f);
+        }
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u * CR_THREADS + threadIdx.x < n_elems) {
+                const float px = fmaxf(a[u].x * a[u].x + a[u].y * a[u].y, MR_CLAMP);
+                const float py = fmaxf(c[u].x * c[u].x + c[u].y * c[u].y, MR_CLAMP);
+                const float mx = sqrtf(px), my = sqrtf(py);
+                t0 += (my - mx) * (my - mx);
+                t1 += py;
+                t2 += fabsf(0.5f * (logf(py) - logf(px)));
+            }
+        }
+        a0 += t0;
+        a1 += t1;
+        a2 += t2;
+    }
+    __shared__ double red[3][CR_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    const int w = threadIdx.x / 32;
+    if ((threadIdx.x & 31) == 0) {
+        red[0][w] = a0;
+        red[1][w] = a1;
+        red[2][w] = a2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0;
+        for (int k = 0; k < CR_THREADS / 32; ++k) t += red[threadIdx.x][k];
+        atomicAdd(sums + sig * 3 + threadIdx.x, t);
+    }
+}
+
+// gX = (k_sc (m(X) - m(Y)) + k_mag sign(m(X) - m(Y)) / m(X)) X / m(X); zero where the clamp is active
+__global__ void mrstft_grad_kernel(const float2* __restrict__ X, const float2* __restrict__ Y,
+                                   const float* __restrict__ k_sc, const float* __restrict__ k_mag,
+                                   int64_t n_elems, float2* __restrict__ gX) {
+    const int64_t sig = blockIdx.y;
+    const float ks = k_sc[sig], km = k_mag[sig];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 a = __ldcs(X + sig * n_elems + i), c = __ldcs(Y + sig * n_elems + i);
+        const float px = a.x * a.x + a.y * a.y;
+        float2 g = make_float2(0.f, 0.f);
+        if (px > MR_CLAMP) {
+            const float mx = sqrtf(px), my = sqrtf(fmaxf(c.x * c.x + c.y * c.y, MR_CLAMP));
+            const float d = mx - my;
+            const float k = (ks * d + (d > 0.f ? km : (d < 0.f ? -km : 0.f)) / mx) / mx;
+            g = make_float2(k * a.x, k * a.y);
+        }
+        gX[sig * n_elems + i] = g;
+    }
+}
+
 // gx[row, n] = coef[row] * sign(s x - y) for n < lengths[b], else 0
 __global__ void l1_rows_grad_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                     const int64_t* __restrict__ lengths,
@@ -600,6 +679,37 @@ extern "C" int brv_mag_l1_backward(const void* X, const void* Y, const float* co
     mag_l1_grad_kernel<<<dim3(blocks, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(
         (const float2*)X, (const float2*)Y, coef, n_elems, (float2*)gX);
     BRV_LAUNCH_CHECK("mag_l1_grad_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_mrstft_forward(const void* X, const void* Y, int64_t n_signals, int64_t n_elems,
+                                  double* sums, void* stream) {
+    BRV_REQUIRE(n_signals >= 0 && n_elems >= 0, "bad shape");
+    if (n_signals == 0) return BRV_OK;
+    BRV_REQUIRE(sums && (n_elems == 0 || (X && Y)), "null pointer argument");
+    BRV_REQUIRE(n_signals < 65536, "more than 65535 signals per call");
+    BRV_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_signals * 3 * sizeof(double), (cudaStream_t)stream));
+    if (n_elems == 0) return BRV_OK;
+    int64_t blocks = brv_ceil_div(n_elems, 4 * CR_THREADS);
+    const int64_t cap = brv_ceil_div(148 * 8, n_signals);          // ~8 CTAs per SM in total
+    if (blocks > cap) blocks = cap < 1 ? 1 : cap;
+    mrstft_sums_kernel<<<dim3((unsigned)blocks, (unsigned)n_signals), CR_THREADS, 0, (cudaStream_t)stream>>>(
+        (const float2*)X, (const float2*)Y, n_elems, sums);
+    BRV_LAUNCH_CHECK("mrstft_sums_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_mrstft_backward(const void* X, const void* Y, const float* k_sc, const float* k_mag,
+                                   int64_t n_signals, int64_t n_elems, void* gX, void* stream) {
+    BRV_REQUIRE(n_signals >= 0 && n_elems >= 0, "bad shape");
+    if (n_signals == 0 || n_elems == 0) return BRV_OK;
+    BRV_REQUIRE(X && Y && k_sc && k_mag && gX, "null pointer argument");
+    BRV_REQUIRE(n_signals < 65536, "more than 65535 signals per call");
+    unsigned blocks = (unsigned)brv_ceil_div(n_elems, 256 * 8);
+    if (blocks > 4096) blocks = 4096;
+    mrstft_grad_kernel<<<dim3(blocks, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(
+        (const float2*)X, (const float2*)Y, k_sc, k_mag, n_elems, (float2*)gX);
+    BRV_LAUNCH_CHECK("mrstft_grad_kernel");
     return BRV_OK;
 }
 

@@ -110,6 +110,8 @@ extern "C" int brv_stft_plan_create(brv_stft_plan** out, int frame_length,
     p->n_fft = n_fft;
     p->onesided = onesided ? 1 : 0;
     p->normalized = normalized ? 1 : 0;
+    p->center = 1;
+    p->pad_frames = 1;
     p->n_bins = onesided ? n_fft / 2 + 1 : n_fft;
     p->n_bins_inv = n_fft / 2 + 1;
     p->compression = compression_factor;
@@ -206,11 +208,93 @@ extern "C" int brv_stft_geometry(const brv_stft_plan* p, int64_t samples,
     // stft.py:146-149: ceil(max(S - L, 0) / H) + 1 frames before centre padding
     int64_t over = samples > p->frame_length ? samples - p->frame_length : 0;
     int64_t frames0 = brv_ceil_div(over, p->hop) + 1;
-    int64_t pad = (frames0 - 1) * p->hop + p->frame_length - samples;  // stft.py:143
-    int64_t padded = samples + pad + 2 * (int64_t)(p->n_fft / 2);      // centre pad
+    int64_t pad = p->pad_frames ? (frames0 - 1) * p->hop + p->frame_length - samples : 0;  // stft.py:143
+    int64_t padded = samples + pad + 2 * (int64_t)brv_left(p);         // centre pad
+    BRV_REQUIRE(padded >= p->n_fft, "input (%lld samples) shorter than one frame of %d",
+                (long long)samples, p->n_fft);
     if (n_frames) *n_frames = 1 + (padded - p->n_fft) / p->hop;
     if (n_bins) *n_bins = p->n_bins;
     if (pad_right) *pad_right = pad;
+    return BRV_OK;
+}
+
+extern "C" int brv_stft_plan_set_framing(brv_stft_plan* p, int center, int pad_to_frames) {
+    BRV_REQUIRE(p != nullptr, "plan is null");
+    p->center = center ? 1 : 0;
+    p->pad_frames = pad_to_frames ? 1 : 0;
+    return BRV_OK;
+}
+
+// out[s, j] = z[s, reflect(j - left)] where z is the signal right-padded to `padded` samples --
+// with zeros (right_reflect = 0) or by mirroring its tail (right_reflect = 1: STFT.pad uses
+// F.pad(mode=pad_mode), stft.py:140-144) -- and reflect() mirrors indices below 0 and beyond
+// padded - 1 without repeating the edge sample (torch.stft pad_mode='reflect', stft.py:66-77).
+__global__ void reflect_pad_kernel(const float* __restrict__ x, int64_t samples, int64_t x_stride,
+                                   int64_t padded, int left, int right_reflect,
+                                   float* __restrict__ out) {
+    const int64_t total = padded + 2 * (int64_t)left;
+    const int64_t sig = blockIdx.y;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = j - left;
+        if (r < 0) r = -r;
+        if (r >= padded) r = 2 * (padded - 1) - r;
+        if (r >= samples && right_reflect) r = 2 * (samples - 1) - r;
+        out[sig * total + j] = (r >= 0 && r < samples) ? __ldg(x + sig * x_stride + r) : 0.f;
+    }
+}
+// adjoint, as a gather: x[r] feeds z[r] and (right_reflect) z[2 (S - 1) - r]; z[q] feeds the padded
+// positions q + left, left - q (1 <= q <= left) and left + 2 (padded - 1) - q (right mirror)
+__global__ void reflect_pad_grad_kernel(const float* __restrict__ g, int64_t samples, int64_t padded,
+                                        int left, int right_reflect, float* __restrict__ gx) {
+    const int64_t total = padded + 2 * (int64_t)left;
+    const int64_t sig = blockIdx.y;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < samples;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const float* gs = g + sig * total;
+        float acc = 0.f;
+        for (int k = 0; k < 2; ++k) {
+            const int64_t q = k == 0 ? r : 2 * (samples - 1) - r;
+            if (k == 1 && !(right_reflect && q >= samples && q < padded)) continue;
+            acc += gs[q + left];
+            if (q >= 1 && q <= left) acc += gs[left - q];
+            const int64_t m = 2 * (padded - 1) - q;
+            if (m >= padded && m < padded + left) acc += gs[m + left];
+        }
+        gx[sig * samples + r] = acc;
+    }
+}
+
+extern "C" int brv_reflect_pad(const float* x, int64_t n_signals, int64_t samples, int64_t x_stride,
+                               int64_t padded, int left, int right_reflect, float* out, void* stream) {
+    BRV_REQUIRE(n_signals >= 0 && samples >= 0 && padded >= samples && left >= 0, "bad reflect-pad shape");
+    // torch raises for a mirror that is not shorter than the signal it mirrors
+    BRV_REQUIRE(left < padded || left == 0, "reflect padding (%d) must be smaller than the signal (%lld)",
+                left, (long long)padded);
+    BRV_REQUIRE(!right_reflect || padded - samples < samples || padded == samples,
+                "reflect padding (%lld) must be smaller than the signal (%lld)",
+                (long long)(padded - samples), (long long)samples);
+    if (n_signals == 0 || padded + 2 * (int64_t)left == 0) return BRV_OK;
+    BRV_REQUIRE(out && (x || samples == 0), "null pointer argument");
+    BRV_REQUIRE(n_signals < 65536, "more than 65535 signals per call");
+    const int64_t total = padded + 2 * (int64_t)left;
+    const unsigned blocks = (unsigned)(brv_ceil_div(total, 256) < 1024 ? brv_ceil_div(total, 256) : 1024);
+    reflect_pad_kernel<<<dim3(blocks, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(
+        x, samples, x_stride, padded, left, right_reflect, out);
+    BRV_LAUNCH_CHECK("reflect_pad_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_reflect_pad_grad(const float* g, int64_t n_signals, int64_t samples, int64_t padded,
+                                    int left, int right_reflect, float* gx, void* stream) {
+    BRV_REQUIRE(n_signals >= 0 && samples >= 0 && padded >= samples && left >= 0, "bad reflect-pad shape");
+    if (n_signals == 0 || samples == 0) return BRV_OK;
+    BRV_REQUIRE(g && gx, "null pointer argument");
+    BRV_REQUIRE(n_signals < 65536, "more than 65535 signals per call");
+    const unsigned blocks = (unsigned)(brv_ceil_div(samples, 256) < 1024 ? brv_ceil_div(samples, 256) : 1024);
+    reflect_pad_grad_kernel<<<dim3(blocks, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(
+        g, samples, padded, left, right_reflect, gx);
+    BRV_LAUNCH_CHECK("reflect_pad_grad_kernel");
     return BRV_OK;
 }
 

@@ -2142,7 +2142,7 @@ void brv_fold_plan_free(brv_stft_plan* p) {
 // loses to one CTA per tile.  Variant 5 forces it, variant 4 disables it.
 static bool fold_forward_uses_t(const brv_stft_plan* p, int64_t n_sig, int64_t n_frames, int origin) {
     const FoldPlan* fp = (const FoldPlan*)p->fold;
-    if (origin < 0) origin = p->n_fft / 2;
+    if (origin < 0) origin = brv_left(p);
     const int shift = p->hop % 4 == 0 ? (4 - (origin & 3)) & 3 : 0;
     if (ft_tile_frames(p->n_fft, p->hop, shift) < 16) return false;
     return g_brv_fold_variant == 5 ||
@@ -2158,7 +2158,7 @@ static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool c
     prm.n_bins = p->n_bins;
     prm.q = fp->q;
     prm.odd = fp->odd;
-    if (prm.origin < 0) prm.origin = p->n_fft / 2;
+    if (prm.origin < 0) prm.origin = brv_left(p);
     // 16-byte aligned span when the hop allows it (n_fft / 2 = 255 would otherwise force scalar loads)
     prm.shift = p->hop % 4 == 0 ? (4 - (prm.origin & 3)) & 3 : 0;
     prm.tmem_cols = fp->tmem_cols;
@@ -2291,7 +2291,7 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     prm.q = fp->q;
     prm.halo = 4 / fp->hq - 1;
     prm.adv = TILE_M - prm.halo;
-    if (prm.origin < 0) prm.origin = p->n_fft / 2;
+    if (prm.origin < 0) prm.origin = brv_left(p);
     prm.n_blocks = (int)brv_ceil_div(prm.origin + out_len, p->hop);
     prm.tiles_per_signal =
         prm.n_blocks <= TILE_M ? 1 : 1 + (int)brv_ceil_div(prm.n_blocks - TILE_M, prm.adv);

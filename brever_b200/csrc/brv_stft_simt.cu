@@ -169,14 +169,14 @@ __global__ void inv_envelope_kernel(const float* __restrict__ wsq, int n_fft, in
 
 // Overlap-add of the workspace frames at stride hop, centre trim, and either the
 // window-sum-square division (inverse) or a plain scale (adjoint of the forward).
-__global__ void overlap_add_kernel(const float* __restrict__ ws, int n_fft, int hop,
+__global__ void overlap_add_kernel(const float* __restrict__ ws, int n_fft, int hop, int left,
                                    int64_t n_frames, int64_t out_len,
                                    const float* __restrict__ inv_env, float scale,
                                    float* __restrict__ y) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t sig = blockIdx.y;
     if (i >= out_len) return;
-    int64_t pos = i + n_fft / 2;
+    int64_t pos = i + left;
     int64_t t_hi = pos / hop;
     if (t_hi > n_frames - 1) t_hi = n_frames - 1;
     int64_t t_lo = pos - n_fft + 1 <= 0 ? 0 : (pos - n_fft + hop) / hop;
@@ -204,7 +204,7 @@ int launch_gemm(ALoad a, const float* B, int K, int n_cols, int64_t n_sig,
 int brv_simt_stft_forward(const brv_stft_plan* p, const float* x, int64_t n_sig,
                           int64_t samples, int64_t x_stride, float2* out,
                           int64_t n_frames, cudaStream_t st) {
-    FrameLoader a{x, x_stride, samples, p->hop, p->n_fft / 2, nullptr};
+    FrameLoader a{x, x_stride, samples, p->hop, brv_left(p), nullptr};
     SpecEpilogue e{reinterpret_cast<float*>(out), n_frames, 2 * p->n_bins, 2 * p->n_bins,
                    (float)(p->compression - 1.0), (float)p->scale};
     return launch_gemm(a, p->basis_fwd, p->n_fft, 2 * p->n_bins, n_sig, n_frames, e, st);
@@ -251,7 +251,7 @@ int brv_overlap_add(const brv_stft_plan* p, const float* frames, int64_t n_sig, 
     }
     BRV_REQUIRE(n_sig < 65536, "more than 65535 signals per call");
     overlap_add_kernel<<<dim3(blocks, (unsigned)n_sig), threads, 0, st>>>(
-        frames, N, p->hop, n_frames, out_len, inverse ? inv_env : nullptr,
+        frames, N, p->hop, inverse ? N / 2 : brv_left(p), n_frames, out_len, inverse ? inv_env : nullptr,
         (float)p->scale, y);
     BRV_LAUNCH_CHECK("overlap_add_kernel");
     return BRV_OK;

@@ -68,6 +68,7 @@ struct TcParams {
     float* out;                  // fwd: (sig, T, n_bins) complex ; inv: (sig, T, n_fft) floats
     int64_t n_frames;
     int n_fft, hop, n_bins;
+    int left;                    // frame t starts `left` samples before t * hop (n_fft / 2 when centred)
     int k_blocks;                // ceil(K / BK)
     int col_blocks;              // packed columns / TILE_N
     int cols_pad;                // col_blocks * TILE_N (lo plane starts at this row)
@@ -239,7 +240,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap basis_map, const TcParams p) {
             const float* xs = p.x + sig * p.x_stride;
             // --- per-hop-block maxima over the samples this tile touches: one
             //     coalesced pass, warp-reduced, then max over the blocks of a frame
-            const int64_t span0 = t0 * p.hop - half;                   // first sample (may be < 0)
+            const int64_t span0 = t0 * p.hop - p.left;                 // first sample (may be < 0)
             const int span_len = (TILE_M - 1) * p.hop + p.n_fft;
             const bool vec = ((((uintptr_t)xs) & 15) == 0) && ((span0 & 3) == 0) && ((p.hop & 3) == 0);
             if (vec) {
@@ -283,7 +284,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap basis_map, const TcParams p) {
             scale = row_scale(__uint_as_float(mx));
             fsrc.xs = xs;
             fsrc.samples = p.samples;
-            fsrc.frame_start = t * p.hop - half;
+            fsrc.frame_start = t * p.hop - p.left;
             fsrc.n_fft = p.n_fft;
             fsrc.aligned = ((((uintptr_t)xs) & 15) == 0) && ((fsrc.frame_start & 3) == 0);
         } else {
@@ -459,6 +460,7 @@ void fill_common(TcParams& prm, const brv_stft_plan* p, const TcBasis& b, int64_
     prm.n_frames = n_frames;
     prm.n_fft = p->n_fft;
     prm.hop = p->hop;
+    prm.left = brv_left(p);
     prm.n_bins = p->n_bins;
     prm.k_blocks = b.k_pad / BK;
     prm.col_blocks = b.cols_pad / TILE_N;

@@ -66,6 +66,18 @@ def irm(foreground_mag, background_mag, mel_fb):
     return (1 + bg / (fg + eps)).pow(-0.5)
 
 
+def _frame_mask(x, frames):
+    """Zero the columns t >= frames[b] of ``(B, ..., T)`` (what collating per-item outputs does)."""
+    flat = x.reshape(x.shape[0], -1, x.shape[-1]).contiguous()
+    out = torch.empty_like(flat)
+    if flat.numel():
+        with _lib.on_device(flat.device):
+            _lib.check(_lib.lib().brv_apply_mask(
+                _lib.ptr(flat), _lib.ptr(frames), flat.shape[0], flat.shape[1], flat.shape[2],
+                _lib.ptr(out), _lib.stream_ptr(flat.device)))
+    return out.view(x.shape)
+
+
 class StaticNormalizer(nn.Module):
     """``(x - mean) / std`` with ``(input_size, 1)`` buffers (ffnn.py:175-187)."""
 
@@ -158,6 +170,33 @@ class FFNNFrontEnd:
         labels = irm(foreground.abs(), background.abs(), self.mel_fb)
         labels = decimate(labels, self.decimation)
         return torch.cat([x, labels])
+
+    def transform_batched(self, batch, lengths):
+        """``FFNN.transform`` for a collated device batch, in one pass of the kernels.
+
+        The reference transforms a validation batch one utterance at a time on the device
+        and re-collates the results (``training.py:336-338``, ``data.py:408-491``); here
+        ``batch`` is the zero-padded ``(B, 2, C, L)`` tensor of (mixture, foreground) pairs
+        with ``lengths`` valid samples per item, and the result is what that loop followed
+        by ``_collate_fn`` returns: ``(B, input_size + n_labels, T')`` with the columns past
+        each item's own frame count zeroed, and the per-item frame counts."""
+        if batch.ndim != 4 or batch.shape[1] != 2:
+            raise ValueError(f'batch must be (B, 2, channels, samples), got {tuple(batch.shape)}')
+        lengths = torch.as_tensor(lengths).to(device=batch.device, dtype=torch.int64)
+        spec = self.stft(batch)                                  # (B, 2, C, F, T)
+        mix, foreground = spec[:, 0], spec[:, 1]
+        background = mix - foreground
+        x = self.features(mix)                                   # (B, input_size, T')
+        fe = self.feature_extractor
+        fg = fe.fbe(foreground, normalize=False, compression='none')     # mel(mean_c |X|^2)
+        bg = fe.fbe(background, normalize=False, compression='none')
+        labels = decimate((1 + bg / (fg + eps)).pow(-0.5), self.decimation)
+        out = torch.cat([x, labels], dim=1)
+        hop, fl = self.stft.hop_length, self.stft.frame_length
+        frames0 = (torch.clamp(lengths - fl, min=0) + hop - 1) // hop + 1       # STFT.frame_count
+        frames = 1 + ((frames0 - 1) * hop + fl + 2 * (self.stft.n_fft // 2) - self.stft.n_fft) // hop
+        out_frames = (frames + self.decimation - 1) // self.decimation
+        return _frame_mask(out, out_frames), out_frames
 
     def enhance(self, x, mask_fn, mean=None, std=None):
         """FFNN._enhance (ffnn.py:100-111); ``mask_fn`` is the network."""

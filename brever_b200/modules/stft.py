@@ -10,8 +10,8 @@ Deliberate differences:
   * CUDA tensors only — a CPU tensor raises instead of silently running torch;
   * ``backward`` never modifies its input (the reference divides a complex
     input by ``scale_factor`` in place, stft.py:114);
-  * ``center=True`` / ``pad_mode='constant'`` only (the reference's own
-    docstring says to always use ``center=True``).
+  * ``pad_mode`` ``'constant'`` and ``'reflect'``; ``center=False`` for the forward transform
+    and its gradient only (the reference's own docstring says to always use ``center=True``).
 """
 import ctypes
 import functools
@@ -43,6 +43,44 @@ class _StftFunction(torch.autograd.Function):
         return ctx.stft._forward_grad_raw(grad, ctx.samples), None
 
 
+class _ReflectPadFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, padded, left, right_reflect):
+        ctx.geom = (x2d.shape[-1], padded, left, right_reflect)
+        return _reflect_pad_raw(x2d, padded, left, right_reflect)
+
+    @staticmethod
+    def backward(ctx, grad):
+        samples, padded, left, right_reflect = ctx.geom
+        grad = grad.float().contiguous()
+        gx = torch.empty((grad.shape[0], samples), dtype=torch.float32, device=grad.device)
+        with _lib.on_device(grad.device):
+            _lib.check(_lib.lib().brv_reflect_pad_grad(
+                _lib.ptr(grad), grad.shape[0], samples, padded, left, int(right_reflect),
+                _lib.ptr(gx), _lib.stream_ptr(grad.device)))
+        return gx, None, None, None
+
+
+def _reflect_pad_raw(x2d, padded, left, right_reflect):
+    n_sig, samples = x2d.shape
+    if x2d.stride(-1) != 1:
+        x2d = x2d.contiguous()
+    if left >= padded > 0 or (right_reflect and padded - samples >= samples > 0):
+        raise RuntimeError('Padding size should be less than the corresponding input dimension')
+    out = torch.empty((n_sig, padded + 2 * left), dtype=torch.float32, device=x2d.device)
+    with _lib.on_device(x2d.device):
+        _lib.check(_lib.lib().brv_reflect_pad(
+            _lib.ptr(x2d), n_sig, samples, x2d.stride(0) if n_sig > 1 else samples, padded, left,
+            int(right_reflect), _lib.ptr(out), _lib.stream_ptr(x2d.device)))
+    return out
+
+
+def _reflect_pad(x2d, padded, left, right_reflect):
+    if torch.is_grad_enabled() and x2d.requires_grad:
+        return _ReflectPadFunction.apply(x2d, padded, left, right_reflect)
+    return _reflect_pad_raw(x2d, padded, left, right_reflect)
+
+
 class _IstftFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec3d, stft):
@@ -70,10 +108,12 @@ class STFT:
                  center=True, pad_mode='constant', normalized=True,
                  onesided=True, compression_factor=1, scale_factor=1,
                  n_fft=None):
-        if not center or pad_mode != 'constant':
+        if pad_mode not in ('constant', 'reflect'):
             raise NotImplementedError(
-                "brever_b200.STFT supports center=True, pad_mode='constant' "
-                'only (the configuration every reference model uses)')
+                "brever_b200.STFT supports pad_mode='constant' and 'reflect' "
+                f'(got {pad_mode!r}; every reference model uses constant)')
+        # raw torch.stft framing (no STFT.pad to whole frames): MANNER's loss (manner.py)
+        self._raw_framing = False
         self.frame_length = frame_length
         self.hop_length = hop_length
         self.center = center
@@ -109,8 +149,15 @@ class STFT:
         except Exception:
             pass
 
-    def _plan(self, device):
-        key = device.index if device.index is not None else torch.cuda.current_device()
+    def _plan(self, device, inverse=False):
+        """Device plan; the forward plan carries the framing of this object (centre / reflect
+        padding / raw framing), the inverse plan is always the centred one torch.istft needs."""
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        # reflect padding is materialised by brv_reflect_pad: the kernels then see plain frames
+        center = bool(self.center) and self.pad_mode == 'constant'
+        pad_frames = self.pad_mode == 'constant' and not self._raw_framing
+        default = center and pad_frames
+        key = index if (inverse or default) else (index, 'framed')
         plan = self._plans.get(key)
         if plan is None:
             win = self.window.detach().to('cpu', torch.float64).contiguous()
@@ -125,6 +172,8 @@ class STFT:
                     ctypes.c_void_p(win.data_ptr()), int(bool(self.normalized)),
                     int(bool(self.onesided)), float(self.compression_factor),
                     float(self.scale_factor)))
+                if key != index:
+                    _lib.check(_lib.lib().brv_stft_plan_set_framing(handle, int(center), int(pad_frames)))
             plan = self._plans[key] = handle
         return plan
 
@@ -140,10 +189,14 @@ class STFT:
             + self.frame_length - samples
         return torch.nn.functional.pad(x, (0, padding), mode=self.pad_mode)
 
+    def _right_pad(self, samples):
+        if self._raw_framing:
+            return 0
+        return (self.frame_count(samples) - 1) * self.hop_length + self.frame_length - samples
+
     def n_frames(self, samples):
         """Frames the forward transform returns for `samples` input samples."""
-        padded = samples + (self.frame_count(samples) - 1) * self.hop_length \
-            + self.frame_length - samples + 2 * (self.n_fft // 2)
+        padded = samples + self._right_pad(samples) + (2 * (self.n_fft // 2) if self.center else 0)
         return 1 + (padded - self.n_fft) // self.hop_length
 
     @property
@@ -156,7 +209,8 @@ class STFT:
         n_sig, samples = x2d.shape
         if x2d.stride(-1) != 1:
             x2d = x2d.contiguous()
-        frames = self.n_frames(samples)
+        frames = self.n_frames(samples) if self.pad_mode == 'constant' else \
+            1 + (samples - self.n_fft) // self.hop_length      # reflect: x2d is already padded
         out = torch.empty((n_sig, frames, self.n_bins), dtype=torch.complex64,
                           device=x2d.device)
         if n_sig:
@@ -192,8 +246,10 @@ class STFT:
         out_len = self.hop_length * (frames - 1) + self.n_fft - 2 * (self.n_fft // 2)
         y = torch.empty((n_sig, out_len), dtype=torch.float32, device=spec3d.device)
         lib = _lib.lib()
+        if not self.center:
+            raise NotImplementedError('STFT.backward is implemented for center=True only')
         with _lib.on_device(spec3d.device):
-            plan = self._plan(spec3d.device)
+            plan = self._plan(spec3d.device, inverse=True)
             nbytes = lib.brv_stft_workspace_bytes_op(plan, n_sig, frames, 0)
             ws = _lib.workspace(nbytes, spec3d.device)
             _lib.check(lib.brv_istft_forward(
@@ -210,7 +266,7 @@ class STFT:
         if n_sig:
             lib = _lib.lib()
             with _lib.on_device(grad.device):
-                plan = self._plan(grad.device)
+                plan = self._plan(grad.device, inverse=True)
                 nbytes = lib.brv_stft_workspace_bytes_op(plan, n_sig, frames, 2)
                 ws = _lib.workspace(nbytes, grad.device)
                 _lib.check(lib.brv_istft_forward_grad(
@@ -234,6 +290,11 @@ class STFT:
         x2d = x.reshape(-1, x.shape[-1])
         if x2d.dtype != torch.float32:
             x2d = x2d.float()  # fp16/bf16 (AMP) and fp64 compute in fp32
+        if self.pad_mode == 'reflect':
+            # STFT.pad mirrors the tail (F.pad(mode=pad_mode), stft.py:140-144), torch.stft the
+            # centre padding: one gather kernel materialises both
+            x2d = _reflect_pad(x2d, x2d.shape[-1] + self._right_pad(x2d.shape[-1]),
+                               self.n_fft // 2 if self.center else 0, not self._raw_framing)
         if torch.is_grad_enabled() and x2d.requires_grad:
             spec = _StftFunction.apply(x2d, self)
         else:

@@ -68,12 +68,28 @@ int brv_device_query(int* sm_count, int* cc_major, int* cc_minor);
  * (scipy.signal.get_window(name, frame_length), periodic).  The plan owns the
  * device-resident DFT bases (window, normalisation 1/sqrt(sum w^2) and the
  * Hermitian weights folded in) on the device that is current at creation.
- * center=True and pad_mode='constant' are the only modes (stft.py:33).       */
+ * Created for center=True, pad_mode='constant' (stft.py:33); see
+ * brv_stft_plan_set_framing / brv_reflect_pad for the other modes.           */
 int brv_stft_plan_create(brv_stft_plan** plan, int frame_length, int hop_length,
                          int n_fft, const double* window, int normalized,
                          int onesided, double compression_factor,
                          double scale_factor);
 int brv_stft_plan_destroy(brv_stft_plan* plan);
+/* Framing of the forward transform, to be set right after creation (default 1, 1 = the
+ * reference's STFT with center=True): center = 0 starts frame t at sample t * hop
+ * (torch.stft center=False, stft.py:66-77); pad_to_frames = 0 skips STFT.pad's right
+ * zero padding (stft.py:140-144), i.e. raw torch.stft framing, T = 1 + (S' - n_fft) / hop
+ * -- what MANNER's loss uses (models/manner/stft_loss.py:33).  The inverse entry points
+ * need center = 1.                                                                    */
+int brv_stft_plan_set_framing(brv_stft_plan* plan, int center, int pad_to_frames);
+/* torch.stft's pad_mode='reflect': out (n_signals, padded + 2 * left) = the signal, right
+ * padded to `padded` samples (zeros, or its mirrored tail when right_reflect: STFT.pad uses
+ * F.pad(mode=pad_mode), stft.py:140-144), mirrored by `left` samples on both sides (edge
+ * sample not repeated); brv_reflect_pad_grad is its adjoint (gx: (n_signals, samples) dense). */
+int brv_reflect_pad(const float* x, int64_t n_signals, int64_t samples, int64_t x_stride,
+                    int64_t padded, int left, int right_reflect, float* out, void* stream);
+int brv_reflect_pad_grad(const float* g, int64_t n_signals, int64_t samples, int64_t padded,
+                         int left, int right_reflect, float* gx, void* stream);
 
 /* Integer frame arithmetic of STFT.pad / STFT.frame_count + torch.stft
  * (stft.py:140-149): for `samples` input samples returns the number of frames
@@ -312,6 +328,19 @@ int brv_criterion_backward(const float* x, const float* y, const int64_t* length
  * themselves: out[b, ..., n] = n < lengths[b] ? x[b, ..., n] : 0.            */
 int brv_apply_mask(const float* x, const int64_t* lengths, int64_t n_batch,
                    int64_t inner, int64_t length, float* out, void* stream);
+
+/* ---- MANNER's multi-resolution STFT loss (models/manner/stft_loss.py:22-151) ----
+ * One resolution, two spectrograms (n_signals, n_elems) complex64 dense: with
+ * m(.) = sqrt(max(re^2 + im^2, 1e-7)) fills sums[s] = {sum (m(Y) - m(X))^2, sum m(Y)^2,
+ * sum |log m(Y) - log m(X)|} (float64; the entry zeroes `sums` itself), from which
+ * spectral convergence = sqrt(s0 / s1) and log-magnitude loss = s2 / n_elems.
+ * backward: gX = (k_sc (m(X) - m(Y)) + k_mag sign(m(X) - m(Y)) / m(X)) X / m(X), zero where
+ * the clamp is active, with per-signal coefficients k_sc = g_sc / sqrt(s0 s1),
+ * k_mag = g_mag / n_elems.                                                        */
+int brv_mrstft_forward(const void* X, const void* Y, int64_t n_signals, int64_t n_elems,
+                       double* sums, void* stream);
+int brv_mrstft_backward(const void* X, const void* Y, const float* k_sc, const float* k_mag,
+                        int64_t n_signals, int64_t n_elems, void* gX, void* stream);
 
 /* ---- spectrogram representations (stft.py:91-110, metricganokd.py:185-195) -----
  * One elementwise pass over n complex64 values and two float32 planes of the same

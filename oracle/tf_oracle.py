@@ -112,11 +112,13 @@ def _padded_window(window, frame_length, n_fft):
 # --------------------------------------------------------------------------- #
 def stft(x, frame_length=512, hop_length=256, window='hann', normalized=True,
          onesided=True, compression_factor=1.0, scale_factor=1.0, n_fft=None,
-         dtype=np.float64):
-    """STFT.forward, stft.py:59-89 (center=True, pad_mode='constant').
+         dtype=np.float64, center=True, pad_mode='constant', raw_framing=False):
+    """STFT.forward, stft.py:59-89.
 
     ``X[k, t] = sum_n w~[n] x~[t H + n] exp(-2 pi i k n / N)``, x~ the signal
-    zero-padded by ``right_padding`` on the right and ``N//2`` on both sides.
+    padded by ``right_padding`` on the right (``STFT.pad``: ``F.pad(mode=pad_mode)``,
+    stft.py:140-144; skipped with ``raw_framing``, i.e. plain ``torch.stft``) and, when
+    ``center``, by ``N//2`` on both sides in ``pad_mode`` ('constant' zeros or 'reflect').
     """
     n_fft = frame_length if n_fft is None else n_fft
     x = np.asarray(x)
@@ -126,10 +128,11 @@ def stft(x, frame_length=512, hop_length=256, window='hann', normalized=True,
     if isinstance(window, str) or window is None:
         window = get_window(window, frame_length)
     win = _padded_window(window, frame_length, n_fft).astype(dtype)
-    pad_r = right_padding(samples, frame_length, hop_length)
-    half = n_fft // 2
-    padded = np.zeros((sig.shape[0], samples + pad_r + 2 * half), dtype=dtype)
-    padded[:, half:half + samples] = sig
+    pad_r = 0 if raw_framing else right_padding(samples, frame_length, hop_length)
+    half = n_fft // 2 if center else 0
+    mode = {'constant': 'constant', 'reflect': 'reflect'}[pad_mode]
+    padded = np.pad(sig, ((0, 0), (0, pad_r)), mode=mode)
+    padded = np.pad(padded, ((0, 0), (half, half)), mode=mode)
     n_frames = 1 + (padded.shape[1] - n_fft) // hop_length
     idx = (np.arange(n_frames)[:, None] * hop_length
            + np.arange(n_fft)[None, :])
@@ -190,6 +193,68 @@ def istft(spec, frame_length=512, hop_length=256, window='hann',
         raise RuntimeError('window overlap add min: 1')  # torch NOLA check
     out = out / env
     return out.reshape(*lead, -1)
+
+
+def stft_grad(w, samples, frame_length=512, hop_length=256, window='hann', normalized=True,
+              scale_factor=1.0, n_fft=None, center=True, pad_mode='constant', raw_framing=False):
+    """Gradient of ``sum(Re X * Re w + Im X * Im w)`` w.r.t. the input of `stft` (no compression):
+    the adjoint of the linear map, built by applying `stft` to the unit impulses' images --
+    here simply via the real-linear structure: g = A^T w with A applied column by column
+    would be O(S^2); instead overlap-add the inverse-DFT-like frames and fold the padding."""
+    n_fft = frame_length if n_fft is None else n_fft
+    w = np.asarray(w, dtype=np.complex128)
+    lead = w.shape[:-2]
+    W = w.reshape(-1, *w.shape[-2:])                       # (sig, F, T)
+    if isinstance(window, str) or window is None:
+        window = get_window(window, frame_length)
+    win = _padded_window(window, frame_length, n_fft).astype(np.float64)
+    scale = scale_factor / (math.sqrt(float(np.sum(np.asarray(window, float) ** 2))) if normalized else 1.0)
+    pad_r = 0 if raw_framing else right_padding(samples, frame_length, hop_length)
+    half = n_fft // 2 if center else 0
+    total = samples + pad_r + 2 * half
+    n_frames = W.shape[-1]
+    # d/dframe of Re<rfft(frame), w> = Re(sum_k conj-weighted basis): irfft-like without 1/N
+    k = np.arange(W.shape[-2])[:, None]
+    n = np.arange(n_fft)[None, :]
+    ang = 2 * np.pi * k * n / n_fft
+    frames = (np.einsum('sft,fn->stn', W.real, np.cos(ang)) - np.einsum('sft,fn->stn', W.imag, np.sin(ang)))
+    frames = frames * win * scale
+    gp = np.zeros((W.shape[0], total))
+    for t in range(n_frames):
+        gp[:, t * hop_length:t * hop_length + n_fft] += frames[:, t]
+    # fold the paddings back (adjoint of np.pad): centre first, then the right padding
+    def unpad(g, left, right, length):
+        core = g[:, left:left + length].copy()
+        if pad_mode == 'reflect':
+            for j in range(left):                          # padded[j] = x[left - j]
+                core[:, left - j] += g[:, j]
+            for j in range(right):                         # padded[left + length + j] = x[length - 2 - j]
+                core[:, length - 2 - j] += g[:, left + length + j]
+        return core
+    g = unpad(gp, half, half, samples + pad_r)
+    g = unpad(g, 0, pad_r, samples)
+    return g.reshape(*lead, samples)
+
+
+def manner_stft_loss(x, y, fft_sizes=(1024, 2048, 512), hop_sizes=(120, 240, 50),
+                     win_lengths=(600, 1200, 240), factor_sc=0.1, factor_mag=0.1):
+    """MultiResolutionSTFTLoss, models/manner/stft_loss.py:22-151: per resolution raw
+    ``torch.stft`` (reflect centre padding, periodic Hann of win_length inside fft_size, no
+    normalisation), ``m = sqrt(max(re^2 + im^2, 1e-7))``, spectral convergence
+    ``||m_y - m_x||_F / ||m_y||_F`` and ``mean |log m_y - log m_x|`` per item; mean over the
+    resolutions, times the factors."""
+    sc_tot, mag_tot = 0.0, 0.0
+    for n_fft, hop, wl in zip(fft_sizes, hop_sizes, win_lengths):
+        kw = dict(frame_length=wl, hop_length=hop, n_fft=n_fft, window='hann', normalized=False,
+                  pad_mode='reflect', raw_framing=True)
+        mags = []
+        for sig in (x, y):
+            spec = stft(sig, **kw)
+            mags.append(np.sqrt(np.maximum(spec.real ** 2 + spec.imag ** 2, 1e-7)))
+        mx, my = mags
+        sc_tot = sc_tot + np.sqrt(((my - mx) ** 2).sum((-2, -1))) / np.sqrt((my ** 2).sum((-2, -1)))
+        mag_tot = mag_tot + np.abs(np.log(my) - np.log(mx)).mean((-2, -1))
+    return factor_sc * sc_tot / len(fft_sizes), factor_mag * mag_tot / len(fft_sizes)
 
 
 def _conv_filters(frame_length, hop_length, window, normalized):

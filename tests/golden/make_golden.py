@@ -286,6 +286,67 @@ def main():
             (crit(e, ref, lengths) * weight).sum().backward()
             out[f'crit_mry_{name}_grad'] = e.grad.numpy()
 
+    # ---- round 2: pad_mode / center variants of STFT.forward (stft.py:59-77,140-144) ----------
+    for tag, kw, shape, seed in [('reflect_512_128', dict(frame_length=512, hop_length=128, pad_mode='reflect'), (3, 3001), 700),
+                                 ('reflect_256_64', dict(frame_length=256, hop_length=64, pad_mode='reflect', normalized=False), (2, 2, 1500), 701),
+                                 ('nocenter_512_128', dict(frame_length=512, hop_length=128, center=False), (3, 3001), 702),
+                                 ('reflect_nocenter_400', dict(frame_length=400, hop_length=100, n_fft=512, center=False, pad_mode='reflect'), (2, 2777), 703)]:
+        st = STFT(**kw)
+        x = randn(shape, seed)
+        spec = st(x)
+        out[f'stft_{tag}'] = spec.numpy()
+        w = crandn(tuple(spec.shape), seed + 50)
+        xg = x.clone().requires_grad_(True)
+        sg = st(xg)
+        (sg.real * w.real + sg.imag * w.imag).sum().backward()
+        out[f'stft_{tag}_grad'] = xg.grad.numpy()
+        if kw.get('center', True):
+            out[f'stft_{tag}_back'] = st.backward(spec.clone()).numpy()
+
+    # ---- round 2: MANNER multi-resolution STFT loss (models/manner/stft_loss.py:22-151) --------
+    from brever.models.manner.stft_loss import MultiResolutionSTFTLoss
+    mx, my = 0.1 * randn((3, 8000), 710), 0.1 * randn((3, 8000), 711)
+    my = 0.7 * mx + 0.3 * my
+    my[2, 5000:] = 0.0                                       # silence: the clamp is active there
+    for tag, kw in (('def', {}), ('small', dict(fft_sizes=[512, 256], hop_sizes=[128, 64], win_lengths=[512, 200],
+                                                factor_sc=0.5, factor_mag=1.0))):
+        crit = MultiResolutionSTFTLoss(**kw)
+        e = mx.clone().requires_grad_(True)
+        sc, mag = crit(e, my)
+        out[f'manner_{tag}_sc'], out[f'manner_{tag}_mag'] = sc.detach().numpy(), mag.detach().numpy()
+        wsc, wmag = torch.tensor([1.0, -0.5, 2.0]), torch.tensor([0.3, 1.5, -1.0])
+        ((sc * wsc).sum() + (mag * wmag).sum()).backward()
+        out[f'manner_{tag}_grad'] = e.grad.numpy()
+
+    # ---- round 2: per-utterance transform + collate (training.py:336-338, data.py:408-491) ----
+    batch = 0.05 * randn((3, 2, 2, 4000), 720)
+    blen = [4000, 3000, 2345]
+    for i, n in enumerate(blen):
+        batch[i, ..., n:] = 0
+    for tag, mdl in (('def', model), ('s3d2', model3)):
+        items = [mdl.transform(batch[i, ..., :n]) for i, n in enumerate(blen)]
+        tmax = max(t.shape[-1] for t in items)
+        out[f'ffnn_tbatch_{tag}'] = torch.stack(
+            [torch.nn.functional.pad(t, (0, tmax - t.shape[-1])) for t in items]).numpy()
+        out[f'ffnn_tbatch_{tag}_len'] = np.array([t.shape[-1] for t in items], dtype=np.int64)
+    sg_stft = STFT(frame_length=512, hop_length=128, window='hann', compression_factor=0.5,
+                   scale_factor=0.15, normalized=False)
+    items = []
+    for i, n in enumerate(blen):
+        src = batch[i, ..., :n].clone().mean(axis=-2)        # sgmse.py:153-158
+        src /= src[0].abs().max()
+        items.append(sg_stft(src)[..., :-1, :])
+    tmax = max(t.shape[-1] for t in items)
+    out['sgmse_tbatch'] = torch.stack(
+        [torch.nn.functional.pad(t, (0, tmax - t.shape[-1])) for t in items]).numpy()
+    out['sgmse_tbatch_len'] = np.array([t.shape[-1] for t in items], dtype=np.int64)
+
+    # ---- round 2: gradient of the scale-invariant MultiResYuLoss (criterion.py:207-226) --------
+    crit = MultiResYuLoss(scale_invariant=True)
+    e = est.clone().requires_grad_(True)
+    (crit(e, ref, lengths) * weight).sum().backward()
+    out['crit_mry_si_grad'] = e.grad.numpy()
+
     path = os.path.join(HERE, 'reference_vectors.npz')
     if os.path.exists(path):      # regenerating must not move any vector already committed
         prev = np.load(path)

@@ -1,0 +1,123 @@
+"""GPU parity tests of the round-2 additions against reference-generated goldens: STFT padding /
+centre modes, MANNER's multi-resolution STFT loss, the batched on-device transforms, the
+scale-invariant MultiResYuLoss gradient."""
+import numpy as np
+import pytest
+import torch
+
+import brever_b200 as brv
+
+from _util import assert_parity, crandn, golden, randn
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+PAD_CASES = [('reflect_512_128', dict(frame_length=512, hop_length=128, pad_mode='reflect'), (3, 3001), 700),
+             ('reflect_256_64', dict(frame_length=256, hop_length=64, pad_mode='reflect', normalized=False), (2, 2, 1500), 701),
+             ('nocenter_512_128', dict(frame_length=512, hop_length=128, center=False), (3, 3001), 702),
+             ('reflect_nocenter_400', dict(frame_length=400, hop_length=100, n_fft=512, center=False, pad_mode='reflect'), (2, 2777), 703)]
+
+
+@pytest.mark.parametrize('tag,kw,shape,seed', PAD_CASES)
+def test_stft_padding_modes(tag, kw, shape, seed):
+    """stft.py:59-77,140-144: pad_mode='reflect' (tail + centre mirrored) and center=False."""
+    g = golden()
+    stft = brv.STFT(**kw)
+    x = randn(shape, seed)
+    spec = stft(x.to(DEV))
+    assert tuple(spec.shape) == g[f'stft_{tag}'].shape
+    assert_parity(cpu(spec), g[f'stft_{tag}'], 1e-4, tag)
+    w = crandn(tuple(spec.shape), seed + 50).to(DEV)
+    xg = x.clone().to(DEV).requires_grad_(True)
+    sg = stft(xg)
+    (sg.real * w.real + sg.imag * w.imag).sum().backward()
+    assert_parity(cpu(xg.grad), g[f'stft_{tag}_grad'], 1e-4, tag + ' gradient')
+    if kw.get('center', True):
+        assert_parity(cpu(stft.backward(spec)), g[f'stft_{tag}_back'], 1e-4, tag + ' inverse')
+    else:
+        with pytest.raises(NotImplementedError):
+            stft.backward(spec)
+    with pytest.raises(NotImplementedError):
+        brv.STFT(pad_mode='replicate')
+
+
+@pytest.mark.parametrize('tag,kw', [('def', {}), ('small', dict(fft_sizes=[512, 256], hop_sizes=[128, 64],
+                                                              win_lengths=[512, 200], factor_sc=0.5, factor_mag=1.0))])
+def test_manner_multi_resolution_stft_loss(tag, kw):
+    """models/manner/stft_loss.py:22-151: values and gradient (1024 / 2048-point transforms on
+    the dense tcgen05 path, 512 / 256 on the folded one; reflect padding; clamp-sqrt)."""
+    g = golden()
+    mx, my = 0.1 * randn((3, 8000), 710), 0.1 * randn((3, 8000), 711)
+    my = 0.7 * mx + 0.3 * my
+    my[2, 5000:] = 0.0
+    crit = brv.manner.MultiResolutionSTFTLoss(**kw)
+    e = mx.clone().to(DEV).requires_grad_(True)
+    sc, mag = crit(e, my.to(DEV))
+    assert sc.shape == (3,) and mag.shape == (3,)
+    assert np.allclose(cpu(sc), g[f'manner_{tag}_sc'], rtol=1e-4)
+    assert np.allclose(cpu(mag), g[f'manner_{tag}_mag'], rtol=1e-4)
+    wsc, wmag = torch.tensor([1.0, -0.5, 2.0], device=DEV), torch.tensor([0.3, 1.5, -1.0], device=DEV)
+    ((sc * wsc).sum() + (mag * wmag).sum()).backward()
+    # the log-magnitude term's gradient is sign(|X| - |Y|) / |X|: wherever float32 rounding decides
+    # the sign (near-ties, the clamped silence of item 2) reference and kernel legitimately differ
+    assert_parity(cpu(e.grad), g[f'manner_{tag}_grad'], 1e-3, 'manner gradient')
+
+
+def _tbatch():
+    batch = 0.05 * randn((3, 2, 2, 4000), 720)
+    blen = [4000, 3000, 2345]
+    for i, n in enumerate(blen):
+        batch[i, ..., n:] = 0
+    return batch, blen
+
+
+@pytest.mark.parametrize('tag,kw', [('def', {}), ('s3d2', dict(stacks=3, decimation=2))])
+def test_ffnn_transform_batched(tag, kw):
+    """training.py:336-338 + data.py:408-491: the per-utterance transform loop + collate."""
+    g = golden()
+    batch, blen = _tbatch()
+    front = brv.ffnn.FFNNFrontEnd(**kw)
+    out, frames = brv.transform_batched('ffnn', batch.to(DEV), torch.tensor(blen), front=front)
+    assert frames.tolist() == g[f'ffnn_tbatch_{tag}_len'].tolist()
+    assert tuple(out.shape) == g[f'ffnn_tbatch_{tag}'].shape
+    n_feat = front.input_size
+    assert_parity(cpu(out[:, :n_feat]), g[f'ffnn_tbatch_{tag}'][:, :n_feat], 1e-4, 'features')
+    assert_parity(cpu(out[:, n_feat:]), g[f'ffnn_tbatch_{tag}'][:, n_feat:], 1e-4, 'labels')
+    for i, t in enumerate(frames.tolist()):
+        assert float(out[i, :, t:].abs().max()) == 0 if t < out.shape[-1] else True
+        one = front.transform(batch[i, ..., :blen[i]].to(DEV))          # per-utterance path
+        assert_parity(cpu(out[i, :, :t]), cpu(one), 2e-6, 'batched == per item')
+
+
+def test_sgmse_transform_batched():
+    g = golden()
+    batch, blen = _tbatch()
+    stft = brv.STFT(frame_length=512, hop_length=128, window='hann', compression_factor=0.5,
+                    scale_factor=0.15, normalized=False)
+    out, frames = brv.transform_batched('sgmsep', batch.to(DEV), torch.tensor(blen), stft=stft)
+    assert frames.tolist() == g['sgmse_tbatch_len'].tolist()
+    assert tuple(out.shape) == g['sgmse_tbatch'].shape
+    assert_parity(cpu(out), g['sgmse_tbatch'], 1e-4, 'sgmse transform')
+    with pytest.raises(ValueError):
+        brv.transform_batched('dccrn', batch.to(DEV), torch.tensor(blen))
+
+
+def test_multiresyu_scale_invariant_gradient():
+    """criterion.py:207-226 with scale_invariant=True: gradient through the scaling factor."""
+    g = golden()
+    B, S, L = 5, 3, 2000
+    est, ref = randn((B, S, L), 600), randn((B, S, L), 601)
+    est = ref.roll(1, 1) * 0.7 + 0.3 * est
+    lengths = torch.from_numpy(g['crit_lengths'])
+    weight = torch.from_numpy(g['crit_mse_weight'])
+    crit = brv.MultiResYuLoss(scale_invariant=True)
+    e = est.clone().to(DEV).requires_grad_(True)
+    out = crit(e, ref.to(DEV), lengths)
+    assert np.allclose(cpu(out), g['crit_mry_si'], rtol=2e-5)
+    (out * weight.to(DEV)).sum().backward()
+    assert_parity(cpu(e.grad), g['crit_mry_si_grad'], 1e-4, 'SI gradient')

@@ -347,3 +347,36 @@ def test_mse_and_multiresyu_port_against_reference():
     e = est.clone().requires_grad_(True)
     (P.multiresyu(e, ref, lengths) * weight).sum().backward()
     assert_parity(e.grad.numpy(), g['crit_mry_def_grad'], 1e-5)
+
+
+# --------------------------------------------------------------------------- #
+# round 2: pad_mode / center variants, MANNER's loss                           #
+# --------------------------------------------------------------------------- #
+PAD_CASES = [('reflect_512_128', dict(frame_length=512, hop_length=128, pad_mode='reflect'), (3, 3001), 700),
+             ('reflect_256_64', dict(frame_length=256, hop_length=64, pad_mode='reflect', normalized=False), (2, 2, 1500), 701),
+             ('nocenter_512_128', dict(frame_length=512, hop_length=128, center=False), (3, 3001), 702),
+             ('reflect_nocenter_400', dict(frame_length=400, hop_length=100, n_fft=512, center=False, pad_mode='reflect'), (2, 2777), 703)]
+
+
+@pytest.mark.parametrize('tag,kw,shape,seed', PAD_CASES)
+def test_oracle_stft_padding_modes(tag, kw, shape, seed):
+    g = golden()
+    x = randn(shape, seed)
+    spec = O.stft(x.numpy(), **kw)
+    assert spec.shape == g[f'stft_{tag}'].shape
+    assert_parity(spec, g[f'stft_{tag}'], 2e-6, tag)
+    w = crandn(tuple(spec.shape), seed + 50).numpy()
+    grad = O.stft_grad(w, shape[-1], **kw)
+    assert_parity(grad, g[f'stft_{tag}_grad'], 1e-5, tag + ' gradient')
+
+
+def test_oracle_manner_loss():
+    g = golden()
+    mx, my = 0.1 * randn((3, 8000), 710), 0.1 * randn((3, 8000), 711)
+    my = 0.7 * mx + 0.3 * my
+    my[2, 5000:] = 0.0
+    sc, mag = O.manner_stft_loss(mx.numpy(), my.numpy())
+    assert np.allclose(sc, g['manner_def_sc'], rtol=2e-5) and np.allclose(mag, g['manner_def_mag'], rtol=2e-5)
+    sc, mag = O.manner_stft_loss(mx.numpy(), my.numpy(), fft_sizes=[512, 256], hop_sizes=[128, 64],
+                                 win_lengths=[512, 200], factor_sc=0.5, factor_mag=1.0)
+    assert np.allclose(sc, g['manner_small_sc'], rtol=2e-5) and np.allclose(mag, g['manner_small_mag'], rtol=2e-5)
