@@ -11,6 +11,7 @@ Kept quirks: ``eps = finfo(float32).eps`` inside and outside the ratio
 Unlike the reference's ``sisnr`` (in-place ``/=`` on the ``amax`` output,
 criterion.py:69-70) ours can be back-propagated.
 """
+import functools
 import inspect
 import math
 from itertools import permutations
@@ -36,9 +37,22 @@ def init_criterion(name, **kwargs):
 
 
 def _lengths_on(lengths, device):
+    """`lengths` as a contiguous int64 tensor on `device`.  A device tensor passes through; a
+    host tensor / list costs one pageable host-to-device copy per call (it synchronises the
+    host and cannot be captured in a CUDA graph): keep lengths on the device in hot loops."""
     if not isinstance(lengths, torch.Tensor):
         lengths = torch.as_tensor(lengths)
+    if lengths.device == device and lengths.dtype == torch.int64 and lengths.is_contiguous():
+        return lengths
     return lengths.to(device=device, dtype=torch.int64).contiguous()
+
+
+@functools.lru_cache(maxsize=None)
+def _perms_on(n_src, device):
+    """All permutations of the sources, resident on `device` (built once per (S, device): a
+    per-call torch.tensor(..., device=cuda) is a host-to-device copy inside the hot path)."""
+    idx = torch.tensor(list(permutations(range(n_src))), dtype=torch.int64)
+    return idx.to(device), torch.arange(n_src, device=device)
 
 
 def _rows(t):
@@ -158,10 +172,9 @@ class _SiSnrFunction(torch.autograd.Function):
             return loss
         db, mom = _moments(x3, y3, lengths, True)
         si_snr = db.view(batch, n_src, n_src)      # [b, target i, estimate j]
-        perms = torch.tensor(list(permutations(range(n_src))),
-                             dtype=torch.int64, device=x.device)
+        perms, src_idx = _perms_on(n_src, x.device)
         # snr_set[b, p] = sum_i si_snr[b, i, perms[p, i]]   (criterion.py:66-68)
-        gathered = si_snr[:, torch.arange(n_src, device=x.device), perms]
+        gathered = si_snr[:, src_idx, perms]
         totals = gathered.sum(-1)
         best, which = totals.max(1)
         perm = perms[which]                        # target i <- estimate perm[b, i]

@@ -278,10 +278,10 @@ mag_l1_kernel(const float2* __restrict__ X, const float2* __restrict__ Y, int64_
 __global__ void mag_l1_grad_kernel(const float2* __restrict__ X, const float2* __restrict__ Y,
                                    const float* __restrict__ coef, int64_t n_elems,
                                    float2* __restrict__ gX) {
-    const int64_t sig = blockIdx.y;
+    const int64_t sig = blockIdx.x;
     const float cf = coef[sig];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n_elems;
+         i += (int64_t)gridDim.y * blockDim.x) {
         const float2 a = __ldcs(X + sig * n_elems + i), c = __ldcs(Y + sig * n_elems + i);
         const float ma = hypotf(a.x, a.y), mc = hypotf(c.x, c.y);
         float2 g = make_float2(0.f, 0.f);
@@ -301,12 +301,12 @@ constexpr float MR_CLAMP = 1e-7f;
 __global__ void __launch_bounds__(CR_THREADS)
 mrstft_sums_kernel(const float2* __restrict__ X, const float2* __restrict__ Y, int64_t n_elems,
                    double* __restrict__ sums) {
-    const int64_t sig = blockIdx.y;
+    const int64_t sig = blockIdx.x;
     const float2* xp = X + sig * n_elems;
     const float2* yp = Y + sig * n_elems;
     double a0 = 0, a1 = 0, a2 = 0;
-    for (int64_t i0 = (int64_t)blockIdx.x * (4 * CR_THREADS); i0 < n_elems;
-         i0 += (int64_t)gridDim.x * (4 * CR_THREADS)) {
+    for (int64_t i0 = (int64_t)blockIdx.y * (4 * CR_THREADS); i0 < n_elems;
+         i0 += (int64_t)gridDim.y * (4 * CR_THREADS)) {
         float2 a[4], c[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -355,10 +355,10 @@ mrstft_sums_kernel(const float2* __restrict__ X, const float2* __restrict__ Y, i
 __global__ void mrstft_grad_kernel(const float2* __restrict__ X, const float2* __restrict__ Y,
                                    const float* __restrict__ k_sc, const float* __restrict__ k_mag,
                                    int64_t n_elems, float2* __restrict__ gX) {
-    const int64_t sig = blockIdx.y;
+    const int64_t sig = blockIdx.x;
     const float ks = k_sc[sig], km = k_mag[sig];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n_elems;
+         i += (int64_t)gridDim.y * blockDim.x) {
         const float2 a = __ldcs(X + sig * n_elems + i), c = __ldcs(Y + sig * n_elems + i);
         const float px = a.x * a.x + a.y * a.y;
         float2 g = make_float2(0.f, 0.f);
@@ -378,15 +378,15 @@ __global__ void l1_rows_grad_kernel(const float* __restrict__ x, const float* __
                                     const float* __restrict__ scale, const float* __restrict__ coef,
                                     int64_t n_rows, int64_t length, int64_t xsb, int64_t xsr,
                                     int64_t ysb, int64_t ysr, float* __restrict__ gx) {
-    const int64_t row = blockIdx.y;
+    const int64_t row = blockIdx.x;
     const int64_t b = row / n_rows, r = row % n_rows;
     int64_t valid = lengths[b];
     if (valid > length) valid = length;
     const float s = scale ? scale[row] : 1.f, cf = coef[row];
     const float* xp = x + b * xsb + r * xsr;
     const float* yp = y + b * ysb + r * ysr;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < length;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < length;
+         i += (int64_t)gridDim.y * blockDim.x) {
         float v = 0.f;
         if (i < valid) {
             const float d = s * __ldg(xp + i) - __ldg(yp + i);
@@ -402,7 +402,7 @@ __global__ void masked_affine_kernel(const float* __restrict__ x, const float* _
                                      int64_t ysr, const float* __restrict__ ca,
                                      const float* __restrict__ cb, const float* __restrict__ c0,
                                      const int32_t* __restrict__ ymap, float* __restrict__ gx) {
-    const int64_t row = blockIdx.y;               // b * n_rows + r
+    const int64_t row = blockIdx.x;               // b * n_rows + r
     const int64_t b = row / n_rows, r = row % n_rows;
     const int64_t yr = ymap ? ymap[row] : r;
     int64_t valid = lengths[b];
@@ -411,8 +411,8 @@ __global__ void masked_affine_kernel(const float* __restrict__ x, const float* _
     const float* xp = x + b * xsb + r * xsr;
     const float* yp = y + b * ysb + yr * ysr;
     float* gp = gx + row * length;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < length;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < length;
+         i += (int64_t)gridDim.y * blockDim.x) {
         float v = 0.f;
         if (i < valid) v = fmaf(a, __ldg(xp + i), fmaf(bb, __ldg(yp + i), c));
         gp[i] = v;
@@ -431,7 +431,7 @@ criterion_grad_kernel(const float* __restrict__ x, const float* __restrict__ y,
                       const int32_t* __restrict__ ymap, int mode, int64_t n_rows, int64_t length,
                       int64_t xsb, int64_t xsr, int64_t ysb, int64_t ysr, float eps,
                       float* __restrict__ gx) {
-    const int64_t row = blockIdx.y;               // b * n_rows + r (estimate row)
+    const int64_t row = blockIdx.x;               // b * n_rows + r (estimate row)
     const int64_t b = row / n_rows, r = row % n_rows;
     const int64_t yr = ymap ? ymap[row] : r;
     int64_t valid = lengths[b];
@@ -476,7 +476,7 @@ criterion_grad_kernel(const float* __restrict__ x, const float* __restrict__ y,
     const float* yp = y + b * ysb + yr * ysr;
     float* gp = gx + row * length;
     const bool vec = (((((uintptr_t)xp) | ((uintptr_t)yp) | ((uintptr_t)gp)) & 15) == 0);
-    const int64_t base = (int64_t)blockIdx.x * 2048 * 4;
+    const int64_t base = (int64_t)blockIdx.y * 2048 * 4;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const int64_t i = base + 4 * (int64_t)(u * 256 + threadIdx.x);
@@ -500,11 +500,11 @@ criterion_grad_kernel(const float* __restrict__ x, const float* __restrict__ y,
 
 __global__ void apply_mask_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengths,
                                   int64_t inner, int64_t length, float* __restrict__ out) {
-    const int64_t row = blockIdx.y;
+    const int64_t row = blockIdx.x;
     const int64_t b = row / inner;
     const int64_t valid = lengths[b];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < length;
-         i += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < length;
+         i += (int64_t)gridDim.y * blockDim.x)
         out[row * length + i] = i < valid ? x[row * length + i] : 0.f;
 }
 
@@ -576,10 +576,11 @@ extern "C" int brv_masked_affine(const float* x, const float* y, const int64_t* 
     BRV_REQUIRE(x && y && lengths && ca && cb && c0 && gx, "null pointer argument");
     const int64_t rows = n_batch * n_rows;
     if (rows == 0 || length == 0) return BRV_OK;
-    BRV_REQUIRE(rows < 65536, "more than 65535 rows per call");
+    BRV_REQUIRE(rows <= 2147483647LL, "too many rows per call");
     unsigned gx_blocks = (unsigned)brv_ceil_div(length, 256 * 8);
     if (gx_blocks < 1) gx_blocks = 1;
-    masked_affine_kernel<<<dim3(gx_blocks, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
+    if (gx_blocks > 65535) gx_blocks = 65535;                  // grid-stride loop inside
+    masked_affine_kernel<<<dim3((unsigned)rows, gx_blocks), 256, 0, (cudaStream_t)stream>>>(
         x, y, lengths, n_rows, length, xsb, xsr, ysb, ysr, ca, cb, c0, ymap, gx);
     BRV_LAUNCH_CHECK("masked_affine_kernel");
     return BRV_OK;
@@ -590,9 +591,10 @@ extern "C" int brv_apply_mask(const float* x, const int64_t* lengths, int64_t n_
     BRV_REQUIRE(x && lengths && out, "null pointer argument");
     const int64_t rows = n_batch * inner;
     if (rows == 0 || length == 0) return BRV_OK;
-    BRV_REQUIRE(rows < 65536, "more than 65535 rows per call");
+    BRV_REQUIRE(rows <= 2147483647LL, "too many rows per call");
     unsigned blocks = (unsigned)brv_ceil_div(length, 256 * 8);
-    apply_mask_kernel<<<dim3(blocks, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
+    if (blocks > 65535) blocks = 65535;                        // grid-stride loop inside
+    apply_mask_kernel<<<dim3((unsigned)rows, blocks), 256, 0, (cudaStream_t)stream>>>(
         x, lengths, inner, length, out);
     BRV_LAUNCH_CHECK("apply_mask_kernel");
     return BRV_OK;
@@ -642,9 +644,10 @@ extern "C" int brv_l1_backward(const float* x, const float* y, const int64_t* le
     BRV_REQUIRE(x && y && lengths && coef && gx, "null pointer argument");
     const int64_t rows = n_batch * n_rows;
     if (rows == 0 || length == 0) return BRV_OK;
-    BRV_REQUIRE(rows < 65536, "more than 65535 rows per call");
+    BRV_REQUIRE(rows <= 2147483647LL, "too many rows per call");
     unsigned blocks = (unsigned)brv_ceil_div(length, 256 * 8);
-    l1_rows_grad_kernel<<<dim3(blocks, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
+    if (blocks > 65535) blocks = 65535;                        // grid-stride loop inside
+    l1_rows_grad_kernel<<<dim3((unsigned)rows, blocks), 256, 0, (cudaStream_t)stream>>>(
         x, y, lengths, scale, coef, n_rows, length, xsb, xsr, ysb, ysr, gx);
     BRV_LAUNCH_CHECK("l1_rows_grad_kernel");
     return BRV_OK;
@@ -673,10 +676,10 @@ extern "C" int brv_mag_l1_backward(const void* X, const void* Y, const float* co
                                    int64_t n_signals, int64_t n_elems, void* gX, void* stream) {
     BRV_REQUIRE(X && Y && coef && gX, "null pointer argument");
     if (n_signals == 0 || n_elems == 0) return BRV_OK;
-    BRV_REQUIRE(n_signals < 65536, "more than 65535 signals per call");
+    BRV_REQUIRE(n_signals <= 2147483647LL, "too many signals per call");
     unsigned blocks = (unsigned)brv_ceil_div(n_elems, 256 * 8);
     if (blocks > 4096) blocks = 4096;
-    mag_l1_grad_kernel<<<dim3(blocks, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(
+    mag_l1_grad_kernel<<<dim3((unsigned)n_signals, blocks), 256, 0, (cudaStream_t)stream>>>(
         (const float2*)X, (const float2*)Y, coef, n_elems, (float2*)gX);
     BRV_LAUNCH_CHECK("mag_l1_grad_kernel");
     return BRV_OK;
@@ -687,13 +690,13 @@ extern "C" int brv_mrstft_forward(const void* X, const void* Y, int64_t n_signal
     BRV_REQUIRE(n_signals >= 0 && n_elems >= 0, "bad shape");
     if (n_signals == 0) return BRV_OK;
     BRV_REQUIRE(sums && (n_elems == 0 || (X && Y)), "null pointer argument");
-    BRV_REQUIRE(n_signals < 65536, "more than 65535 signals per call");
+    BRV_REQUIRE(n_signals <= 2147483647LL, "too many signals per call");
     BRV_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_signals * 3 * sizeof(double), (cudaStream_t)stream));
     if (n_elems == 0) return BRV_OK;
     int64_t blocks = brv_ceil_div(n_elems, 4 * CR_THREADS);
     const int64_t cap = brv_ceil_div(148 * 8, n_signals);          // ~8 CTAs per SM in total
     if (blocks > cap) blocks = cap < 1 ? 1 : cap;
-    mrstft_sums_kernel<<<dim3((unsigned)blocks, (unsigned)n_signals), CR_THREADS, 0, (cudaStream_t)stream>>>(
+    mrstft_sums_kernel<<<dim3((unsigned)n_signals, (unsigned)blocks), CR_THREADS, 0, (cudaStream_t)stream>>>(
         (const float2*)X, (const float2*)Y, n_elems, sums);
     BRV_LAUNCH_CHECK("mrstft_sums_kernel");
     return BRV_OK;
@@ -704,10 +707,10 @@ extern "C" int brv_mrstft_backward(const void* X, const void* Y, const float* k_
     BRV_REQUIRE(n_signals >= 0 && n_elems >= 0, "bad shape");
     if (n_signals == 0 || n_elems == 0) return BRV_OK;
     BRV_REQUIRE(X && Y && k_sc && k_mag && gX, "null pointer argument");
-    BRV_REQUIRE(n_signals < 65536, "more than 65535 signals per call");
+    BRV_REQUIRE(n_signals <= 2147483647LL, "too many signals per call");
     unsigned blocks = (unsigned)brv_ceil_div(n_elems, 256 * 8);
     if (blocks > 4096) blocks = 4096;
-    mrstft_grad_kernel<<<dim3(blocks, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(
+    mrstft_grad_kernel<<<dim3((unsigned)n_signals, blocks), 256, 0, (cudaStream_t)stream>>>(
         (const float2*)X, (const float2*)Y, k_sc, k_mag, n_elems, (float2*)gX);
     BRV_LAUNCH_CHECK("mrstft_grad_kernel");
     return BRV_OK;
@@ -722,9 +725,10 @@ extern "C" int brv_criterion_backward(const float* x, const float* y, const int6
     BRV_REQUIRE(x && y && lengths && moments && gout && gx, "null pointer argument");
     const int64_t rows = n_batch * n_rows;
     if (rows == 0 || length == 0) return BRV_OK;
-    BRV_REQUIRE(rows < 65536, "more than 65535 rows per call");
+    BRV_REQUIRE(rows <= 2147483647LL, "too many rows per call");
     const unsigned blocks = (unsigned)brv_ceil_div(length, 2048 * 4);
-    criterion_grad_kernel<<<dim3(blocks, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
+    BRV_REQUIRE(blocks <= 65535, "rows longer than 2^29 samples are not supported");
+    criterion_grad_kernel<<<dim3((unsigned)rows, blocks), 256, 0, (cudaStream_t)stream>>>(
         x, y, lengths, moments, gout, gout_stride, gscale, ymap, pairwise ? 1 : 0, n_rows, length,
         xsb, xsr, ysb, ysr, eps, gx);
     BRV_LAUNCH_CHECK("criterion_grad_kernel");

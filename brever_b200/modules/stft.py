@@ -346,7 +346,8 @@ class ConvSTFT:
     frames start ``L - H`` samples before ``t * H``, the DC row carries ``1 / sqrt(2)``, the
     synthesis is the exact adjoint (no envelope division) trimmed by ``L - H`` per side.
     Supported on the kernels' sizes only (``frame_length`` in {128, 256, 384, 512} and
-    ``hop_length`` = L/4, L/2 or L); no autograd (no reference model uses ConvSTFT).
+    ``hop_length`` = L/4, L/2 or L); differentiable in both directions through the adjoint pair
+    (``compression_factor == 1``).
     """
 
     def __init__(self, frame_length=512, hop_length=256, window='hann',
@@ -407,6 +408,17 @@ class ConvSTFT:
             x2d = x2d.float()
         if x2d.stride(-1) != 1:
             x2d = x2d.contiguous()
+        bins = self.frame_length // 2 + 1
+        if torch.is_grad_enabled() and x2d.requires_grad:
+            spec = _ConvForwardFunction.apply(x2d, self)
+        else:
+            spec = self._conv_forward_raw(x2d)
+        spec = spec.view(*lead, bins, spec.shape[-1])
+        if return_type == 'complex':
+            return spec
+        return specfmt.split(spec, return_type)
+
+    def _conv_forward_raw(self, x2d):
         n_sig, samples = x2d.shape
         frames, bins = self.n_frames(samples), self.frame_length // 2 + 1
         out = torch.empty((n_sig, frames, bins), dtype=torch.complex64, device=x2d.device)
@@ -416,31 +428,10 @@ class ConvSTFT:
                     self._core._plan(x2d.device), _lib.ptr(x2d), n_sig, samples,
                     x2d.stride(0) if n_sig > 1 else samples, int(bool(self.normalized)),
                     _lib.ptr(out), _lib.stream_ptr(x2d.device)))
-        spec = out.transpose(1, 2).view(*lead, bins, frames)
-        if return_type == 'complex':
-            return spec
-        if return_type == 'real_imag':
-            return spec.real, spec.imag
-        return spec.abs(), spec.angle()
+        return out.transpose(1, 2)
 
-    def backward(self, x, input_type='complex'):
-        if input_type == 'real_imag':
-            real, imag = x
-            x = torch.complex(real, imag)
-        elif input_type == 'mag_phase':
-            mag, phase = x
-            x = torch.polar(mag, phase)
-        elif input_type != 'complex':
-            raise ValueError('input_type must be complex, real_imag or '
-                             f'mag_phase, got {input_type}')
-        _lib.require_cuda(x, 'ConvSTFT.backward input')
-        if not x.is_complex():
-            raise RuntimeError('ConvSTFT.backward input must be complex')
-        lead = x.shape[:-2]
-        spec3d = x.reshape(-1, *x.shape[-2:]).to(torch.complex64).resolve_conj().resolve_neg()
+    def _conv_backward_raw(self, spec3d):
         n_sig, bins, frames = spec3d.shape
-        if bins != self.frame_length // 2 + 1:
-            raise RuntimeError(f'expected {self.frame_length // 2 + 1} frequency bins, got {bins}')
         out_len = max((frames + 1) * self.hop_length - self.frame_length, 0)
         if self.frame_length == self.hop_length:
             out_len = 0   # the reference slices ``x[..., 0:-0]`` = nothing (stft.py:296-298)
@@ -451,7 +442,79 @@ class ConvSTFT:
                     self._core._plan(spec3d.device), _lib.ptr(spec3d), spec3d.stride(0),
                     spec3d.stride(1), spec3d.stride(2), n_sig, frames,
                     int(bool(self.normalized)), _lib.ptr(y), _lib.stream_ptr(spec3d.device)))
+        return y
+
+    def _gains(self):
+        """(analysis gain, synthesis gain) the kernels apply besides scale_factor (stft.py:232-238,
+        291-292): the two maps are adjoint up to these, which is what the gradients use."""
+        nf = self._normalization_factor
+        return (1.0 / nf, 1.0 / nf) if self.normalized else (1.0, 1.0 / (nf * nf))
+
+    def backward(self, x, input_type='complex'):
+        if input_type in ('real_imag', 'mag_phase'):
+            a, b = x
+            _lib.require_cuda(a, 'ConvSTFT.backward input')
+            x = specfmt.join(a, b, input_type)
+        elif input_type != 'complex':
+            raise ValueError('input_type must be complex, real_imag or '
+                             f'mag_phase, got {input_type}')
+        _lib.require_cuda(x, 'ConvSTFT.backward input')
+        if not x.is_complex():
+            raise RuntimeError('ConvSTFT.backward input must be complex')
+        lead = x.shape[:-2]
+        spec3d = x.reshape(-1, *x.shape[-2:]).to(torch.complex64).resolve_conj().resolve_neg()
+        if spec3d.shape[1] != self.frame_length // 2 + 1:
+            raise RuntimeError(f'expected {self.frame_length // 2 + 1} frequency bins, got {spec3d.shape[1]}')
+        if torch.is_grad_enabled() and spec3d.requires_grad:
+            y = _ConvBackwardFunction.apply(spec3d, self)
+        else:
+            y = self._conv_backward_raw(spec3d)
         return y.view(*lead, -1)
+
+
+def _conv_grad_check(conv):
+    if conv.compression_factor != 1:
+        raise NotImplementedError('gradient of the compressed ConvSTFT (compression_factor != 1) '
+                                  'is not implemented')
+    if conv.frame_length == conv.hop_length:
+        raise NotImplementedError('ConvSTFT gradients need hop_length < frame_length (the synthesis '
+                                  'returns an empty signal at hop_length == frame_length, stft.py:296-298)')
+
+
+class _ConvForwardFunction(torch.autograd.Function):
+    """X = s g_a A x; the synthesis kernel computes (g_s / s) Re(A^H X): dL/dx = s^2 g_a / g_s of it."""
+
+    @staticmethod
+    def forward(ctx, x2d, conv):
+        _conv_grad_check(conv)
+        ctx.conv, ctx.samples = conv, x2d.shape[-1]
+        return conv._conv_forward_raw(x2d)
+
+    @staticmethod
+    def backward(ctx, grad):
+        conv = ctx.conv
+        ga, gs = conv._gains()
+        g = grad.to(torch.complex64).resolve_conj().resolve_neg()
+        full = conv._conv_backward_raw(g)              # right-padded length >= samples
+        return full[..., :ctx.samples] * (conv.scale_factor ** 2 * ga / gs), None
+
+
+class _ConvBackwardFunction(torch.autograd.Function):
+    """y = (g_s / s) Re(A^H X); the analysis kernel computes s g_a A y': dL/dX = g_s / (s^2 g_a) of it."""
+
+    @staticmethod
+    def forward(ctx, spec3d, conv):
+        _conv_grad_check(conv)
+        ctx.conv, ctx.frames, ctx.in_dtype = conv, spec3d.shape[-1], spec3d.dtype
+        return conv._conv_backward_raw(spec3d)
+
+    @staticmethod
+    def backward(ctx, grad):
+        conv = ctx.conv
+        ga, gs = conv._gains()
+        g = conv._conv_forward_raw(grad.float().contiguous())
+        assert g.shape[-1] == ctx.frames
+        return (g * (gs / (conv.scale_factor ** 2 * ga))).to(ctx.in_dtype), None
 
 
 class _MelApply(torch.autograd.Function):

@@ -613,10 +613,6 @@ def test_multiresyu_against_reference(name):
     out = crit(e[:, 0], r[:, 0], lengths)
     assert out.ndim == 0 and abs(float(out) - float(g[f'crit_mry_{name}_2d'])) < 2e-4
     eg = est.clone().to(DEV).requires_grad_(True)
-    if name == 'si':
-        with pytest.raises(NotImplementedError):
-            crit(eg, r, lengths)
-        return
     weight = torch.tensor(g['crit_mse_weight']).to(DEV)
     (crit(eg, r, lengths) * weight).sum().backward()
     assert_parity(cpu(eg.grad), g[f'crit_mry_{name}_grad'], 1e-4)

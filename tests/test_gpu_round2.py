@@ -121,3 +121,110 @@ def test_multiresyu_scale_invariant_gradient():
     assert np.allclose(cpu(out), g['crit_mry_si'], rtol=2e-5)
     (out * weight.to(DEV)).sum().backward()
     assert_parity(cpu(e.grad), g['crit_mry_si_grad'], 1e-4, 'SI gradient')
+
+
+@pytest.mark.parametrize('normalized', [True, False])
+def test_conv_stft_gradients(normalized):
+    """ConvSTFT is differentiable in the reference (F.conv1d / F.conv_transpose1d, stft.py:244-300):
+    both directions against torch autograd through that formulation in float64 on the CPU."""
+    import torch.nn.functional as F
+    L, H, s = 256, 64, 0.7
+    conv = brv.ConvSTFT(frame_length=L, hop_length=H, scale_factor=s, normalized=normalized)
+    filters = conv.filters.double()
+    dim = L // 2 + 1
+    nf2 = 1.0 if normalized else conv._normalization_factor ** 2
+    x = randn((3, 2000), 41)
+    w = crandn((3, dim, conv.n_frames(2000)), 42)
+
+    def ref_forward(xd):
+        out = F.conv1d(conv.pad(xd).unsqueeze(1), filters, stride=H) * s
+        return torch.complex(out[:, :dim], out[:, dim:])
+
+    def ref_backward(X):
+        z = torch.cat([X.real, X.imag], dim=-2) / s
+        y = F.conv_transpose1d(z, filters, stride=H) / nf2
+        return y[:, 0, L - H:-(L - H)]
+
+    xr = x.double().requires_grad_(True)
+    (ref_forward(xr) * w.conj().to(torch.complex128)).real.sum().backward()
+    xg = x.clone().to(DEV).requires_grad_(True)
+    (conv(xg) * w.conj().to(DEV)).real.sum().backward()
+    assert_parity(cpu(xg.grad), xr.grad.numpy(), 1e-4, 'd ConvSTFT / dx')
+
+    X = crandn((3, dim, 40), 43)
+    v = randn((3, 41 * H - L), 44)
+    Xr = X.to(torch.complex128).requires_grad_(True)
+    (ref_backward(Xr) * v.double()).sum().backward()
+    Xg = X.clone().to(DEV).requires_grad_(True)
+    (conv.backward(Xg) * v.to(DEV)).sum().backward()
+    assert_parity(cpu(Xg.grad), Xr.grad.numpy(), 1e-4, 'd ConvSTFT.backward / dX')
+    with pytest.raises(NotImplementedError):
+        c2 = brv.ConvSTFT(frame_length=L, hop_length=H, compression_factor=0.5)
+        c2(x.clone().to(DEV).requires_grad_(True))
+
+
+def test_istft_complex32_input():
+    """AMP: TF-GridNet hands torch.complex(half, half) to STFT.backward; computed
+    in float32, returned as float16."""
+    stft = brv.STFT(256, 128, normalized=False)
+    spec = crandn((2, 129, 60), 51).to(DEV)
+    half = torch.complex(spec.real.half(), spec.imag.half())
+    assert half.dtype == torch.complex32
+    y = stft.backward(half)
+    assert y.dtype == torch.float16
+    ref = stft.backward(torch.complex(half.real.float(), half.imag.float()))
+    assert torch.allclose(y.float(), ref, atol=2e-3 * float(ref.abs().max()))
+
+
+BENCH_SHAPES = [
+    ('cfg3', None, (256, 1, 64000)),
+    ('cfg4', dict(frame_length=510, hop_length=128, normalized=False, compression_factor=0.5, scale_factor=0.15),
+     (128, 128000)),
+    ('cfg5', dict(frame_length=256, hop_length=128, normalized=False), (1024, 2, 64000)),
+]
+
+
+@pytest.mark.parametrize('name,kw,shape', BENCH_SHAPES)
+def test_exact_bench_shapes(name, kw, shape):
+    """The tensors bench.py times (same generator, same seeds): >= 8 signals spread over the batch
+    against the float64 oracle, a checksum of every row against the generic path, and the round
+    trip -- the dispatch (strip kernel, strip scheduling, persistent tile order) depends on the
+    launch size, so reduced batches do not cover it."""
+    from _util import synthetic_mixture
+    from brever_b200 import _lib
+    from oracle import tf_oracle as O
+    mix, fg = synthetic_mixture(shape, 1000 + int(name[-1]))
+    if kw is None:                                      # cfg3: criterion only
+        lengths = torch.full((shape[0],), shape[-1])
+        out = brv.sisnr(mix.to(DEV), fg.to(DEV), lengths)
+        rows = np.linspace(0, shape[0] - 1, 8).astype(int)
+        ref, _ = O.sisnr(mix[rows].numpy(), fg[rows].numpy(), lengths[rows].numpy())
+        assert np.allclose(cpu(out[rows]), ref, atol=1e-4)
+        return
+    stft = brv.STFT(**kw)
+    x = mix.to(DEV)
+    spec = stft(x)
+    flat = x.reshape(-1, x.shape[-1])
+    fspec = spec.reshape(-1, *spec.shape[-2:])
+    rows = np.linspace(0, flat.shape[0] - 1, 8).astype(int)
+    for r in rows:
+        assert_parity(cpu(fspec[r]), O.stft(cpu(flat[r]), **kw), 1e-4, f'{name} stft row {r}')
+    # checksum of every row against the generic (float64-accumulating SIMT) path, in chunks
+    prev = _lib.lib().brv_set_force_generic(1)
+    try:
+        for start in range(0, flat.shape[0], 256):
+            gen = stft(flat[start:start + 256])
+            a = fspec[start:start + 256]
+            num = (a - gen).abs().amax(dim=(-2, -1))
+            den = gen.abs().amax(dim=(-2, -1))
+            assert float((num / den).max()) < 1e-4, (name, start)
+            del gen
+    finally:
+        _lib.lib().brv_set_force_generic(prev)
+    sel = spec[:, 0] if spec.ndim == 4 else spec
+    y = stft.backward(sel)[..., :shape[-1]]
+    xs = x[:, 0] if x.ndim == 3 else x
+    err = (y - xs).abs().amax(-1) / xs.abs().amax(-1)
+    assert float(err.max()) < 2e-4, (name, float(err.max()))
+    for r in np.linspace(0, sel.shape[0] - 1, 8).astype(int):
+        assert_parity(cpu(y[r]), O.istft(cpu(sel[r]), **kw)[..., :shape[-1]], 1e-4, f'{name} istft row {r}')
