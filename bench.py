@@ -241,7 +241,7 @@ class Pipeline:
     def select(self, spec):
         """What goes back through the iSTFT: channel mean (FFNN), source 0 (TF-GridNet)."""
         if self.name == 'cfg1':
-            return spec.mean(1)
+            return self.brv.ffnn.channel_mean(spec)      # FFNN._enhance's x.mean(1), one fused pass
         if self.name == 'cfg5':
             return spec[:, 0]
         return spec
@@ -345,7 +345,7 @@ def measure_workload(name, wl, device, rank, world, steps, warmup, use_graph=Tru
 
     def full_step(mix, target):
         loss = pipe.step(mix, target)
-        total.add_(loss.mean())                      # running metric (training.py:369-373)
+        pipe.brv.ffnn.accumulate_mean(total, loss)   # running metric (training.py:369-373), one launch
         return loss
 
     lib = _lib.lib()

@@ -82,6 +82,9 @@ PROTOTYPES = {
     'brv_reflect_pad_grad': (_int, [_ptr, _i64, _i64, _i64, _int, _int, _ptr, _ptr]),
     'brv_mrstft_forward': (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr]),
     'brv_mrstft_backward': (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr]),
+    'brv_channel_mean_mask': (_int, [_ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i64, _int, _int,
+                                     _i64, _ptr, _ptr]),
+    'brv_accumulate_mean': (_int, [_ptr, _i64, _ptr, _ptr]),
     'brv_spec_split': (_int, [_ptr, _i64, _int, _f32, _ptr, _ptr, _ptr]),
     'brv_spec_join': (_int, [_ptr, _ptr, _i64, _int, _ptr, _ptr]),
     'brv_spec_split_grad': (_int, [_ptr, _ptr, _ptr, _i64, _int, _f32, _ptr, _ptr]),

@@ -185,3 +185,71 @@ extern "C" int brv_spec_join_grad(const void* gX, const float* a, const float* b
     BRV_LAUNCH_CHECK("spec_join_grad_kernel");
     return BRV_OK;
 }
+
+// ---- mean over channels times a real per-bin mask, in one pass ------------------------------
+// FFNN._enhance (models/ffnn/ffnn.py:107-110): `x = x.mean(1); x = stft.backward(x * mask)` -- the
+// reference (and an eager mirror) runs a complex mean and a broadcast multiply over the whole
+// spectrogram.  out[b, t, f] = mask[b, f, t] / C * sum_c X[b, c, f, t], written frame-major (the
+// layout the iSTFT kernels stream), X and mask with arbitrary element strides.
+namespace {
+__global__ void __launch_bounds__(256)
+channel_mean_mask_kernel(const float2* __restrict__ X, int64_t xb, int64_t xc, int64_t xf, int64_t xt,
+                         const float* __restrict__ mask, int64_t mb, int64_t mf, int64_t mt,
+                         int n_channels, int n_bins, int64_t n_frames, float2* __restrict__ out) {
+    const int64_t b = blockIdx.z;
+    const int64_t t = (int64_t)blockIdx.y;
+    const float inv_c = 1.f / (float)n_channels;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n_bins; f += gridDim.x * blockDim.x) {
+        const float2* src = X + b * xb + (int64_t)f * xf + t * xt;
+        float re = 0.f, im = 0.f;
+        for (int c = 0; c < n_channels; ++c) {
+            const float2 v = __ldg(src + (int64_t)c * xc);
+            re += v.x;
+            im += v.y;
+        }
+        const float m = mask ? __ldg(mask + b * mb + (int64_t)f * mf + t * mt) * inv_c : inv_c;
+        out[(b * n_frames + t) * n_bins + f] = make_float2(re * m, im * m);
+    }
+}
+
+// total += mean(v): the running metric of the training loop (training.py:369-373) without two
+// ATen launches per step
+__global__ void accumulate_mean_kernel(const float* __restrict__ v, int64_t n, float* __restrict__ total) {
+    double acc = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)v[i];
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x / 32] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int k = 0; k < (int)blockDim.x / 32; ++k) t += red[k];
+        *total += (float)(t / (double)n);
+    }
+}
+}  // namespace
+
+extern "C" int brv_channel_mean_mask(const void* X, int64_t xb, int64_t xc, int64_t xf, int64_t xt,
+                                     const float* mask, int64_t mb, int64_t mf, int64_t mt,
+                                     int64_t n_batch, int n_channels, int n_bins, int64_t n_frames,
+                                     void* out, void* stream) {
+    BRV_REQUIRE(n_batch >= 0 && n_channels >= 1 && n_bins >= 1 && n_frames >= 0, "bad shape");
+    if (n_batch == 0 || n_frames == 0) return BRV_OK;
+    BRV_REQUIRE(X && out, "null pointer argument");
+    BRV_REQUIRE(n_batch < 65536 && n_frames < 65536, "more than 65535 batch items / frames per call");
+    dim3 grid((unsigned)brv_ceil_div(n_bins, 256), (unsigned)n_frames, (unsigned)n_batch);
+    channel_mean_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const float2*)X, xb, xc, xf, xt, mask, mb, mf, mt, n_channels, n_bins, n_frames, (float2*)out);
+    BRV_LAUNCH_CHECK("channel_mean_mask_kernel");
+    return BRV_OK;
+}
+
+extern "C" int brv_accumulate_mean(const float* v, int64_t n, float* total, void* stream) {
+    BRV_REQUIRE(n >= 0, "bad shape");
+    if (n == 0) return BRV_OK;
+    BRV_REQUIRE(v && total, "null pointer argument");
+    accumulate_mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(v, n, total);
+    BRV_LAUNCH_CHECK("accumulate_mean_kernel");
+    return BRV_OK;
+}

@@ -66,6 +66,39 @@ def irm(foreground_mag, background_mag, mel_fb):
     return (1 + bg / (fg + eps)).pow(-0.5)
 
 
+def channel_mean(spec, mask=None):
+    """``spec.mean(1) [* mask]`` of a ``(B, C, F, T)`` complex STFT with a real ``(B, F, T)`` mask,
+    in one pass (``FFNN._enhance``, ffnn.py:107-110).  Returns the ``(B, F, T)`` view of
+    frame-major memory that ``STFT.backward`` streams.  Not differentiable: inference path."""
+    _lib.require_cuda(spec, 'channel_mean input')
+    if spec.ndim != 4 or not spec.is_complex():
+        raise ValueError(f'expected a complex (B, C, F, T) tensor, got {tuple(spec.shape)}')
+    spec = spec.to(torch.complex64).resolve_conj().resolve_neg()
+    batch, channels, bins, frames = spec.shape
+    ms = (0, 0, 0)
+    if mask is not None:
+        _lib.require_cuda(mask, 'channel_mean mask')
+        mask = mask.float().expand(batch, bins, frames)
+        ms = mask.stride()
+    out = torch.empty((batch, frames, bins), dtype=torch.complex64, device=spec.device)
+    for start in range(0, batch, 65535):
+        sub, msub = spec[start:start + 65535], None if mask is None else mask[start:start + 65535]
+        with _lib.on_device(spec.device):
+            _lib.check(_lib.lib().brv_channel_mean_mask(
+                _lib.ptr(sub), *sub.stride(), _lib.ptr(msub), *ms, sub.shape[0], channels, bins, frames,
+                _lib.ptr(out[start:start + 65535]), _lib.stream_ptr(spec.device)))
+    return out.transpose(1, 2)
+
+
+def accumulate_mean(total, values):
+    """``total += values.mean()`` in one launch (the trainer's running loss, training.py:369-373)."""
+    v = values.detach().float().contiguous()
+    with _lib.on_device(v.device):
+        _lib.check(_lib.lib().brv_accumulate_mean(_lib.ptr(v), v.numel(), _lib.ptr(total),
+                                                  _lib.stream_ptr(v.device)))
+    return total
+
+
 def _frame_mask(x, frames):
     """Zero the columns t >= frames[b] of ``(B, ..., T)`` (what collating per-item outputs does)."""
     flat = x.reshape(x.shape[0], -1, x.shape[-1]).contiguous()
@@ -205,5 +238,5 @@ class FFNNFrontEnd:
         feats = self.features(spec, mean, std)
         mask = mask_fn(feats)
         extrapolated = self.mel_fb.backward(mask)
-        out = self.stft.backward(spec.mean(1) * extrapolated)
+        out = self.stft.backward(channel_mean(spec, extrapolated))     # one pass: mean_c X * mask
         return out[..., :length]

@@ -359,6 +359,18 @@ int brv_spec_split_grad(const float* ga, const float* gb, const void* X, int64_t
 int brv_spec_join_grad(const void* gX, const float* a, const float* b, int64_t n, int mode,
                        float* ga, float* gb, void* stream);
 
+/* FFNN._enhance's `x.mean(1) * mask` (models/ffnn/ffnn.py:107-110) in one pass:
+ * out[b, t, f] = mask[b, f, t] / C * sum_c X[b, c, f, t]; X complex64 and mask float32
+ * (nullable) with element strides, out (n_batch, n_frames, n_bins) complex64 dense --
+ * frame-major, the layout the iSTFT kernels stream.                                  */
+int brv_channel_mean_mask(const void* X, int64_t x_stride_batch, int64_t x_stride_channel,
+                          int64_t x_stride_bin, int64_t x_stride_frame, const float* mask,
+                          int64_t m_stride_batch, int64_t m_stride_bin, int64_t m_stride_frame,
+                          int64_t n_batch, int n_channels, int n_bins, int64_t n_frames,
+                          void* out, void* stream);
+/* *total += mean(v[0..n)): the running metric of the training loop (training.py:369-373). */
+int brv_accumulate_mean(const float* v, int64_t n, float* total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

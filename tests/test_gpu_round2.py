@@ -228,3 +228,20 @@ def test_exact_bench_shapes(name, kw, shape):
     assert float(err.max()) < 2e-4, (name, float(err.max()))
     for r in np.linspace(0, sel.shape[0] - 1, 8).astype(int):
         assert_parity(cpu(y[r]), O.istft(cpu(sel[r]), **kw)[..., :shape[-1]], 1e-4, f'{name} istft row {r}')
+
+
+def test_channel_mean_mask_and_accumulate():
+    """FFNN._enhance's `x.mean(1) * mask` (ffnn.py:107-110) and the running-loss update in one launch each."""
+    spec = crandn((3, 2, 257, 40), 61).to(DEV)
+    mask = randn((3, 257, 40), 62).abs().to(DEV)
+    out = brv.ffnn.channel_mean(spec, mask)
+    ref = spec.mean(1) * mask
+    assert out.shape == ref.shape and out.transpose(1, 2).is_contiguous()
+    assert torch.allclose(out, ref, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(brv.ffnn.channel_mean(spec.transpose(2, 3).contiguous().transpose(2, 3)), spec.mean(1),
+                          rtol=1e-6, atol=1e-7)
+    total = torch.zeros((), device=DEV)
+    v = randn((37,), 63).to(DEV)
+    brv.ffnn.accumulate_mean(total, v)
+    brv.ffnn.accumulate_mean(total, v)
+    assert abs(float(total) - 2 * float(v.mean())) < 1e-6
