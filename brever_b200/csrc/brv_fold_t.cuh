@@ -600,12 +600,22 @@ constexpr int IT_EPI_WARP0 = 4, IT_EPI_SET_WARPS = 4;
 constexpr int IT_BUILD_WARP0 = 12, IT_BUILD_WARPS = 8, IT_BUILD_THREADS = IT_BUILD_WARPS * 32;
 constexpr int IT_SCOUT_WARP0 = 20, IT_SCOUT_WARPS = 8, IT_SCOUT_THREADS = IT_SCOUT_WARPS * 32;
 constexpr int IT_XP = MAX_Q + 1;                              // exchange row pitch (floats)
-constexpr int IT_OFF_EXCH = T_SMEM_STAGES;                    // [set 2][buffer 2][8 frames][IT_XP]
-constexpr int IT_OFF_CARRY = IT_OFF_EXCH + 2 * 2 * 8 * IT_XP * 4;   // [consumer set 2][slot 2][6][128]
-constexpr int IT_OFF_ROWINFO = IT_OFF_CARRY + 2 * 2 * 6 * 128 * 4;  // 2 slots x 64 float4
-constexpr int IT_OFF_SCRATCH = IT_OFF_ROWINFO + 2 * T_NF * 16;      // [12][64] floats (builders 0..7, scouts 8..11)
-constexpr int IT_SMEM_BYTES = 1024 + IT_OFF_SCRATCH + 12 * T_NF * 4;
-static_assert(IT_SMEM_BYTES <= 227 * 1024, "transposed inverse kernel shared memory");
+// Shared memory of the inverse kernel for NF frames per tile (64: two TMEM buffers, 3 stages;
+// 32: four TMEM buffers, 4 stages -- more tiles in flight for launches of a few tiles per SM)
+template <int NF>
+struct ItLayout {
+    static constexpr int NBUF = T_TMEM_COLS / (4 * NF);          // tiles resident in TMEM
+    static constexpr int DATA_TILE = NF * BK * 2;
+    static constexpr int STAGE_BYTES = T_STAGE_BASIS + 4 * DATA_TILE;
+    static constexpr int STAGES = NF == 64 ? 3 : 4;
+    static constexpr int OFF_EXCH = STAGES * STAGE_BYTES;                   // [set 2][buffer 2][8 frames][IT_XP]
+    static constexpr int OFF_CARRY = OFF_EXCH + 2 * 2 * 8 * IT_XP * 4;      // [consumer set 2][slot 2][6][128]
+    static constexpr int OFF_ROWINFO = OFF_CARRY + 2 * 2 * 6 * 128 * 4;     // NBUF slots x NF float4
+    static constexpr int OFF_SCRATCH = OFF_ROWINFO + NBUF * NF * 16;        // [12][64] floats (builders 0..7, scouts 8..11)
+    static constexpr int SMEM_BYTES = 1024 + OFF_SCRATCH + 12 * 64 * 4;
+    static_assert(SMEM_BYTES <= 227 * 1024, "transposed inverse kernel shared memory");
+};
+constexpr int IT_MAX_BUF = 4;
 
 struct InvStrip {
     uint32_t g, g1, per_signal;
@@ -638,51 +648,66 @@ __device__ __noinline__ float it_edge_envelope(const float* env_per, const float
     return ola_inv_envelope(env_per, wsq, N, H, n_frames, u, off);
 }
 
-// the four values of one frame for sample offset n from its row of Ce, Co, Se, So
+// the four values of one frame for sample offset n from its row of Ce, Co, Se, So.
+// ri = { basis_scale_inv / frame scale, f[Q], f[3Q], Nyquist term } (the builders finish the first
+// three).  Nothing is masked here: stale accumulators of columns past the tile's end, and lanes
+// n >= Q, produce values that are never stored nor carried into a stored sum.
 __device__ __forceinline__ void it_frame_values(uint32_t ace, uint32_t aco, uint32_t ase, uint32_t aso,
-                                                const float4 ri, bool live, bool t0, float sgn,
-                                                const float4 wn, float bsi, float wq, float w3q,
+                                                const float4 ri, bool t0, float sgn, const float4 wn,
                                                 float& a, float& b, float& c, float& d) {
-    // columns >= ncols hold stale accumulators: select, do not multiply, them away
-    const float g0 = bsi * pow2_inv(ri.x);             // ri = scale, 2 pacc, 2 racc, nyquist term
-    const float ce = live ? __uint_as_float(ace) * g0 : 0.f;
-    const float co = live ? __uint_as_float(aco) * g0 : 0.f;
-    const float se = live ? __uint_as_float(ase) * g0 : 0.f;
-    const float so = live ? __uint_as_float(aso) * g0 : 0.f;
-    const float ny = live ? sgn * ri.w : 0.f;
-    const float cp = ce + co, cm = ce - co, sp = se + so, sm = se - so;
-    a = ((cp - sp) + ny) * wn.x;
-    b = ((cm + sm) + ny) * wn.y;
-    c = ((cm - sm) + ny) * wn.z;
-    d = ((cp + sp) + ny) * wn.w;
-    // thread 0: f[Q], f[3Q] (Q is even: the Nyquist term enters with +1); selects, not a branch
-    const float fq = live ? (ri.y - ri.z + ri.w) * wq : 0.f;
-    const float f3q = live ? (ri.y + ri.z + ri.w) * w3q : 0.f;
-    b = t0 ? fq : b;
-    d = t0 ? f3q : d;
+    const float fce = __uint_as_float(ace), fco = __uint_as_float(aco);
+    const float fse = __uint_as_float(ase), fso = __uint_as_float(aso);
+    const float ny = sgn * ri.w;
+    const float cpn = fmaf(fce + fco, ri.x, ny), cmn = fmaf(fce - fco, ri.x, ny);
+    const float spg = (fse + fso) * ri.x, smg = (fse - fso) * ri.x;
+    a = (cpn - spg) * wn.x;
+    b = (cmn + smg) * wn.y;
+    c = (cmn - smg) * wn.z;
+    d = (cpn + spg) * wn.w;
+    b = t0 ? ri.y : b;                  // thread 0 carries f[Q], f[3Q] in its b, d slots
+    d = t0 ? ri.z : d;
 }
 
-template <int HQ, bool FRAMES_FAST, bool DECOMP>
+// columns [lo, hi) of a tile whose sample index ibase + col * H lies in [0, out_len)
+__device__ __forceinline__ void it_store_range(int64_t ibase, int64_t out_len, int H, int skip, int ncols,
+                                               bool valid, int& lo, int& hi) {
+    lo = skip;
+    hi = ncols;
+    if (ibase < 0) lo = max(lo, (int)(((uint32_t)(-ibase) + (uint32_t)H - 1u) / (uint32_t)H));
+    const int64_t rem = out_len - ibase;            // col * H < rem
+    if (rem < (int64_t)ncols * H) hi = rem <= 0 ? 0 : (int)(((uint32_t)rem + (uint32_t)H - 1u) / (uint32_t)H);
+    if (!valid) hi = 0;
+}
+
+#ifdef BRV_T_NO_FENCE      // dev ablation: wrong results, timing only
+#define IT_BUILD_FENCE() do {} while (0)
+#else
+#define IT_BUILD_FENCE() fence_proxy_async()
+#endif
+template <int HQ, bool FRAMES_FAST, bool DECOMP, int NF>
 __global__ void __launch_bounds__(IT_THREADS, 1)
 istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParams p) {
+    using L = ItLayout<NF>;
+    constexpr int NBUF = L::NBUF, NSTAGE = L::STAGES, STAGE_BYTES = L::STAGE_BYTES, DATA_TILE = L::DATA_TILE;
+    static_assert(!FRAMES_FAST || NF == 64, "the bin-major builder is written for 64-frame tiles");
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[T_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[T_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full[2];     // MMA -> epilogue set
-    __shared__ __align__(8) uint64_t tmem_empty[2];    // epilogue set -> MMA
-    __shared__ __align__(8) uint64_t scale_full[2];    // scouts -> builders (frame scales ready)
-    __shared__ __align__(8) uint64_t scale_empty[2];   // epilogue set -> scouts (row info slot reusable)
-    __shared__ __align__(8) uint64_t ri_full[2];       // builders -> epilogue (rank-1 sums written)
+    __shared__ __align__(8) uint64_t full_bar[4];
+    __shared__ __align__(8) uint64_t empty_bar[4];
+    __shared__ __align__(8) uint64_t tmem_full[IT_MAX_BUF];     // MMA -> epilogue set
+    __shared__ __align__(8) uint64_t tmem_empty[IT_MAX_BUF];    // epilogue set -> MMA
+    __shared__ __align__(8) uint64_t scale_full[IT_MAX_BUF];    // scouts -> builders (frame scales ready)
+    __shared__ __align__(8) uint64_t scale_empty[IT_MAX_BUF];   // epilogue set -> scouts (row info slot reusable)
+    __shared__ __align__(8) uint64_t ri_full[IT_MAX_BUF];       // builders -> epilogue (rank-1 sums written)
     __shared__ __align__(8) uint64_t carry_full[2];    // other set -> set: carried values written
     __shared__ __align__(8) uint64_t carry_empty[2];   // set -> other set: carried values read
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     uint8_t* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* exch_base = reinterpret_cast<float*>(stages + IT_OFF_EXCH);
-    float* carry_base = reinterpret_cast<float*>(stages + IT_OFF_CARRY);
-    float4* rowinfo2 = reinterpret_cast<float4*>(stages + IT_OFF_ROWINFO);
-    float* scratch = reinterpret_cast<float*>(stages + IT_OFF_SCRATCH);
+    float* exch_base = reinterpret_cast<float*>(stages + L::OFF_EXCH);
+    float* carry_base = reinterpret_cast<float*>(stages + L::OFF_CARRY);
+    float4* rowinfo2 = reinterpret_cast<float4*>(stages + L::OFF_ROWINFO);
+    float* scratch = reinterpret_cast<float*>(stages + L::OFF_SCRATCH);
 
     const int N = p.n_fft, H = p.hop, Q = p.q, Hf = N / 2;
     const int n_kc = Q / BK;
@@ -690,16 +715,18 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
     constexpr int R = 4 / HQ;                      // frames overlapping one hop block
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < T_STAGES; ++s) {
+        for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full_bar[s], 1 + IT_BUILD_WARPS);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             mbar_init(&tmem_full[b], 1);
             mbar_init(&tmem_empty[b], IT_EPI_SET_WARPS);
             mbar_init(&scale_full[b], IT_SCOUT_WARPS);
             mbar_init(&scale_empty[b], IT_EPI_SET_WARPS);
             mbar_init(&ri_full[b], IT_BUILD_WARPS);
+        }
+        for (int b = 0; b < 2; ++b) {
             mbar_init(&carry_full[b], IT_EPI_SET_WARPS);
             mbar_init(&carry_empty[b], IT_EPI_SET_WARPS);
         }
@@ -711,7 +738,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    InvStrip strip(p.total_tiles, p.n_blocks, T_NF, R - 1, (int)blockIdx.x, (int)gridDim.x);
+    InvStrip strip(p.total_tiles, p.n_blocks, NF, R - 1, (int)blockIdx.x, (int)gridDim.x);
     int64_t sig, c0;
     int ncols, skip;
     bool fresh;
@@ -726,12 +753,12 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
             int g = 0;
             while (strip.next(sig, c0, ncols, skip, fresh))
                 for (int it = 0; it < n_it; ++it, ++g) {
-                    const int s = g % T_STAGES;
-                    const uint32_t ph = (g / T_STAGES) & 1;
+                    const int s = g % NSTAGE;
+                    const uint32_t ph = (g / NSTAGE) & 1;
                     const int kc = it >> 1, pair = it & 1;
                     T_WAITED(0, mbar_wait_relaxed(&empty_bar[s], ph ^ 1));
                     mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
-                    uint8_t* sb = stages + (size_t)s * T_STAGE_BYTES;
+                    uint8_t* sb = stages + (size_t)s * STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -747,30 +774,30 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
             T_WAIT_DECL;
             int g = 0, n = 0;
             for (; strip.next(sig, c0, ncols, skip, fresh); ++n) {
-                const int buf = n & 1;
+                const int buf = n % NBUF;
                 const uint32_t idesc = umma_idesc_f16(TILE_M, (ncols + 15) & ~15);
                 T_STAMP(2, n, 0);
-                T_WAITED(0, mbar_wait_relaxed(&tmem_empty[buf], (uint32_t)(((n >> 1) & 1) ^ 1)));
+                T_WAITED(0, mbar_wait_relaxed(&tmem_empty[buf], (uint32_t)(((n / NBUF) & 1) ^ 1)));
                 tcgen05_fence_after();
                 T_STAMP(2, n, 1);
                 for (int it = 0; it < n_it; ++it, ++g) {
-                    const int s = g % T_STAGES;
-                    const uint32_t ph = (g / T_STAGES) & 1;
+                    const int s = g % NSTAGE;
+                    const uint32_t ph = (g / NSTAGE) & 1;
                     const int kc = it >> 1, pair = it & 1;
                     T_WAITED(1, mbar_wait_relaxed(&full_bar[s], ph, 32));
                     tcgen05_fence_after();
-                    const uint32_t a0 = smem_u32(stages + (size_t)s * T_STAGE_BYTES);
+                    const uint32_t a0 = smem_u32(stages + (size_t)s * STAGE_BYTES);
                     const uint32_t b0 = a0 + T_STAGE_BASIS;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        const uint32_t d = tmem_base + (uint32_t)(buf * 4 * T_NF + (pair * 2 + j) * T_NF);
+                        const uint32_t d = tmem_base + (uint32_t)(buf * 4 * NF + (pair * 2 + j) * NF);
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
                             const uint32_t off = ks * UMMA_K * 2;
                             const uint64_t bh = umma_desc_sw64(a0 + (j * 2) * SUB_TILE + off);
                             const uint64_t bl = umma_desc_sw64(a0 + (j * 2 + 1) * SUB_TILE + off);
-                            const uint64_t dh = umma_desc_sw64(b0 + (j * 2) * T_DATA_TILE + off);
-                            const uint64_t dl = umma_desc_sw64(b0 + (j * 2 + 1) * T_DATA_TILE + off);
+                            const uint64_t dh = umma_desc_sw64(b0 + (j * 2) * DATA_TILE + off);
+                            const uint64_t dl = umma_desc_sw64(b0 + (j * 2 + 1) * DATA_TILE + off);
                             umma_f16(d, bh, dh, idesc, (kc | ks) != 0);
                             umma_f16(d, bh, dl, idesc, 1);
                             umma_f16(d, bl, dh, idesc, 1);
@@ -803,36 +830,32 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
         float* carry_out = carry_base + (set ^ 1) * (2 * 6 * 128);
         uint32_t n_in = 0, n_out = 0;              // carried-state hand-offs received / sent
         int pp = 0;                                // exchange buffer
-        InvStrip ahead = strip;
-        int64_t sig_n, c0_n;
-        int ncols_n, skip_n;
-        bool fresh_n;
-        bool more = ahead.next(sig_n, c0_n, ncols_n, skip_n, fresh_n);
         for (int n = 0; strip.next(sig, c0, ncols, skip, fresh); ++n) {
-            more = ahead.next(sig_n, c0_n, ncols_n, skip_n, fresh_n);      // tile n + 1
             if ((n & 1) != set) continue;
-            const int buf = set;
-            const float4* rowinfo = rowinfo2 + buf * T_NF;
-            const uint32_t kph = (uint32_t)((n >> 1) & 1);
+            // the next tile continues this signal (then this tile is full)
+            const bool cont = strip.g < strip.g1 && c0 + ncols < (int64_t)strip.per_signal;
+            const int buf = n % NBUF;
+            const float4* rowinfo = rowinfo2 + buf * NF;
+            const uint32_t kph = (uint32_t)((n >> 1) & 1);         // carried-state slot
+            const uint32_t bph = (uint32_t)((n / NBUF) & 1);       // use parity of the TMEM buffer
             if (q == 0) T_STAMP(3, n, 0);
-            T_WAITED(0, mbar_wait_relaxed(&ri_full[buf], kph));
-            T_WAITED(1, mbar_wait_relaxed(&tmem_full[buf], kph));
+            T_WAITED(0, mbar_wait_relaxed(&ri_full[buf], bph));
+            T_WAITED(1, mbar_wait_relaxed(&tmem_full[buf], bph));
             tcgen05_fence_after();
             if (q == 0) T_STAMP(3, n, 1);
-            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * T_NF);
-            if (more && !fresh_n) {
-                // ---- the next tile continues this signal (this one is full): the values its
-                //      first hop blocks need from this tile's last R - 1 frames go out first ----
+            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * NF);
+            if (cont) {
+                // ---- the values the next tile's first hop blocks need from this tile's last
+                //      R - 1 frames go out first, so that the other set can start ----
                 uint32_t A[4][8];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) tmem_ld8_nowait(tq + (uint32_t)(a * T_NF + T_NF - 8), A[a]);
+                for (int a = 0; a < 4; ++a) tmem_ld8_nowait(tq + (uint32_t)(a * NF + NF - 8), A[a]);
                 tmem_ld_wait();
                 float va[3], vb[3], vc[3], vd[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
                     it_frame_values(A[0][5 + j], A[1][5 + j], A[2][5 + j], A[3][5 + j],
-                                    rowinfo[T_NF - 3 + j], valid, t0, sgn, wn, p.basis_scale_inv, p.wq,
-                                    p.w3q, va[j], vb[j], vc[j], vd[j]);
+                                    rowinfo[NF - 3 + j], t0, sgn, wn, va[j], vb[j], vc[j], vd[j]);
                 T_WAITED(2, mbar_wait_relaxed(&carry_empty[set ^ 1], (n_out & 1) ^ 1));
                 float* co = carry_out + (int)kph * (6 * 128) + nn;
                 co[0 * 128] = vc[2];               // c(v-1)
@@ -855,22 +878,28 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&carry_empty[set]);
             }
-            float* ys = p.y + sig * p.out_len;
-            const int64_t ibase = c0 * H + nn - p.origin;        // output index of (column 0, offset n)
+            // per tile, not per column: the store ranges (sample index inside the output, column
+            // owned by this strip) and the columns whose envelope is the periodic interior one
+            const int64_t ibase = c0 * H + nn - p.origin;          // output index of (column 0, offset n)
+            float* yd = p.y + sig * p.out_len + ibase;             // never dereferenced outside [lo, hi)
+            float* ym = yd + (moff - nn);
+            int lo, hi, lo_m = 0, hi_m = 0;
+            it_store_range(ibase, p.out_len, H, skip, ncols, valid, lo, hi);
+            if (HQ == 2) it_store_range(ibase + (moff - nn), p.out_len, H, skip, ncols, valid, lo_m, hi_m);
+            const int e_lo = p.no_env ? 0 : (int)max((int64_t)0, (int64_t)(R - 1) - c0);
+            const int e_hi = p.no_env ? ncols : (int)max((int64_t)0, min((int64_t)ncols, p.n_frames - c0));
 #pragma unroll 1
             for (int cb = 0; cb < ncols; cb += 8) {
                 uint32_t A[4][8];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) tmem_ld8_nowait(tq + (uint32_t)(a * T_NF + cb), A[a]);
+                for (int a = 0; a < 4; ++a) tmem_ld8_nowait(tq + (uint32_t)(a * NF + cb), A[a]);
                 tmem_ld_wait();
                 float dv[8], mv[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int col = cb + j;
                     float a, b, c, d;
-                    it_frame_values(A[0][j], A[1][j], A[2][j], A[3][j], rowinfo[min(col, T_NF - 1)],
-                                    col < ncols && valid, t0, sgn, wn, p.basis_scale_inv, p.wq, p.w3q,
-                                    a, b, c, d);
+                    it_frame_values(A[0][j], A[1][j], A[2][j], A[3][j], rowinfo[min(cb + j, NF - 1)], t0, sgn,
+                                    wn, a, b, c, d);
                     if (HQ == 1) {
                         dv[j] = a + c2; mv[j] = b1 + d3;
                         c2 = c1; c1 = c; d3 = d2; d2 = d1; d1 = d; b1 = b;
@@ -888,6 +917,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         mbar_arrive(&scale_empty[buf]);
                     }
                 }
+                const bool interior = cb >= e_lo && cb + 8 <= e_hi;      // the whole batch (warp-uniform)
                 if (HQ == 1) {
                     float* xb = exch + pp * (8 * IT_XP);
                     pp ^= 1;
@@ -896,33 +926,52 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         for (int j = 0; j < 8; ++j) xb[j * IT_XP + moff] = mv[j];
                     }
                     named_bar_sync(3 + set, IT_EPI_SET_WARPS * 32);
+                    if (interior) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = cb + j;
-                        const int64_t u = c0 + col;
-                        const int64_t i = ibase + (int64_t)col * H;
-                        if (col >= skip && col < ncols && valid && i >= 0 && i < p.out_len) {
-                            const float v = dv[j] + xb[j * IT_XP + nn];
-                            const bool interior = p.no_env || (u >= R - 1 && u <= p.n_frames - 1);
-                            ys[i] = v * (interior ? env_n
-                                                  : it_edge_envelope(p.env_per, p.wsq, N, H, p.n_frames, u, nn));
+                        for (int j = 0; j < 8; ++j) {
+                            const int col = cb + j;
+                            if (col >= lo && col < hi) yd[col * H] = (dv[j] + xb[j * IT_XP + nn]) * env_n;
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int j = 0; j < 8; ++j) {
+                            const int col = cb + j;
+                            if (col >= lo && col < hi) {
+                                float v = dv[0];
+#pragma unroll
+                                for (int jj = 1; jj < 8; ++jj) v = j == jj ? dv[jj] : v;
+                                const bool in = col >= e_lo && col < e_hi;
+                                yd[col * H] = (v + xb[j * IT_XP + nn]) *
+                                              (in ? env_n : it_edge_envelope(p.env_per, p.wsq, N, H, p.n_frames,
+                                                                             c0 + col, nn));
+                            }
                         }
                     }
                 } else {
+                    if (interior) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = cb + j;
-                        const int64_t u = c0 + col;
-                        const int64_t i = ibase + (int64_t)col * H;
-                        const int64_t im = i + (moff - nn);
-                        if (col >= skip && col < ncols && valid) {
-                            const bool interior = p.no_env || (u >= R - 1 && u <= p.n_frames - 1);
-                            if (i >= 0 && i < p.out_len)
-                                ys[i] = dv[j] * (interior ? env_n
-                                                          : it_edge_envelope(p.env_per, p.wsq, N, H, p.n_frames, u, nn));
-                            if (im >= 0 && im < p.out_len)
-                                ys[im] = mv[j] * (interior ? env_m
-                                                           : it_edge_envelope(p.env_per, p.wsq, N, H, p.n_frames, u, moff));
+                        for (int j = 0; j < 8; ++j) {
+                            const int col = cb + j;
+                            if (col >= lo && col < hi) yd[col * H] = dv[j] * env_n;
+                            if (col >= lo_m && col < hi_m) ym[col * H] = mv[j] * env_m;
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int j = 0; j < 8; ++j) {
+                            const int col = cb + j;
+                            float vd_ = dv[0], vm_ = mv[0];
+#pragma unroll
+                            for (int jj = 1; jj < 8; ++jj) {
+                                vd_ = j == jj ? dv[jj] : vd_;
+                                vm_ = j == jj ? mv[jj] : vm_;
+                            }
+                            const bool in = col >= e_lo && col < e_hi;
+                            if (col >= lo && col < hi)
+                                yd[col * H] = vd_ * (in ? env_n : it_edge_envelope(p.env_per, p.wsq, N, H,
+                                                                                   p.n_frames, c0 + col, nn));
+                            if (col >= lo_m && col < hi_m)
+                                ym[col * H] = vm_ * (in ? env_m : it_edge_envelope(p.env_per, p.wsq, N, H,
+                                                                                   p.n_frames, c0 + col, moff));
                         }
                     }
                 }
@@ -939,15 +988,15 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
         int g = 0;
         if (FRAMES_FAST) {
             // lanes along frames: thread = (frame row, 8 k = 16 bins of every 32-wide k-chunk)
-            const int row = bt & (T_NF - 1), kq = bt >> 6;
+            const int row = bt & (NF - 1), kq = bt >> 6;
             const uint32_t sw = (uint32_t)((row >> 1) & 3);
             for (int n = 0; strip.next(sig, c0, ncols, skip, fresh); ++n) {
-                const int slot = n & 1;
-                float4* rowinfo = rowinfo2 + slot * T_NF;
+                const int slot = n % NBUF;
+                float4* rowinfo = rowinfo2 + slot * NF;
                 const bool live = row < ncols && c0 + row < p.n_frames;
                 const float2* xr = p.spec + sig * p.ss + (c0 + (live ? row : 0)) * p.sf;
                 if (bw == 0) T_STAMP(1, n, 0);
-                T_WAITED(0, mbar_wait_relaxed(&scale_full[slot], (uint32_t)((n >> 1) & 1), 20));
+                T_WAITED(0, mbar_wait_relaxed(&scale_full[slot], (uint32_t)((n / NBUF) & 1), 20));
                 if (bw == 0) T_STAMP(1, n, 1);
                 const float sc = live ? rowinfo[row].x : 0.f;
                 float pacc = 0.f, racc = 0.f;
@@ -971,10 +1020,10 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                     if (bin0 == 0) pacc -= 0.5f * c[0].x;             // c_0 = 1, the others 2
 #pragma unroll
                     for (int pair = 0; pair < 2; ++pair, ++g) {
-                        const int s = g % T_STAGES;
-                        const uint32_t ph = (g / T_STAGES) & 1;
+                        const int s = g % NSTAGE;
+                        const uint32_t ph = (g / NSTAGE) & 1;
                         T_WAITED(2, mbar_wait_relaxed(&empty_bar[s], ph ^ 1, 20));
-                        uint8_t* sa = stages + (size_t)s * T_STAGE_BYTES + T_STAGE_BASIS + row * (BK * 2);
+                        uint8_t* sa = stages + (size_t)s * STAGE_BYTES + T_STAGE_BASIS + row * (BK * 2);
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {          // sub-GEMM: even / odd bins
                             uint32_t hi[4], lo[4];
@@ -990,23 +1039,26 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                                 lo[e] = *reinterpret_cast<const uint32_t*>(&l);
                             }
                             const uint32_t dst = (((uint32_t)kq) ^ sw) << 4;
-                            *reinterpret_cast<uint4*>(sa + (j * 2) * T_DATA_TILE + dst) =
+                            *reinterpret_cast<uint4*>(sa + (j * 2) * DATA_TILE + dst) =
                                 make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4*>(sa + (j * 2 + 1) * T_DATA_TILE + dst) =
+                            *reinterpret_cast<uint4*>(sa + (j * 2 + 1) * DATA_TILE + dst) =
                                 make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                         if (pair == 1 && kc == n_kc - 1) {
-                            scratch[kq * T_NF + row] = pacc;
-                            scratch[4 * T_NF + kq * T_NF + row] = racc;
+                            scratch[kq * NF + row] = pacc;
+                            scratch[4 * NF + kq * NF + row] = racc;
                             T_WAITED(3, named_bar_sync(1, IT_BUILD_THREADS));
                             if (kq == 0) {
-                                rowinfo[row].y = 2.f * ((scratch[row] + scratch[T_NF + row]) +
-                                                        (scratch[2 * T_NF + row] + scratch[3 * T_NF + row]));
-                                rowinfo[row].z = 2.f * ((scratch[4 * T_NF + row] + scratch[5 * T_NF + row]) +
-                                                        (scratch[6 * T_NF + row] + scratch[7 * T_NF + row]));
+                                const float pa = 2.f * ((scratch[row] + scratch[NF + row]) +
+                                                        (scratch[2 * NF + row] + scratch[3 * NF + row]));
+                                const float ra = 2.f * ((scratch[4 * NF + row] + scratch[5 * NF + row]) +
+                                                        (scratch[6 * NF + row] + scratch[7 * NF + row]));
+                                const float ny = rowinfo[row].w;
+                                rowinfo[row] = make_float4(sc > 0.f ? p.basis_scale_inv * pow2_inv(sc) : 0.f,
+                                                           (pa - ra + ny) * p.wq, (pa + ra + ny) * p.w3q, ny);
                             }
                         }
-                        fence_proxy_async();
+                        IT_BUILD_FENCE();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&full_bar[s]);
                     }
@@ -1021,7 +1073,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
             const int half = lane >> 4;
             const int pr = lane & 15;              // m pair inside the 32-wide k-chunk
             const uint32_t chunk = (uint32_t)(pr >> 2);
-            constexpr int RI = T_NF / IT_BUILD_WARPS / 2;     // 4 row pairs per warp
+            constexpr int RI = NF / IT_BUILD_WARPS / 2;     // 4 row pairs per warp
             // bins 2 m0 .. 2 m0 + 3 (m0 = 32 kc + 2 pr) of the warp's frames of k-chunk kc
             auto load_chunk = [&](float2 (&dst)[RI][4], int64_t sig_, int64_t c0_, int ncols_, int kc) {
 #pragma unroll
@@ -1054,10 +1106,10 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 }
 #pragma unroll
                 for (int pair = 0; pair < 2; ++pair, ++g) {
-                    const int s = g % T_STAGES;
-                    const uint32_t ph = (g / T_STAGES) & 1;
+                    const int s = g % NSTAGE;
+                    const uint32_t ph = (g / NSTAGE) & 1;
                     T_WAITED(2, mbar_wait_relaxed(&empty_bar[s], ph ^ 1, 20));
-                    uint8_t* sa = stages + (size_t)s * T_STAGE_BYTES + T_STAGE_BASIS;
+                    uint8_t* sa = stages + (size_t)s * STAGE_BYTES + T_STAGE_BASIS;
 #pragma unroll
                     for (int i = 0; i < RI; ++i) {
                         const int row = bw * (2 * RI) + 2 * i + half;
@@ -1065,12 +1117,12 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         uint8_t* dst = sa + row * (BK * 2) +
                                        ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
                         if (pair == 0) {
-                            split_store(dst, dst + T_DATA_TILE, cur[i][0].x * sc, cur[i][2].x * sc);
-                            split_store(dst + 2 * T_DATA_TILE, dst + 3 * T_DATA_TILE, cur[i][1].x * sc,
+                            split_store(dst, dst + DATA_TILE, cur[i][0].x * sc, cur[i][2].x * sc);
+                            split_store(dst + 2 * DATA_TILE, dst + 3 * DATA_TILE, cur[i][1].x * sc,
                                         cur[i][3].x * sc);
                         } else {
-                            split_store(dst, dst + T_DATA_TILE, cur[i][0].y * sc, cur[i][2].y * sc);
-                            split_store(dst + 2 * T_DATA_TILE, dst + 3 * T_DATA_TILE, cur[i][1].y * sc,
+                            split_store(dst, dst + DATA_TILE, cur[i][0].y * sc, cur[i][2].y * sc);
+                            split_store(dst + 2 * DATA_TILE, dst + 3 * DATA_TILE, cur[i][1].y * sc,
                                         cur[i][3].y * sc);
                         }
                     }
@@ -1086,53 +1138,71 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                             }
                             const int row = bw * (2 * RI) + 2 * i + half;
                             if (pr == 0) {
-                                rowinfo[row].y = 2.f * a;
-                                rowinfo[row].z = 2.f * b;
+                                // what the epilogue needs: 1 / scales, f[Q] and f[3Q] (Q is even: the
+                                // Nyquist term enters them with +1), the Nyquist term
+                                const float ny = rowinfo[row].w, sc = rscale[i];
+                                rowinfo[row] = make_float4(sc > 0.f ? p.basis_scale_inv * pow2_inv(sc) : 0.f,
+                                                           (2.f * a - 2.f * b + ny) * p.wq,
+                                                           (2.f * a + 2.f * b + ny) * p.w3q, ny);
                             }
                         }
                     }
-                    fence_proxy_async();
+                    IT_BUILD_FENCE();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full_bar[s]);
                 }
             };
-            float2 bufa[RI][4], bufb[RI][4];
-            const bool even_kc = (n_kc & 1) == 0;  // buffers then alternate cleanly across tiles
-            InvStrip ahead = strip;                // runs one tile ahead (prefetch of its first k-chunk)
-            int64_t sig_n, c0_n;
-            int ncols_n, skip_n;
-            bool fresh_n;
-            bool more = ahead.next(sig_n, c0_n, ncols_n, skip_n, fresh_n);
-            if (more && even_kc) load_chunk(bufa, sig_n, c0_n, ncols_n, 0);
-            for (int n = 0; strip.next(sig, c0, ncols, skip, fresh); ++n) {
-                const int slot = n & 1;
-                rowinfo = rowinfo2 + slot * T_NF;
-                more = ahead.next(sig_n, c0_n, ncols_n, skip_n, fresh_n);
-                if (!even_kc) load_chunk(bufa, sig, c0, ncols, 0);
-                if (bw == 0) T_STAMP(1, n, 0);
-                T_WAITED(0, mbar_wait_relaxed(&scale_full[slot], (uint32_t)((n >> 1) & 1), 20));
-                if (bw == 0) T_STAMP(1, n, 1);
-#pragma unroll
-                for (int i = 0; i < RI; ++i) {
-                    pacc[i] = racc[i] = 0.f;
-                    const int row = bw * (2 * RI) + 2 * i + half;
-                    rscale[i] = (row < ncols && c0 + row < p.n_frames) ? rowinfo[row].x : 0.f;
+            // The k-chunks of all the strip's tiles form one stream; NB register buffers rotate
+            // over it, so the loads of the next NB - 1 chunks (also across tiles) are in flight while
+            // one is converted: a warp's few KB per chunk need that depth to cover the L2 latency.
+            constexpr int NB = NF == 32 ? 4 : 2;
+            float2 ring[NB][RI][4];
+            InvStrip ahead = strip;                // load cursor
+            int64_t sig_l, c0_l;
+            int ncols_l, skip_l, kc_l = 0;
+            bool fresh_l;
+            bool more_l = ahead.next(sig_l, c0_l, ncols_l, skip_l, fresh_l);
+            auto load_next = [&](float2 (&dst)[RI][4]) {
+                if (!more_l) return;
+                load_chunk(dst, sig_l, c0_l, ncols_l, kc_l);
+                if (++kc_l == n_kc) {
+                    kc_l = 0;
+                    more_l = ahead.next(sig_l, c0_l, ncols_l, skip_l, fresh_l);
                 }
-                for (int kc = 0; kc < n_kc; kc += 2) {
-                    // buffer a holds k-chunk kc; the loads of the chunk after it (of this tile, or the
-                    // first of the next tile) fly while it is converted
-                    if (kc + 1 < n_kc) load_chunk(bufb, sig, c0, ncols, kc + 1);
-                    convert(bufa, kc);
-                    if (kc + 1 < n_kc) {
-                        if (kc + 2 < n_kc) load_chunk(bufa, sig, c0, ncols, kc + 2);
-                        else if (more) load_chunk(bufa, sig_n, c0_n, ncols_n, 0);
-                        convert(bufb, kc + 1);
+            };
+#pragma unroll
+            for (int u = 0; u < NB - 1; ++u) load_next(ring[u]);
+            bool more = strip.next(sig, c0, ncols, skip, fresh);
+            int n = 0, kc = 0, slot = 0;
+            while (more) {
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    if (!more) break;
+                    load_next(ring[(u + NB - 1) % NB]);
+                    if (kc == 0) {
+                        slot = n % NBUF;
+                        rowinfo = rowinfo2 + slot * NF;
+                        if (bw == 0) T_STAMP(1, n, 0);
+                        T_WAITED(0, mbar_wait_relaxed(&scale_full[slot], (uint32_t)((n / NBUF) & 1), 20));
+                        if (bw == 0) T_STAMP(1, n, 1);
+#pragma unroll
+                        for (int i = 0; i < RI; ++i) {
+                            pacc[i] = racc[i] = 0.f;
+                            const int row = bw * (2 * RI) + 2 * i + half;
+                            rscale[i] = (row < ncols && c0 + row < p.n_frames) ? rowinfo[row].x : 0.f;
+                        }
+                    }
+                    convert(ring[u], kc);
+                    if (++kc == n_kc) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ri_full[slot]);
+                        if (bw == 0) T_STAMP(1, n, 2);
+                        if (bw == 0) T_WAIT_FLUSH(1);
+                        kc = 0;
+                        ++n;
+                        more = strip.next(sig, c0, ncols, skip, fresh);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ri_full[slot]);
-                if (bw == 0) T_STAMP(1, n, 2);
-                if (bw == 0) T_WAIT_FLUSH(1);
             }
         }
     } else {
@@ -1141,16 +1211,16 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
         T_WAIT_DECL;
         const int sw = warp - IT_SCOUT_WARP0;      // 0..7
         for (int n = 0; strip.next(sig, c0, ncols, skip, fresh); ++n) {
-            const int slot = n & 1;
-            float4* ri = rowinfo2 + slot * T_NF;
+            const int slot = n % NBUF;
+            float4* ri = rowinfo2 + slot * NF;
             const float2* xs = p.spec + sig * p.ss;
             if (sw == 0) T_STAMP(0, n, 0);
-            T_WAITED(0, mbar_wait_relaxed(&scale_empty[slot], (uint32_t)(((n >> 1) & 1) ^ 1)));
+            T_WAITED(0, mbar_wait_relaxed(&scale_empty[slot], (uint32_t)(((n / NBUF) & 1) ^ 1)));
             if (sw == 0) T_STAMP(0, n, 1);
             if (FRAMES_FAST) {
                 // thread = (frame, quarter of the 16-bin groups); lanes along frames
                 const int st = sw * 32 + lane;
-                const int row = st & (T_NF - 1), part = st >> 6;       // part 0..3
+                const int row = st & (NF - 1), part = st >> 6;       // part 0..3
                 const bool live = row < ncols && c0 + row < p.n_frames;
                 const float2* col = xs + (c0 + (live ? row : 0)) * p.sf;
                 float m = 0.f;
@@ -1165,15 +1235,15 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         m = fmaxf(m, abs2_finite(prep_bin<DECOMP>(v[e], p.pre_scale, p.pre_expo)));
                 }
                 // scratch rows 8.. are the scouts' (the builders use rows 0..7)
-                float* sc = scratch + 8 * T_NF;
-                sc[part * T_NF + row] = m;
+                float* sc = scratch + 8 * NF;
+                sc[part * NF + row] = m;
                 T_WAITED(1, named_bar_sync(2, IT_SCOUT_THREADS));
                 if (part == 0) {
                     float ny = 0.f;
                     if (live)
                         ny = prep_bin<DECOMP>(__ldg(col + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x *
                              p.edge_gain;
-                    const float mm = fmaxf(fmaxf(sc[row], sc[T_NF + row]), fmaxf(sc[2 * T_NF + row], sc[3 * T_NF + row]));
+                    const float mm = fmaxf(fmaxf(sc[row], sc[NF + row]), fmaxf(sc[2 * NF + row], sc[3 * NF + row]));
                     ri[row] = make_float4(live ? row_scale(mm) : 1.f, 0.f, 0.f, ny);
                 }
                 T_WAITED(1, named_bar_sync(2, IT_SCOUT_THREADS));
@@ -1181,7 +1251,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 // warp = frame (bins contiguous), two frames in flight per warp
                 const int nj = Q / 16;             // 32-bin groups below the Nyquist bin
 #pragma unroll 1
-                for (int r0 = 2 * sw; r0 < T_NF; r0 += 2 * IT_SCOUT_WARPS) {
+                for (int r0 = 2 * sw; r0 < NF; r0 += 2 * IT_SCOUT_WARPS) {
                     float2 v[2][8];
                     float2 vn[2];
 #pragma unroll
@@ -1204,7 +1274,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                             m = fmaxf(m, abs2_finite(prep_bin<DECOMP>(v[r][j], p.pre_scale, p.pre_expo)));
 #pragma unroll
                         for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                        if (lane == 0 && row < T_NF) {
+                        if (lane == 0 && row < NF) {
                             const bool live = row < ncols && c0 + row < p.n_frames;
                             const float ny = prep_bin<DECOMP>(vn[r], p.pre_scale, p.pre_expo).x * p.edge_gain;
                             ri[row] = make_float4(live ? row_scale(m) : 1.f, 0.f, 0.f, live ? ny : 0.f);

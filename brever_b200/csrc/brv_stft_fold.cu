@@ -2113,14 +2113,21 @@ int brv_fold_plan_init(brv_stft_plan* p) {
                                      INV_SMEM_BYTES) != cudaSuccess)
                 rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_fold_kernel)");
         const void* tkernels[8] = {
-            (const void*)istft_t_kernel<1, false, false>, (const void*)istft_t_kernel<1, true, false>,
-            (const void*)istft_t_kernel<2, false, false>, (const void*)istft_t_kernel<2, true, false>,
-            (const void*)istft_t_kernel<1, false, true>, (const void*)istft_t_kernel<1, true, true>,
-            (const void*)istft_t_kernel<2, false, true>, (const void*)istft_t_kernel<2, true, true>};
+            (const void*)istft_t_kernel<1, false, false, 64>, (const void*)istft_t_kernel<1, true, false, 64>,
+            (const void*)istft_t_kernel<2, false, false, 64>, (const void*)istft_t_kernel<2, true, false, 64>,
+            (const void*)istft_t_kernel<1, false, true, 64>, (const void*)istft_t_kernel<1, true, true, 64>,
+            (const void*)istft_t_kernel<2, false, true, 64>, (const void*)istft_t_kernel<2, true, true, 64>};
         for (const void* k : tkernels)
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     IT_SMEM_BYTES) != cudaSuccess)
+                                     ItLayout<64>::SMEM_BYTES) != cudaSuccess)
                 rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_t_kernel)");
+        const void* tkernels32[4] = {
+            (const void*)istft_t_kernel<1, false, false, 32>, (const void*)istft_t_kernel<2, false, false, 32>,
+            (const void*)istft_t_kernel<1, false, true, 32>, (const void*)istft_t_kernel<2, false, true, 32>};
+        for (const void* k : tkernels32)
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ItLayout<32>::SMEM_BYTES) != cudaSuccess)
+                rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_t_kernel<32>)");
     }
     if (rc != BRV_OK) {
         free_fold(fp);
@@ -2301,24 +2308,47 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     prm.wsq = p->window_sq;
     prm.total_tiles = n_sig * prm.tiles_per_signal;
     const bool frames_fast = prm.sb != 1;
-    if (g_brv_fold_variant == 6 && !fp->odd && (fp->hq == 1 || fp->hq == 2)) {
-        // transposed strip kernel (on request only: measured slower than the one-tile-per-TMEM kernel,
-        // 70 vs 60 us on 64 x 4 s at 512 / 128; see DESIGN.md 4.2 for the ablation that explains why)
-        prm.total_tiles = n_sig * (int64_t)prm.n_blocks;     // columns (hop blocks), not tiles
-        BRV_REQUIRE(prm.total_tiles < (1LL << 31), "too many hop blocks (%lld)", (long long)prm.total_tiles);
+    // Which kernel (measured on B200, tools/t_sweep.py):
+    //   * the transposed strip kernel (istft_t_kernel) for n_fft = 512-class geometries (Q = 128)
+    //     at any launch size, and for Q = 64 with hop = Q on frame-major spectrograms;
+    //   * the one-tile-per-TMEM kernel for everything else (odd folds, hop = 4Q, Q = 64 bin-major
+    //     or hop = 2Q, Q = 32), and for a launch that is exactly one well-filled wave of its tiles.
+    // Variants 6 / 7 force the strip kernel (64- / 32-frame tiles), variant 4 the tile kernel.
+    const int64_t cols = n_sig * (int64_t)prm.n_blocks;
+    bool use_t = false, nf32 = false;
+    if (!fp->odd && (fp->hq == 1 || fp->hq == 2) && cols < (1LL << 31)) {
+        if (g_brv_fold_variant == 6 || g_brv_fold_variant == 7) {
+            use_t = true;
+            nf32 = g_brv_fold_variant == 7 && !frames_fast;
+        } else if (g_brv_fold_variant == 0) {
+            const bool one_wave = prm.total_tiles > fp->sm_count / 2 && prm.total_tiles <= fp->sm_count;
+            if (fp->q == 128) use_t = !one_wave;
+            else if (fp->q == 64) use_t = fp->hq == 1 && !frames_fast && !one_wave;
+            // 32-frame tiles (four in flight) while a strip is only a few tiles long
+            nf32 = !frames_fast && cols < 600LL * fp->sm_count;
+        }
+    }
+    if (use_t) {
+        prm.total_tiles = cols;                              // columns (hop blocks), not tiles
         const int64_t want = brv_ceil_div(prm.total_tiles, 16);
         const unsigned ctas = (unsigned)(want < fp->sm_count ? want : fp->sm_count);
-#define BRV_LAUNCH_INV_T(HQ_, FF_)                                                                \
+#define BRV_LAUNCH_INV_T(HQ_, FF_, NF_)                                                           \
     do {                                                                                          \
         if (decomp)                                                                               \
-            istft_t_kernel<HQ_, FF_, true><<<ctas, IT_THREADS, IT_SMEM_BYTES, st>>>(fp->inv.map, prm); \
+            istft_t_kernel<HQ_, FF_, true, NF_>                                                   \
+                <<<ctas, IT_THREADS, ItLayout<NF_>::SMEM_BYTES, st>>>(fp->inv.map, prm);          \
         else                                                                                      \
-            istft_t_kernel<HQ_, FF_, false><<<ctas, IT_THREADS, IT_SMEM_BYTES, st>>>(fp->inv.map, prm); \
+            istft_t_kernel<HQ_, FF_, false, NF_>                                                  \
+                <<<ctas, IT_THREADS, ItLayout<NF_>::SMEM_BYTES, st>>>(fp->inv.map, prm);          \
     } while (0)
         if (fp->hq == 1) {
-            if (frames_fast) BRV_LAUNCH_INV_T(1, true); else BRV_LAUNCH_INV_T(1, false);
+            if (frames_fast) BRV_LAUNCH_INV_T(1, true, 64);
+            else if (nf32) BRV_LAUNCH_INV_T(1, false, 32);
+            else BRV_LAUNCH_INV_T(1, false, 64);
         } else {
-            if (frames_fast) BRV_LAUNCH_INV_T(2, true); else BRV_LAUNCH_INV_T(2, false);
+            if (frames_fast) BRV_LAUNCH_INV_T(2, true, 64);
+            else if (nf32) BRV_LAUNCH_INV_T(2, false, 32);
+            else BRV_LAUNCH_INV_T(2, false, 64);
         }
 #undef BRV_LAUNCH_INV_T
         BRV_LAUNCH_CHECK("istft_t_kernel");
