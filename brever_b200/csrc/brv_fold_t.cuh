@@ -1104,12 +1104,15 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                     racc[i] += cur[i][1].y - cur[i][3].y;
                     pacc[i] -= dc_half * cur[i][0].x;
                 }
+                // both sub-GEMM pairs of the chunk (two stages) are handed over together: one
+                // proxy fence and one warp barrier per k-chunk instead of per stage
+                const int s0 = g % NSTAGE, s1 = (g + 1) % NSTAGE;
+                T_WAITED(2, mbar_wait_relaxed(&empty_bar[s0], (uint32_t)(((g / NSTAGE) & 1) ^ 1), 20));
+                T_WAITED(2, mbar_wait_relaxed(&empty_bar[s1], (uint32_t)((((g + 1) / NSTAGE) & 1) ^ 1), 20));
+                g += 2;
 #pragma unroll
-                for (int pair = 0; pair < 2; ++pair, ++g) {
-                    const int s = g % NSTAGE;
-                    const uint32_t ph = (g / NSTAGE) & 1;
-                    T_WAITED(2, mbar_wait_relaxed(&empty_bar[s], ph ^ 1, 20));
-                    uint8_t* sa = stages + (size_t)s * STAGE_BYTES + T_STAGE_BASIS;
+                for (int pair = 0; pair < 2; ++pair) {
+                    uint8_t* sa = stages + (size_t)(pair ? s1 : s0) * STAGE_BYTES + T_STAGE_BASIS;
 #pragma unroll
                     for (int i = 0; i < RI; ++i) {
                         const int row = bw * (2 * RI) + 2 * i + half;
@@ -1126,36 +1129,42 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                                         cur[i][3].y * sc);
                         }
                     }
-                    if (pair == 1 && kc == n_kc - 1) {
-                        // rank-1 sums must be visible before the tile's last stage is released
+                }
+                if (kc == n_kc - 1) {
+                    // rank-1 sums must be visible before the tile's last stage is released
 #pragma unroll
-                        for (int i = 0; i < RI; ++i) {
-                            float a = pacc[i], b = racc[i];
+                    for (int i = 0; i < RI; ++i) {
+                        float a = pacc[i], b = racc[i];
 #pragma unroll
-                            for (int o = 8; o; o >>= 1) {
-                                a += __shfl_xor_sync(0xffffffffu, a, o);
-                                b += __shfl_xor_sync(0xffffffffu, b, o);
-                            }
-                            const int row = bw * (2 * RI) + 2 * i + half;
-                            if (pr == 0) {
-                                // what the epilogue needs: 1 / scales, f[Q] and f[3Q] (Q is even: the
-                                // Nyquist term enters them with +1), the Nyquist term
-                                const float ny = rowinfo[row].w, sc = rscale[i];
-                                rowinfo[row] = make_float4(sc > 0.f ? p.basis_scale_inv * pow2_inv(sc) : 0.f,
-                                                           (2.f * a - 2.f * b + ny) * p.wq,
-                                                           (2.f * a + 2.f * b + ny) * p.w3q, ny);
-                            }
+                        for (int o = 8; o; o >>= 1) {
+                            a += __shfl_xor_sync(0xffffffffu, a, o);
+                            b += __shfl_xor_sync(0xffffffffu, b, o);
+                        }
+                        const int row = bw * (2 * RI) + 2 * i + half;
+                        if (pr == 0) {
+                            // what the epilogue needs: 1 / scales, f[Q] and f[3Q] (Q is even: the
+                            // Nyquist term enters them with +1), the Nyquist term
+                            const float ny = rowinfo[row].w, sc = rscale[i];
+                            rowinfo[row] = make_float4(sc > 0.f ? p.basis_scale_inv * pow2_inv(sc) : 0.f,
+                                                       (2.f * a - 2.f * b + ny) * p.wq,
+                                                       (2.f * a + 2.f * b + ny) * p.w3q, ny);
                         }
                     }
-                    IT_BUILD_FENCE();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[s]);
+                }
+                IT_BUILD_FENCE();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&full_bar[s0]);
+                    mbar_arrive(&full_bar[s1]);
                 }
             };
             // The k-chunks of all the strip's tiles form one stream; NB register buffers rotate
             // over it, so the loads of the next NB - 1 chunks (also across tiles) are in flight while
             // one is converted: a warp's few KB per chunk need that depth to cover the L2 latency.
-            constexpr int NB = NF == 32 ? 4 : 2;
+#ifndef BRV_T_NB
+#define BRV_T_NB 2
+#endif
+            constexpr int NB = NF == 32 ? BRV_T_NB : 2;
             float2 ring[NB][RI][4];
             InvStrip ahead = strip;                // load cursor
             int64_t sig_l, c0_l;

@@ -192,23 +192,36 @@ extern "C" int brv_spec_join_grad(const void* gX, const float* a, const float* b
 // spectrogram.  out[b, t, f] = mask[b, f, t] / C * sum_c X[b, c, f, t], written frame-major (the
 // layout the iSTFT kernels stream), X and mask with arbitrary element strides.
 namespace {
+constexpr int CM_ITEMS = 4;        // (frame, bin) elements per thread, all loads issued first
 __global__ void __launch_bounds__(256)
 channel_mean_mask_kernel(const float2* __restrict__ X, int64_t xb, int64_t xc, int64_t xf, int64_t xt,
                          const float* __restrict__ mask, int64_t mb, int64_t mf, int64_t mt,
                          int n_channels, int n_bins, int64_t n_frames, float2* __restrict__ out) {
-    const int64_t b = blockIdx.z;
-    const int64_t t = (int64_t)blockIdx.y;
+    const int64_t b = blockIdx.y;
+    const int64_t total = n_frames * n_bins;
     const float inv_c = 1.f / (float)n_channels;
-    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n_bins; f += gridDim.x * blockDim.x) {
-        const float2* src = X + b * xb + (int64_t)f * xf + t * xt;
-        float re = 0.f, im = 0.f;
-        for (int c = 0; c < n_channels; ++c) {
-            const float2 v = __ldg(src + (int64_t)c * xc);
-            re += v.x;
-            im += v.y;
+    const float2* xs = X + b * xb;
+    float re[CM_ITEMS], im[CM_ITEMS], m[CM_ITEMS];
+#pragma unroll
+    for (int k = 0; k < CM_ITEMS; ++k) {
+        const int64_t e = ((int64_t)blockIdx.x * CM_ITEMS + k) * 256 + threadIdx.x;
+        re[k] = im[k] = 0.f;
+        m[k] = inv_c;
+        if (e < total) {
+            const int64_t t = e / n_bins, f = e - t * n_bins;
+            const float2* src = xs + f * xf + t * xt;
+            for (int c = 0; c < n_channels; ++c) {
+                const float2 v = __ldg(src + (int64_t)c * xc);
+                re[k] += v.x;
+                im[k] += v.y;
+            }
+            if (mask) m[k] = __ldg(mask + b * mb + f * mf + t * mt) * inv_c;
         }
-        const float m = mask ? __ldg(mask + b * mb + (int64_t)f * mf + t * mt) * inv_c : inv_c;
-        out[(b * n_frames + t) * n_bins + f] = make_float2(re * m, im * m);
+    }
+#pragma unroll
+    for (int k = 0; k < CM_ITEMS; ++k) {
+        const int64_t e = ((int64_t)blockIdx.x * CM_ITEMS + k) * 256 + threadIdx.x;
+        if (e < total) out[b * total + e] = make_float2(re[k] * m[k], im[k] * m[k]);
     }
 }
 
@@ -237,8 +250,9 @@ extern "C" int brv_channel_mean_mask(const void* X, int64_t xb, int64_t xc, int6
     BRV_REQUIRE(n_batch >= 0 && n_channels >= 1 && n_bins >= 1 && n_frames >= 0, "bad shape");
     if (n_batch == 0 || n_frames == 0) return BRV_OK;
     BRV_REQUIRE(X && out, "null pointer argument");
-    BRV_REQUIRE(n_batch < 65536 && n_frames < 65536, "more than 65535 batch items / frames per call");
-    dim3 grid((unsigned)brv_ceil_div(n_bins, 256), (unsigned)n_frames, (unsigned)n_batch);
+    BRV_REQUIRE(n_batch < 65536, "more than 65535 batch items per call");
+    BRV_REQUIRE(n_frames * n_bins < (1LL << 40), "spectrogram too large");
+    dim3 grid((unsigned)brv_ceil_div(n_frames * n_bins, 256 * CM_ITEMS), (unsigned)n_batch);
     channel_mean_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const float2*)X, xb, xc, xf, xt, mask, mb, mf, mt, n_channels, n_bins, n_frames, (float2*)out);
     BRV_LAUNCH_CHECK("channel_mean_mask_kernel");
