@@ -1074,35 +1074,42 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
             const int pr = lane & 15;              // m pair inside the 32-wide k-chunk
             const uint32_t chunk = (uint32_t)(pr >> 2);
             constexpr int RI = NF / IT_BUILD_WARPS / 2;     // 4 row pairs per warp
-            // bins 2 m0 .. 2 m0 + 3 (m0 = 32 kc + 2 pr) of the warp's frames of k-chunk kc
-            auto load_chunk = [&](float2 (&dst)[RI][4], int64_t sig_, int64_t c0_, int ncols_, int kc) {
+            // per-thread constants: first row, swizzled byte offset of its 4 bytes inside a data block
+            const int row0 = bw * (2 * RI) + half;             // rows row0 + 2 i
+            uint32_t soff[RI];
 #pragma unroll
-                for (int i = 0; i < RI; ++i) {
-                    const int row = bw * (2 * RI) + 2 * i + half;
-                    const bool live = row < ncols_ && c0_ + row < p.n_frames;
-                    const float2* xr = p.spec + sig_ * p.ss + (c0_ + row) * p.sf + 2 * (kc * BK + 2 * pr);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        dst[i][e] = live ? __ldg(xr + e) : make_float2(0.f, 0.f);      // sb == 1
-                }
-            };
+            for (int i = 0; i < RI; ++i) {
+                const uint32_t row = (uint32_t)(row0 + 2 * i);
+                soff[i] = row * (BK * 2) + ((chunk ^ ((row >> 1) & 3u)) << 4) + (uint32_t)(pr & 3) * 4u;
+            }
+            const int64_t sf2 = 2 * p.sf;
+            // the plain path folds pre_scale into the frame scales (a power of two times it: same bits)
+            const float fold_scale = DECOMP ? 1.f : p.pre_scale;
             float pacc[RI], racc[RI], rscale[RI];
             float4* rowinfo = rowinfo2;
             // one k-chunk: scale, split, store both sub-GEMM pairs
             auto convert = [&](float2 (&cur)[RI][4], int kc) {
-                const int m0 = kc * BK + 2 * pr;   // bins 2 m0 .. 2 m0 + 3
-                const bool dc = m0 == 0;
-                const float dc_mul = dc ? p.dc_gain : 1.f, dc_half = dc ? 0.5f : 0.f;
+                if (DECOMP) {
+#pragma unroll
+                    for (int i = 0; i < RI; ++i)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            cur[i][e] = prep_bin<true>(cur[i][e], p.pre_scale, p.pre_expo);
+                }
+                if (kc == 0) {                     // the DC bin lives in lane pr = 0 of the first chunk
+                    const bool dc = pr == 0;
+                    const float dc_mul = dc ? p.dc_gain : 1.f, dc_half = dc ? 0.5f : 0.f;
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) {
+                        cur[i][0].y = dc ? 0.f : cur[i][0].y;      // Im X[0] is ignored by the c2r inverse
+                        cur[i][0].x *= dc_mul;
+                        pacc[i] -= dc_half * cur[i][0].x;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < RI; ++i) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        cur[i][e] = prep_bin<DECOMP>(cur[i][e], p.pre_scale, p.pre_expo);
-                    cur[i][0].y = dc ? 0.f : cur[i][0].y;      // Im X[0] is ignored by the c2r inverse
-                    cur[i][0].x *= dc_mul;
                     pacc[i] += cur[i][0].x - cur[i][2].x;
                     racc[i] += cur[i][1].y - cur[i][3].y;
-                    pacc[i] -= dc_half * cur[i][0].x;
                 }
                 // both sub-GEMM pairs of the chunk (two stages) are handed over together: one
                 // proxy fence and one warp barrier per k-chunk instead of per stage
@@ -1115,10 +1122,8 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                     uint8_t* sa = stages + (size_t)(pair ? s1 : s0) * STAGE_BYTES + T_STAGE_BASIS;
 #pragma unroll
                     for (int i = 0; i < RI; ++i) {
-                        const int row = bw * (2 * RI) + 2 * i + half;
                         const float sc = rscale[i];
-                        uint8_t* dst = sa + row * (BK * 2) +
-                                       ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
+                        uint8_t* dst = sa + soff[i];
                         if (pair == 0) {
                             split_store(dst, dst + DATA_TILE, cur[i][0].x * sc, cur[i][2].x * sc);
                             split_store(dst + 2 * DATA_TILE, dst + 3 * DATA_TILE, cur[i][1].x * sc,
@@ -1140,14 +1145,15 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                             a += __shfl_xor_sync(0xffffffffu, a, o);
                             b += __shfl_xor_sync(0xffffffffu, b, o);
                         }
-                        const int row = bw * (2 * RI) + 2 * i + half;
                         if (pr == 0) {
                             // what the epilogue needs: 1 / scales, f[Q] and f[3Q] (Q is even: the
                             // Nyquist term enters them with +1), the Nyquist term
-                            const float ny = rowinfo[row].w, sc = rscale[i];
-                            rowinfo[row] = make_float4(sc > 0.f ? p.basis_scale_inv * pow2_inv(sc) : 0.f,
-                                                       (2.f * a - 2.f * b + ny) * p.wq,
-                                                       (2.f * a + 2.f * b + ny) * p.w3q, ny);
+                            const float4 ri = rowinfo[row0 + 2 * i];
+                            a *= 2.f * fold_scale;
+                            b *= 2.f * fold_scale;
+                            rowinfo[row0 + 2 * i] =
+                                make_float4(rscale[i] != 0.f ? p.basis_scale_inv * pow2_inv(ri.x) : 0.f,
+                                            (a - b + ri.w) * p.wq, (a + b + ri.w) * p.w3q, ri.w);
                         }
                     }
                 }
@@ -1171,12 +1177,30 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
             int ncols_l, skip_l, kc_l = 0;
             bool fresh_l;
             bool more_l = ahead.next(sig_l, c0_l, ncols_l, skip_l, fresh_l);
+            // per load tile: pointer to this lane's 4 bins of k-chunk 0 of row0, liveness bit per row
+            const float2* base_l = p.spec;
+            uint32_t live_l = 0;
+            auto set_load_tile = [&]() {
+                base_l = p.spec + sig_l * p.ss + (c0_l + row0) * p.sf + 4 * pr;
+                live_l = 0;
+#pragma unroll
+                for (int i = 0; i < RI; ++i)
+                    if (row0 + 2 * i < ncols_l && c0_l + row0 + 2 * i < p.n_frames) live_l |= 1u << i;
+            };
+            if (more_l) set_load_tile();
+            // bins 2 m0 .. 2 m0 + 3 (m0 = 32 kc + 2 pr) of the warp's frames, next k-chunk of the stream
             auto load_next = [&](float2 (&dst)[RI][4]) {
                 if (!more_l) return;
-                load_chunk(dst, sig_l, c0_l, ncols_l, kc_l);
+                const float2* xr = base_l + kc_l * (2 * BK);
+#pragma unroll
+                for (int i = 0; i < RI; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)       // sb == 1
+                        dst[i][e] = ((live_l >> i) & 1u) ? __ldg(xr + i * sf2 + e) : make_float2(0.f, 0.f);
                 if (++kc_l == n_kc) {
                     kc_l = 0;
                     more_l = ahead.next(sig_l, c0_l, ncols_l, skip_l, fresh_l);
+                    if (more_l) set_load_tile();
                 }
             };
 #pragma unroll
@@ -1197,8 +1221,8 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
 #pragma unroll
                         for (int i = 0; i < RI; ++i) {
                             pacc[i] = racc[i] = 0.f;
-                            const int row = bw * (2 * RI) + 2 * i + half;
-                            rscale[i] = (row < ncols && c0 + row < p.n_frames) ? rowinfo[row].x : 0.f;
+                            const int row = row0 + 2 * i;
+                            rscale[i] = (row < ncols && c0 + row < p.n_frames) ? rowinfo[row].x * fold_scale : 0.f;
                         }
                     }
                     convert(ring[u], kc);
