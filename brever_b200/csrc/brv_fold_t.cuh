@@ -340,6 +340,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
         const bool alt = (pitch & 3) != 0;         // row alignment alternates between 16 and 8 bytes
         const float ps = COMPRESS ? 1.f : p.post_scale;   // without compression scale_factor folds in
         const float dcs = m == 0 ? p.dc_scale : 1.f;
+        const float nys = (p.odd && m == Q - 1) ? p.edge_scale : 1.f;   // n_fft = 4Q - 2: Nyquist = last odd bin
         const float gb = ps * p.basis_scale_inv;
         for (int n = 0; strip.next(sig, t0, ncols); ++n) {
             const int buf = n & 1;
@@ -373,7 +374,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                         const float4 ri = rowinfo[c0 + j];         // scale, nyquist sum, ee[Q], oo[Q]
                         const float g0 = gb * pow2_inv(ri.x);
                         float re_e = fmaf(__uint_as_float(r0[j]), g0, sgn * ps * ri.z) * dcs;
-                        float re_o = __uint_as_float(r1[j]) * g0;
+                        float re_o = __uint_as_float(r1[j]) * g0 * nys;
                         float im_e = __uint_as_float(r2[j]) * g0;
                         float im_o = fmaf(__uint_as_float(r3[j]), g0, -sgn * ps * ri.w);
                         if (COMPRESS) {

@@ -432,6 +432,8 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
                 f0[j] = f0[j] * g0 + sg * eeq;
                 if (j == 0 && m0 == 0) f0[j] *= p.dc_scale;        // DC bin (its Im is exactly 0)
                 f1[j] = f1[j] * g0;
+                // n_fft = 4Q - 2: the Nyquist bin is the last odd bin (Hermitian weight 1 in the gradient)
+                if (j == 15 && p.odd && m0 + 16 == p.q) f1[j] *= p.edge_scale;
                 f2[j] = f2[j] * g0;
                 f3[j] = f3[j] * g0 - sg * ooq;
             }
@@ -670,6 +672,7 @@ stft_fold2_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPa
                         float re = fmaf(__uint_as_float(r0[j]), g0, (j & 1) ? -rq : rq);   // m0 is even
                         float im = fmaf(__uint_as_float(r1[j]), g0, (j & 1) ? -iq : iq);
                         if (j == 0 && c == 0 && pass == 0) re *= p.dc_scale;     // DC bin
+                        if (j == 15 && pass == 1 && p.odd && c == Q / 16 - 1) re *= p.edge_scale;   // Nyquist (4Q - 2)
                         if (COMPRESS) {
                             compress(re, im, p.post_expo);
                             re *= p.post_scale;
@@ -1525,7 +1528,10 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                             c[0].y = 0.f;              // Im X[0] is ignored by the c2r inverse
                             c[0].x *= p.dc_gain;
                         }
-                        if (ODD && bin0 + 32 == 2 * Q) c[31].y = 0.f;   // so is Im X[N/2]
+                        if (ODD && bin0 + 32 == 2 * Q) {
+                            c[31].y = 0.f;             // so is Im X[N/2]
+                            c[31].x *= p.edge_gain;    // (1 except in the STFT gradient: unit bin weights)
+                        }
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
                             pacc += c[2 * j].x - c[2 * j + 2].x;          // (-1)^m Re X[2m]
@@ -1618,6 +1624,7 @@ istft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvPa
                         c[i][0].y = dc ? 0.f : c[i][0].y;      // Im X[0] is ignored by the c2r inverse
                         c[i][0].x *= dc_mul;
                         c[i][3].y = ny_im ? 0.f : c[i][3].y;   // so is Im X[N/2]
+                        if (ODD) c[i][3].x *= ny_im ? p.edge_gain : 1.f;
                         pacc[i] += c[i][0].x - c[i][2].x;
                         racc[i] += c[i][1].y - c[i][3].y;
                         pacc[i] -= dc_half * c[i][0].x;
@@ -1953,11 +1960,9 @@ int g_brv_fold_variant = 0;
 
 bool brv_fold_supported(const brv_stft_plan* p) { return p->fold != nullptr; }
 
-// the gradient entry points reuse the kernels with edge-bin weights that the n_fft = 4Q - 2
-// layout (k = N/2 inside the odd bins) does not carry: those plans differentiate on the generic path
-bool brv_fold_grad_supported(const brv_stft_plan* p) {
-    return p->fold != nullptr && !((const FoldPlan*)p->fold)->odd;
-}
+// the gradient entry points reuse the kernels with edge-bin weights (DC and Nyquist count once in
+// the Hermitian sums); for n_fft = 4Q - 2 the Nyquist bin is the last odd bin of the contraction
+bool brv_fold_grad_supported(const brv_stft_plan* p) { return p->fold != nullptr; }
 
 int brv_fold_plan_init(brv_stft_plan* p) {
     const int N = p->n_fft;

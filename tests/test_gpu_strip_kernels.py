@@ -125,7 +125,8 @@ def test_strip_inverse(kw, shape, layout, vi):
 
 @pytest.mark.parametrize('kw', [dict(frame_length=512, hop_length=128),
                                 dict(frame_length=512, hop_length=256, scale_factor=0.3),
-                                dict(frame_length=256, hop_length=128, normalized=False)])
+                                dict(frame_length=256, hop_length=128, normalized=False),
+                                dict(frame_length=510, hop_length=128, normalized=False)])
 @pytest.mark.parametrize('shape', [(3, 130), (160, 157)])
 def test_strip_gradients(kw, shape):
     """d iSTFT / dX on the forward strip kernel (envelope summed on the fly by its loader warp)

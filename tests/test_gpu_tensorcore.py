@@ -115,7 +115,9 @@ def test_pipelined_forward_matches_single_tile_kernel_and_oracle(kw, shape):
 @pytest.mark.parametrize('kw', [dict(frame_length=512, hop_length=128),
                                 dict(frame_length=512, hop_length=256, scale_factor=0.3),
                                 dict(frame_length=256, hop_length=128, normalized=False),
-                                dict(frame_length=400, hop_length=128, n_fft=512)])
+                                dict(frame_length=400, hop_length=128, n_fft=512),
+                                dict(frame_length=510, hop_length=128, normalized=False),   # n_fft = 4Q - 2
+                                dict(frame_length=254, hop_length=64)])
 @pytest.mark.parametrize('shape', [(2, 3), (3, 130), (160, 157), (64, 501)])
 @pytest.mark.parametrize('variant', [2, 3])
 def test_tensorcore_istft_gradient(kw, shape, variant):
@@ -156,7 +158,9 @@ def test_tensorcore_istft_gradient(kw, shape, variant):
 @pytest.mark.parametrize('kw', [dict(frame_length=512, hop_length=128),
                                 dict(frame_length=512, hop_length=256, scale_factor=0.3),
                                 dict(frame_length=256, hop_length=128, normalized=False),
-                                dict(frame_length=400, hop_length=128, n_fft=512)])
+                                dict(frame_length=400, hop_length=128, n_fft=512),
+                                dict(frame_length=510, hop_length=128, normalized=False),   # n_fft = 4Q - 2
+                                dict(frame_length=254, hop_length=64)])
 @pytest.mark.parametrize('shape', [(2, 100), (3, 4097), (160, 20000), (64, 64000)])
 def test_tensorcore_stft_gradient(kw, shape):
     """d STFT.forward / dx on the folded tcgen05 inverse kernel (all bins weigh 1, no
