@@ -73,6 +73,30 @@ def load_peaks():
                 source='fallback (B200_PROFILING.md)')
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `index`, so that the pinned
+    host buffers allocated afterwards are first touched on the GPU's NUMA node (eight ranks
+    streaming H2D from one node's memory is what stopped the end-to-end number scaling in
+    round 1).  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        if not uuid.startswith('GPU-'):
+            uuid = 'GPU-' + uuid
+        handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return 'nvml reported no local cpus inside the cpuset of this process'
+        os.sched_setaffinity(0, cpus)
+        return f'process bound to the {len(cpus)} cpus local to the gpu (nvml)'
+    except Exception as exc:        # noqa: BLE001 -- best effort, never fails the bench
+        return f'not bound ({type(exc).__name__})'
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons DURING the timed region.
 
@@ -437,6 +461,8 @@ def measure_workload(name, wl, device, rank, world, steps, warmup, use_graph=Tru
     def pack(m, f):
         return torch.cat([m.reshape(-1), f.reshape(-1)]).cpu().pin_memory()
 
+    cpus_before = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(device.index)     # before the pinned buffers are first touched
     host = [pack(m, f) for m, f in sets[:2]]
     n_mix = sets[0][0].numel()
     h2d = host[0].numel() * 4
@@ -447,6 +473,7 @@ def measure_workload(name, wl, device, rank, world, steps, warmup, use_graph=Tru
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     result = torch.empty(wl['batch'], dtype=torch.float32).pin_memory()
+    os.sched_setaffinity(0, cpus_before)           # the CPU baseline legs use every core again
     if use_graph:
         e2e_steps = [graphs.capture(full_step, *dev_bufs[b]) for b in range(2)]
     else:
@@ -498,6 +525,7 @@ def measure_workload(name, wl, device, rank, world, steps, warmup, use_graph=Tru
                   'h2d_only_ms_per_step': round(h2d_only_s * 1e3, 4),
                   'h2d_gb_per_s': round(h2d / h2d_only_s / 1e9, 1),
                   'h2d_gb_per_s_per_rank': [round(float(r), 1) for r in rates],
+                  'numa': numa,
                   'note': 'one pinned host -> device copy of mixture+target per step, double-buffered on a copy stream; '
                           'loss read back every step; h2d_only_* = the same copies with no compute (the PCIe bound)'}
     return res
@@ -770,10 +798,20 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
 
+    # exactly ONE line on stdout: libraries that print there (NCCL's version banner does) are
+    # sent to stderr, the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + '\n').encode())
+
     if args.impl == 'reference':
         out = run_reference(args, rank, world)
         if out is not None:
-            print(json.dumps(out), flush=True)
+            emit(out)
         return 0
 
     if not torch.cuda.is_available():
@@ -792,7 +830,7 @@ def main():
             import torch.distributed as dist
             dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     return 0
 
 
