@@ -690,7 +690,6 @@ __global__ void __launch_bounds__(IT_THREADS, 1)
 istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParams p) {
     using L = ItLayout<NF>;
     constexpr int NBUF = L::NBUF, NSTAGE = L::STAGES, STAGE_BYTES = L::STAGE_BYTES, DATA_TILE = L::DATA_TILE;
-    static_assert(!FRAMES_FAST || NF == 64, "the bin-major builder is written for 64-frame tiles");
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[4];
     __shared__ __align__(8) uint64_t empty_bar[4];
@@ -717,7 +716,8 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&full_bar[s], 1 + IT_BUILD_WARPS);
+            // arrivals per stage: the TMA producer + the builder warps that write it
+            mbar_init(&full_bar[s], 1 + (FRAMES_FAST ? IT_BUILD_THREADS / 32 / (IT_BUILD_THREADS / (4 * NF)) : IT_BUILD_WARPS));
             mbar_init(&empty_bar[s], 1);
         }
         for (int b = 0; b < NBUF; ++b) {
@@ -988,10 +988,14 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
         const int bt = bw * 32 + lane;             // 0..255
         int g = 0;
         if (FRAMES_FAST) {
-            // lanes along frames: thread = (frame row, 8 k = 16 bins of every 32-wide k-chunk)
-            const int row = bt & (NF - 1), kq = bt >> 6;
+            // lanes along frames: thread = (frame row, 8 k = 16 bins of a 32-wide k-chunk, group);
+            // with 32-frame tiles the 256 threads form two groups that alternate k-chunks (a group's
+            // loads are in flight while the other one converts)
+            constexpr int NGRP = IT_BUILD_THREADS / (4 * NF);
+            const int row = bt & (NF - 1), kq = (bt / NF) & 3, grp = bt / (4 * NF);
             const uint32_t sw = (uint32_t)((row >> 1) & 3);
-            for (int n = 0; strip.next(sig, c0, ncols, skip, fresh); ++n) {
+            const uint32_t dst = (((uint32_t)kq) ^ sw) << 4;
+            for (int n = 0; strip.next(sig, c0, ncols, skip, fresh); ++n, g += n_it) {
                 const int slot = n % NBUF;
                 float4* rowinfo = rowinfo2 + slot * NF;
                 const bool live = row < ncols && c0 + row < p.n_frames;
@@ -1001,7 +1005,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 if (bw == 0) T_STAMP(1, n, 1);
                 const float sc = live ? rowinfo[row].x : 0.f;
                 float pacc = 0.f, racc = 0.f;
-                for (int kc = 0; kc < n_kc; ++kc) {
+                for (int kc = grp; kc < n_kc; kc += NGRP) {
                     float2 c[16];                      // bins 64 kc + 16 kq + e
                     const int bin0 = 64 * kc + 16 * kq;
 #pragma unroll
@@ -1019,12 +1023,15 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         racc += c[2 * j + 1].y - c[2 * j + 3].y;      // (-1)^m Im X[2m+1]
                     }
                     if (bin0 == 0) pacc -= 0.5f * c[0].x;             // c_0 = 1, the others 2
+                    // both sub-GEMM pairs of the chunk (two stages) are handed over together
+                    const int g0 = g + 2 * kc;
+                    const int s0 = g0 % NSTAGE, s1 = (g0 + 1) % NSTAGE;
+                    T_WAITED(2, mbar_wait_relaxed(&empty_bar[s0], (uint32_t)(((g0 / NSTAGE) & 1) ^ 1), 20));
+                    T_WAITED(2, mbar_wait_relaxed(&empty_bar[s1], (uint32_t)((((g0 + 1) / NSTAGE) & 1) ^ 1), 20));
 #pragma unroll
-                    for (int pair = 0; pair < 2; ++pair, ++g) {
-                        const int s = g % NSTAGE;
-                        const uint32_t ph = (g / NSTAGE) & 1;
-                        T_WAITED(2, mbar_wait_relaxed(&empty_bar[s], ph ^ 1, 20));
-                        uint8_t* sa = stages + (size_t)s * STAGE_BYTES + T_STAGE_BASIS + row * (BK * 2);
+                    for (int pair = 0; pair < 2; ++pair) {
+                        uint8_t* sa = stages + (size_t)(pair ? s1 : s0) * STAGE_BYTES + T_STAGE_BASIS +
+                                      row * (BK * 2) + dst;
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {          // sub-GEMM: even / odd bins
                             uint32_t hi[4], lo[4];
@@ -1039,30 +1046,35 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                                 hi[e] = *reinterpret_cast<const uint32_t*>(&h);
                                 lo[e] = *reinterpret_cast<const uint32_t*>(&l);
                             }
-                            const uint32_t dst = (((uint32_t)kq) ^ sw) << 4;
-                            *reinterpret_cast<uint4*>(sa + (j * 2) * DATA_TILE + dst) =
+                            *reinterpret_cast<uint4*>(sa + (j * 2) * DATA_TILE) =
                                 make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4*>(sa + (j * 2 + 1) * DATA_TILE + dst) =
+                            *reinterpret_cast<uint4*>(sa + (j * 2 + 1) * DATA_TILE) =
                                 make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
-                        if (pair == 1 && kc == n_kc - 1) {
-                            scratch[kq * NF + row] = pacc;
-                            scratch[4 * NF + kq * NF + row] = racc;
-                            T_WAITED(3, named_bar_sync(1, IT_BUILD_THREADS));
-                            if (kq == 0) {
-                                const float pa = 2.f * ((scratch[row] + scratch[NF + row]) +
-                                                        (scratch[2 * NF + row] + scratch[3 * NF + row]));
-                                const float ra = 2.f * ((scratch[4 * NF + row] + scratch[5 * NF + row]) +
-                                                        (scratch[6 * NF + row] + scratch[7 * NF + row]));
-                                const float ny = rowinfo[row].w;
-                                rowinfo[row] = make_float4(sc > 0.f ? p.basis_scale_inv * pow2_inv(sc) : 0.f,
-                                                           (pa - ra + ny) * p.wq, (pa + ra + ny) * p.w3q, ny);
-                            }
-                        }
-                        IT_BUILD_FENCE();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&full_bar[s]);
                     }
+                    IT_BUILD_FENCE();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&full_bar[s0]);
+                        mbar_arrive(&full_bar[s1]);
+                    }
+                }
+                // rank-1 sums: 4 NGRP partials per frame through the scratch rows
+                scratch[(grp * 4 + kq) * NF + row] = pacc;
+                scratch[(4 * NGRP + grp * 4 + kq) * NF + row] = racc;
+                T_WAITED(3, named_bar_sync(1, IT_BUILD_THREADS));
+                if (kq == 0 && grp == 0) {
+                    float pa = 0.f, ra = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4 * NGRP; ++k) {
+                        pa += scratch[k * NF + row];
+                        ra += scratch[(4 * NGRP + k) * NF + row];
+                    }
+                    pa *= 2.f;
+                    ra *= 2.f;
+                    const float ny = rowinfo[row].w;
+                    rowinfo[row] = make_float4(sc > 0.f ? p.basis_scale_inv * pow2_inv(sc) : 0.f,
+                                               (pa - ra + ny) * p.wq, (pa + ra + ny) * p.w3q, ny);
                 }
                 T_WAITED(3, named_bar_sync(1, IT_BUILD_THREADS));       // scratch is rewritten by the next tile
                 if (lane == 0) mbar_arrive(&ri_full[slot]);
@@ -1252,13 +1264,14 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
             T_WAITED(0, mbar_wait_relaxed(&scale_empty[slot], (uint32_t)(((n / NBUF) & 1) ^ 1)));
             if (sw == 0) T_STAMP(0, n, 1);
             if (FRAMES_FAST) {
-                // thread = (frame, quarter of the 16-bin groups); lanes along frames
+                // thread = (frame, one of NPART interleaved sets of 16-bin groups); lanes along frames
+                constexpr int NPART = IT_SCOUT_THREADS / NF;
                 const int st = sw * 32 + lane;
-                const int row = st & (NF - 1), part = st >> 6;       // part 0..3
+                const int row = st & (NF - 1), part = st / NF;
                 const bool live = row < ncols && c0 + row < p.n_frames;
                 const float2* col = xs + (c0 + (live ? row : 0)) * p.sf;
                 float m = 0.f;
-                for (int b0 = 16 * part; b0 < 2 * Q; b0 += 64) {
+                for (int b0 = 16 * part; b0 < 2 * Q; b0 += 16 * NPART) {
                     float2 v[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
@@ -1268,8 +1281,8 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                     for (int e = 0; e < 16; ++e)
                         m = fmaxf(m, abs2_finite(prep_bin<DECOMP>(v[e], p.pre_scale, p.pre_expo)));
                 }
-                // scratch rows 8.. are the scouts' (the builders use rows 0..7)
-                float* sc = scratch + 8 * NF;
+                // scratch floats 512.. are the scouts' (the builders use 0..511)
+                float* sc = scratch + 512;
                 sc[part * NF + row] = m;
                 T_WAITED(1, named_bar_sync(2, IT_SCOUT_THREADS));
                 if (part == 0) {
@@ -1277,7 +1290,9 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                     if (live)
                         ny = prep_bin<DECOMP>(__ldg(col + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x *
                              p.edge_gain;
-                    const float mm = fmaxf(fmaxf(sc[row], sc[NF + row]), fmaxf(sc[2 * NF + row], sc[3 * NF + row]));
+                    float mm = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NPART; ++k) mm = fmaxf(mm, sc[k * NF + row]);
                     ri[row] = make_float4(live ? row_scale(mm) : 1.f, 0.f, 0.f, ny);
                 }
                 T_WAITED(1, named_bar_sync(2, IT_SCOUT_THREADS));

@@ -2126,9 +2126,11 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ItLayout<64>::SMEM_BYTES) != cudaSuccess)
                 rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_t_kernel)");
-        const void* tkernels32[4] = {
+        const void* tkernels32[8] = {
             (const void*)istft_t_kernel<1, false, false, 32>, (const void*)istft_t_kernel<2, false, false, 32>,
-            (const void*)istft_t_kernel<1, false, true, 32>, (const void*)istft_t_kernel<2, false, true, 32>};
+            (const void*)istft_t_kernel<1, false, true, 32>, (const void*)istft_t_kernel<2, false, true, 32>,
+            (const void*)istft_t_kernel<1, true, false, 32>, (const void*)istft_t_kernel<2, true, false, 32>,
+            (const void*)istft_t_kernel<1, true, true, 32>, (const void*)istft_t_kernel<2, true, true, 32>};
         for (const void* k : tkernels32)
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ItLayout<32>::SMEM_BYTES) != cudaSuccess)
@@ -2314,23 +2316,19 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     prm.total_tiles = n_sig * prm.tiles_per_signal;
     const bool frames_fast = prm.sb != 1;
     // Which kernel (measured on B200, tools/t_sweep.py):
-    //   * the transposed strip kernel (istft_t_kernel) for n_fft = 512-class geometries (Q = 128)
-    //     at any launch size, and for Q = 64 with hop = Q on frame-major spectrograms;
-    //   * the one-tile-per-TMEM kernel for everything else (odd folds, hop = 4Q, Q = 64 bin-major
-    //     or hop = 2Q, Q = 32), and for a launch that is exactly one well-filled wave of its tiles.
+    //   * the transposed strip kernel (istft_t_kernel, 32-frame tiles) for Q = 128 (n_fft 512-class)
+    //     and for Q = 64 with hop = Q, at any launch size and for both spectrogram layouts;
+    //   * the one-tile-per-TMEM kernel for everything else: odd folds, hop = 4Q, Q = 64 with hop = 2Q
+    //     (half of the strip kernel's epilogue lanes idle there), Q = 32.
     // Variants 6 / 7 force the strip kernel (64- / 32-frame tiles), variant 4 the tile kernel.
     const int64_t cols = n_sig * (int64_t)prm.n_blocks;
-    bool use_t = false, nf32 = false;
+    bool use_t = false, nf32 = true;
     if (!fp->odd && (fp->hq == 1 || fp->hq == 2) && cols < (1LL << 31)) {
         if (g_brv_fold_variant == 6 || g_brv_fold_variant == 7) {
             use_t = true;
-            nf32 = g_brv_fold_variant == 7 && !frames_fast;
+            nf32 = g_brv_fold_variant == 7;
         } else if (g_brv_fold_variant == 0) {
-            const bool one_wave = prm.total_tiles > fp->sm_count / 2 && prm.total_tiles <= fp->sm_count;
-            if (fp->q == 128) use_t = !one_wave;
-            else if (fp->q == 64) use_t = fp->hq == 1 && !frames_fast && !one_wave;
-            // 32-frame tiles (four in flight) while a strip is only a few tiles long
-            nf32 = !frames_fast && cols < 600LL * fp->sm_count;
+            use_t = fp->q == 128 || (fp->q == 64 && fp->hq == 1);
         }
     }
     if (use_t) {
@@ -2347,11 +2345,11 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
                 <<<ctas, IT_THREADS, ItLayout<NF_>::SMEM_BYTES, st>>>(fp->inv.map, prm);          \
     } while (0)
         if (fp->hq == 1) {
-            if (frames_fast) BRV_LAUNCH_INV_T(1, true, 64);
+            if (frames_fast) { if (nf32) BRV_LAUNCH_INV_T(1, true, 32); else BRV_LAUNCH_INV_T(1, true, 64); }
             else if (nf32) BRV_LAUNCH_INV_T(1, false, 32);
             else BRV_LAUNCH_INV_T(1, false, 64);
         } else {
-            if (frames_fast) BRV_LAUNCH_INV_T(2, true, 64);
+            if (frames_fast) { if (nf32) BRV_LAUNCH_INV_T(2, true, 32); else BRV_LAUNCH_INV_T(2, true, 64); }
             else if (nf32) BRV_LAUNCH_INV_T(2, false, 32);
             else BRV_LAUNCH_INV_T(2, false, 64);
         }
