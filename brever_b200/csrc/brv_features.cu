@@ -58,6 +58,7 @@ fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_
     int32_t* rowptr = cols + nnz;
     float* power = reinterpret_cast<float*>(rowptr + n_mel + 1);
     float* energy = power + (size_t)staged * ldP;
+    float* norm_tab = energy + (size_t)staged * ldE;       // mean[rows] | std[rows] (stack path)
 
     const int64_t b = blockIdx.x / tiles_per_item;
     const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_item) * tile;
@@ -70,6 +71,13 @@ fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_
         cols[j] = __ldg(mel_cols + j);
     }
     for (int j = threadIdx.x; j <= n_mel; j += FT_THREADS) rowptr[j] = __ldg(mel_rowptr + j);
+    if (!n_dct) {
+        const int rows_n = n_mel * (stacks + 1);
+        for (int j = threadIdx.x; j < rows_n; j += FT_THREADS) {
+            norm_tab[j] = mean ? __ldg(mean + j) : 0.f;
+            norm_tab[rows_n + j] = stdv ? __ldg(stdv + j) : 1.f;
+        }
+    }
 
     // ---- phase 1: per-bin quantity -> power[staged][n_bins] ----
     const float2* xb = X + b * sb;
@@ -115,10 +123,11 @@ fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int c = 0; c < C; ++c) {
                     float2 v[4];
+                    const float2* bc = base + (int64_t)c * sc;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int f = f0 + u * 32 + lane;
-                        v[u] = f < n_bins ? __ldg(base + (int64_t)c * sc + (int64_t)f * sf)
+                        v[u] = f < n_bins ? __ldg(sf == 1 ? bc + f : bc + (int64_t)f * sf)
                                           : make_float2(0.f, 0.f);
                     }
 #pragma unroll
@@ -149,10 +158,13 @@ fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_
     __syncthreads();
 
     // ---- phase 2: banded mel projection (stft.py:189-190) ----
-    for (int idx = threadIdx.x; idx < staged * n_mel; idx += FT_THREADS) {
-        const int s = idx / n_mel, m = idx - s * n_mel;
+    // lanes along the staged frames of one band (padded to a power of two), so that a warp's lanes
+    // walk CSR rows of (nearly) the same length: the filters are 2 .. 35 bins wide
+    const int sp_shift = 32 - __clz(staged - 1 > 0 ? staged - 1 : 1);
+    for (int idx = threadIdx.x; idx < (n_mel << sp_shift); idx += FT_THREADS) {
+        const int s = idx & ((1 << sp_shift) - 1), m = idx >> sp_shift;
         const int64_t t = first + s;
-        if (t < 0 || t >= n_frames) continue;
+        if (s >= staged || t < 0 || t >= n_frames) continue;
         const float* pw = power + (size_t)s * ldP;
         float e = 0.f;
         for (int j = rowptr[m]; j < rowptr[m + 1]; ++j) e = fmaf(vals[j], pw[cols[j]], e);
@@ -171,11 +183,11 @@ fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_
         __syncthreads();
     }
     if (compression) {
-        for (int idx = threadIdx.x; idx < staged * n_mel; idx += FT_THREADS) {
-            const int s = idx / n_mel, m = idx - s * n_mel;
-            float e = energy[s * ldE + m];
+        // (the pad column of every row is transformed too: never read)
+        for (int idx = threadIdx.x; idx < staged * ldE; idx += FT_THREADS) {
+            float e = energy[idx];
             e = compression == 1 ? logf(e + eps) : (compression == 2 ? cbrtf(e) : sqrtf(e));
-            energy[s * ldE + m] = e;
+            energy[idx] = e;
         }
         __syncthreads();
     }
@@ -220,16 +232,21 @@ fbe_features_kernel(const float2* __restrict__ X, int64_t sb, int64_t sc, int64_
     const int64_t o1 = brv_ceil_div(t_end, decimation);
     const int width = (int)(o1 - o0);
     if (width <= 0) return;
-    for (int idx = threadIdx.x; idx < rows * width; idx += FT_THREADS) {
-        int r = idx / width, w = idx - r * width;
-        int k = r / n_mel, m = r - k * n_mel;
-        int64_t t = (o0 + w) * decimation;
-        int64_t src = t - k;
-        if (src < 0) src = 0;
-        float v = energy[(int)(src - first) * ldE + m];
-        if (mean) v -= __ldg(mean + r);
-        if (stdv) v /= __ldg(stdv + r);
-        out[(b * rows + r) * out_frames + o0 + w] = v;
+    // thread = (band m, output frame w) with the frame count padded to a power of two: no integer
+    // divisions per element; mean / std come from shared memory
+    const int wp_shift = 32 - __clz(width - 1 > 0 ? width - 1 : 1);
+    float* ob = out + b * rows * out_frames + o0;
+    for (int k = 0; k <= stacks; ++k) {
+        for (int idx = threadIdx.x; idx < (n_mel << wp_shift); idx += FT_THREADS) {
+            const int w = idx & ((1 << wp_shift) - 1), m = idx >> wp_shift;
+            if (w >= width) continue;
+            const int r = k * n_mel + m;
+            int64_t src = (o0 + w) * decimation - k;
+            if (src < 0) src = 0;
+            float v = energy[(int)(src - first) * ldE + m] - norm_tab[r];
+            if (stdv) v /= norm_tab[rows + r];
+            ob[r * out_frames + w] = v;
+        }
     }
 }
 
@@ -375,7 +392,7 @@ static int launch_features(const void* X, int64_t sb, int64_t sc, int64_t sf, in
     BRV_REQUIRE(nnz >= 0 && nnz <= n_mel * n_bins, "bad CSR row pointer");
     const int staged = tile + (n_dct ? 2 : stacks);
     size_t smem = ((size_t)2 * nnz + n_mel + 1 + (size_t)staged * (n_bins | 1) +
-                   (size_t)staged * (n_mel + 1)) * sizeof(float);
+                   (size_t)staged * (n_mel + 1) + (n_dct ? 0 : (size_t)2 * n_mel * (stacks + 1))) * sizeof(float);
     BRV_REQUIRE(smem <= 200 * 1024, "feature tile does not fit shared memory (%zu bytes)", smem);
     if (smem > 48 * 1024)
         BRV_CUDA(cudaFuncSetAttribute(fbe_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
