@@ -420,6 +420,12 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
         const int shift = p.shift;
         constexpr int RI = T_NF / FT_BUILD_WARPS / 2;     // row pairs per warp (2)
         constexpr int ROWS_W = 2 * RI;                    // rows per warp (4)
+        uint32_t soff[RI];                                // swizzled byte offset of this lane's 4 bytes per row
+#pragma unroll
+        for (int i = 0; i < RI; ++i) {
+            const uint32_t row = (uint32_t)(bw * ROWS_W + 2 * i + half);
+            soff[i] = row * (BK * 2) + ((chunk ^ ((row >> 1) & 3u)) << 4) + (uint32_t)(pr & 3) * 4u;
+        }
         int g = 0;
         for (int n = 0; strip.next(sig, t0, ncols); ++n) {
             const int b = n & 1;
@@ -510,7 +516,6 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
 #endif
 #pragma unroll
                     for (int i = 0; i < RI; ++i) {
-                        const int row = bw * ROWS_W + 2 * i + half;
                         float u0, u1, v0, v1;
                         if (pair == 0) {
                             u0 = sp0[i] + rp0[i]; u1 = sp1[i] + rp1[i];    // ee
@@ -521,8 +526,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                             v0 = sm0[i] + rm0[i]; v1 = sm1[i] + rm1[i];    // oo
                         }
                         const float sc = rscale[i];
-                        uint8_t* dst = sa + row * (BK * 2) +
-                                       ((chunk ^ (uint32_t)((row >> 1) & 3)) << 4) + (pr & 3) * 4;
+                        uint8_t* dst = sa + soff[i];
                         split_store(dst, dst + T_DATA_TILE, u0 * sc, u1 * sc);
                         split_store(dst + 2 * T_DATA_TILE, dst + 3 * T_DATA_TILE, v0 * sc, v1 * sc);
                     }
@@ -603,20 +607,34 @@ constexpr int IT_SCOUT_WARP0 = 20, IT_SCOUT_WARPS = 8, IT_SCOUT_THREADS = IT_SCO
 constexpr int IT_XP = MAX_Q + 1;                              // exchange row pitch (floats)
 // Shared memory of the inverse kernel for NF frames per tile (64: two TMEM buffers, 3 stages;
 // 32: four TMEM buffers, 4 stages -- more tiles in flight for launches of a few tiles per SM)
-template <int NF>
+template <int NF, bool ODD = false>
 struct ItLayout {
     static constexpr int NBUF = T_TMEM_COLS / (4 * NF);          // tiles resident in TMEM
     static constexpr int DATA_TILE = NF * BK * 2;
     static constexpr int STAGE_BYTES = T_STAGE_BASIS + 4 * DATA_TILE;
-    static constexpr int STAGES = NF == 64 ? 3 : 4;
-    static constexpr int OFF_EXCH = STAGES * STAGE_BYTES;                   // [set 2][buffer 2][8 frames][IT_XP]
-    static constexpr int OFF_CARRY = OFF_EXCH + 2 * 2 * 8 * IT_XP * 4;      // [consumer set 2][slot 2][6][128]
+    static constexpr int STAGES = (NF == 64 || ODD) ? 3 : 4;
+    static constexpr int XPLANES = ODD ? 3 : 1;                  // exchange planes (see the odd-fold epilogue)
+    static constexpr int OFF_EXCH = STAGES * STAGE_BYTES;                   // [set 2][buffer 2][plane][8 frames][IT_XP]
+    static constexpr int OFF_CARRY = OFF_EXCH + 2 * 2 * XPLANES * 8 * IT_XP * 4;   // [consumer set 2][slot 2][6][128]
     static constexpr int OFF_ROWINFO = OFF_CARRY + 2 * 2 * 6 * 128 * 4;     // NBUF slots x NF float4
     static constexpr int OFF_SCRATCH = OFF_ROWINFO + NBUF * NF * 16;        // [12][64] floats (builders 0..7, scouts 8..11)
     static constexpr int SMEM_BYTES = 1024 + OFF_SCRATCH + 12 * 64 * 4;
     static_assert(SMEM_BYTES <= 227 * 1024, "transposed inverse kernel shared memory");
 };
 constexpr int IT_MAX_BUF = 4;
+
+// Scouts of a compressed spectrogram: the frame scale comes from a bound on the decompressed
+// magnitudes, max_k (|pre_scale X_k|)^(1 + expo), from one |X|^2 per bin and one power per frame,
+// instead of decompressing every bin a second time (the bound is at most sqrt(2) above the largest
+// component: half a bit of the split's 22)
+__device__ __forceinline__ float norm2_finite(float2 c) {
+    const float fx = finite_abs(c.x), fy = finite_abs(c.y);
+    return fminf(fmaf(fx, fx, fy * fy), 3.0e38f);
+}
+__device__ __forceinline__ float decomp_bound(float m2, float pre_scale, float expo) {
+    const float mag2 = fminf(pre_scale * pre_scale * m2, 3.0e38f);
+    return mag2 > 0.f ? fminf(sqrtf(mag2) * pow_half_expo(mag2, expo), 3.0e38f) : 0.f;
+}
 
 struct InvStrip {
     uint32_t g, g1, per_signal;
@@ -653,11 +671,22 @@ __device__ __noinline__ float it_edge_envelope(const float* env_per, const float
 // ri = { basis_scale_inv / frame scale, f[Q], f[3Q], Nyquist term } (the builders finish the first
 // three).  Nothing is masked here: stale accumulators of columns past the tile's end, and lanes
 // n >= Q, produce values that are never stored nor carried into a stored sum.
+template <bool ODD>
 __device__ __forceinline__ void it_frame_values(uint32_t ace, uint32_t aco, uint32_t ase, uint32_t aso,
                                                 const float4 ri, bool t0, float sgn, const float4 wn,
                                                 float& a, float& b, float& c, float& d) {
     const float fce = __uint_as_float(ace), fco = __uint_as_float(aco);
     const float fse = __uint_as_float(ase), fso = __uint_as_float(aso);
+    if (ODD) {
+        // n_fft = 4Q - 2: no Nyquist term outside the contraction, no self-paired samples
+        const float cp = (fce + fco) * ri.x, cm = (fce - fco) * ri.x;
+        const float sp = (fse + fso) * ri.x, sm = (fse - fso) * ri.x;
+        a = (cp - sp) * wn.x;           // f[n]
+        b = (cm + sm) * wn.y;           // f[N/2 - n]
+        c = (cm - sm) * wn.z;           // f[N/2 + n]   (n >= 1)
+        d = (cp + sp) * wn.w;           // f[N - n]     (n >= 1; the table holds 0 for n = 0)
+        return;
+    }
     const float ny = sgn * ri.w;
     const float cpn = fmaf(fce + fco, ri.x, ny), cmn = fmaf(fce - fco, ri.x, ny);
     const float spg = (fse + fso) * ri.x, smg = (fse - fso) * ri.x;
@@ -685,10 +714,11 @@ __device__ __forceinline__ void it_store_range(int64_t ibase, int64_t out_len, i
 #else
 #define IT_BUILD_FENCE() fence_proxy_async()
 #endif
-template <int HQ, bool FRAMES_FAST, bool DECOMP, int NF>
+template <int HQ, bool FRAMES_FAST, bool DECOMP, int NF, bool ODD = false>
 __global__ void __launch_bounds__(IT_THREADS, 1)
 istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParams p) {
-    using L = ItLayout<NF>;
+    using L = ItLayout<NF, ODD>;
+    static_assert(!ODD || HQ == 1, "n_fft = 4Q - 2 runs with hop = Q only");
     constexpr int NBUF = L::NBUF, NSTAGE = L::STAGES, STAGE_BYTES = L::STAGE_BYTES, DATA_TILE = L::DATA_TILE;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[4];
@@ -826,7 +856,8 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
         const int moff = HQ == 1 ? (t0 ? 0 : Q - nn) : (t0 ? Q : 2 * Q - nn);   // mirrored offset
         const float env_n = p.no_env ? 1.f : (valid ? __ldg(p.env_per + nn) : 0.f);
         const float env_m = p.no_env ? 1.f : ((valid && HQ == 2) ? __ldg(p.env_per + moff) : 0.f);
-        float* exch = exch_base + set * (2 * 8 * IT_XP);
+        constexpr int XPL = L::XPLANES * 8 * IT_XP;          // floats per exchange buffer
+        float* exch = exch_base + set * (2 * XPL);
         float* carry_in = carry_base + set * (2 * 6 * 128);
         float* carry_out = carry_base + (set ^ 1) * (2 * 6 * 128);
         uint32_t n_in = 0, n_out = 0;              // carried-state hand-offs received / sent
@@ -855,7 +886,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 float va[3], vb[3], vc[3], vd[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
-                    it_frame_values(A[0][5 + j], A[1][5 + j], A[2][5 + j], A[3][5 + j],
+                    it_frame_values<ODD>(A[0][5 + j], A[1][5 + j], A[2][5 + j], A[3][5 + j],
                                     rowinfo[NF - 3 + j], t0, sgn, wn, va[j], vb[j], vc[j], vd[j]);
                 T_WAITED(2, mbar_wait_relaxed(&carry_empty[set ^ 1], (n_out & 1) ^ 1));
                 float* co = carry_out + (int)kph * (6 * 128) + nn;
@@ -896,12 +927,26 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 for (int a = 0; a < 4; ++a) tmem_ld8_nowait(tq + (uint32_t)(a * NF + cb), A[a]);
                 tmem_ld_wait();
                 float dv[8], mv[8];
+                float* xb = exch + pp * XPL;           // (hop = Q only)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float a, b, c, d;
-                    it_frame_values(A[0][j], A[1][j], A[2][j], A[3][j], rowinfo[min(cb + j, NF - 1)], t0, sgn,
+                    it_frame_values<ODD>(A[0][j], A[1][j], A[2][j], A[3][j], rowinfo[min(cb + j, NF - 1)], t0, sgn,
                                     wn, a, b, c, d);
-                    if (HQ == 1) {
+                    if (ODD) {
+                        // n_fft = 4Q - 2: the other three segments land one sample apart from each
+                        // other's mirror (b at Q-1-n, c at n-1, d at Q-2-n; d of thread Q-1 one block
+                        // early at Q-1): three exchange planes, every slot written by exactly one thread
+                        dv[j] = a;
+                        if (valid) {
+                            float* x0 = xb + j * IT_XP;
+                            x0[Q - 1 - nn] = b1;
+                            if (nn >= 1) x0[8 * IT_XP + nn - 1] = c2;
+                            if (nn == Q - 1) x0[8 * IT_XP + Q - 1] = d2;
+                            x0[16 * IT_XP + (nn <= Q - 2 ? Q - 2 - nn : Q - 1)] = nn <= Q - 2 ? d3 : 0.f;
+                        }
+                        c2 = c1; c1 = c; d3 = d2; d2 = d1; d1 = d; b1 = b;
+                    } else if (HQ == 1) {
                         dv[j] = a + c2; mv[j] = b1 + d3;
                         c2 = c1; c1 = c; d3 = d2; d2 = d1; d1 = d; b1 = b;
                     } else {
@@ -920,13 +965,17 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 }
                 const bool interior = cb >= e_lo && cb + 8 <= e_hi;      // the whole batch (warp-uniform)
                 if (HQ == 1) {
-                    float* xb = exch + pp * (8 * IT_XP);
                     pp ^= 1;
-                    if (valid) {
+                    if (valid && !ODD) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) xb[j * IT_XP + moff] = mv[j];
                     }
                     named_bar_sync(3 + set, IT_EPI_SET_WARPS * 32);
+                    if (ODD) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            dv[j] += xb[(8 + j) * IT_XP + nn] + xb[(16 + j) * IT_XP + nn];
+                    }
                     if (interior) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -1016,6 +1065,10 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                     if (bin0 == 0) {
                         c[0].y = 0.f;                  // Im X[0] is ignored by the c2r inverse
                         c[0].x *= p.dc_gain;
+                    }
+                    if (ODD && bin0 + 16 == 2 * Q) {   // n_fft = 4Q - 2: the Nyquist bin is the last odd bin
+                        c[15].y = 0.f;
+                        c[15].x *= p.edge_gain;
                     }
 #pragma unroll
                     for (int j = 0; j < 8; j += 2) {
@@ -1117,6 +1170,15 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         cur[i][0].y = dc ? 0.f : cur[i][0].y;      // Im X[0] is ignored by the c2r inverse
                         cur[i][0].x *= dc_mul;
                         pacc[i] -= dc_half * cur[i][0].x;
+                    }
+                }
+                if (ODD && kc == n_kc - 1 && pr == 15) {
+                    // n_fft = 4Q - 2: the Nyquist bin is the last odd bin (Im ignored, unit weight
+                    // except in the STFT gradient)
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) {
+                        cur[i][3].y = 0.f;
+                        cur[i][3].x *= p.edge_gain;
                     }
                 }
 #pragma unroll
@@ -1279,7 +1341,8 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                     if (b0 == 0) v[0].y = 0.f;
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
-                        m = fmaxf(m, abs2_finite(prep_bin<DECOMP>(v[e], p.pre_scale, p.pre_expo)));
+                        m = fmaxf(m, DECOMP ? norm2_finite(v[e])
+                                            : abs2_finite(prep_bin<false>(v[e], p.pre_scale, p.pre_expo)));
                 }
                 // scratch floats 512.. are the scouts' (the builders use 0..511)
                 float* sc = scratch + 512;
@@ -1287,12 +1350,13 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 T_WAITED(1, named_bar_sync(2, IT_SCOUT_THREADS));
                 if (part == 0) {
                     float ny = 0.f;
-                    if (live)
+                    if (live && !ODD)
                         ny = prep_bin<DECOMP>(__ldg(col + (int64_t)Hf * p.sb), p.pre_scale, p.pre_expo).x *
                              p.edge_gain;
                     float mm = 0.f;
 #pragma unroll
                     for (int k = 0; k < NPART; ++k) mm = fmaxf(mm, sc[k * NF + row]);
+                    if (DECOMP) mm = decomp_bound(mm, p.pre_scale, p.pre_expo);
                     ri[row] = make_float4(live ? row_scale(mm) : 1.f, 0.f, 0.f, ny);
                 }
                 T_WAITED(1, named_bar_sync(2, IT_SCOUT_THREADS));
@@ -1311,7 +1375,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             v[r][j] = (live && j < nj) ? __ldg(xr + j * 32 + lane) : make_float2(0.f, 0.f);
-                        vn[r] = (live && lane == 0) ? __ldg(xr + Hf) : make_float2(0.f, 0.f);
+                        vn[r] = (live && lane == 0 && !ODD) ? __ldg(xr + Hf) : make_float2(0.f, 0.f);
                     }
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
@@ -1320,9 +1384,11 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         float m = 0.f;
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            m = fmaxf(m, abs2_finite(prep_bin<DECOMP>(v[r][j], p.pre_scale, p.pre_expo)));
+                            m = fmaxf(m, DECOMP ? norm2_finite(v[r][j])
+                                                : abs2_finite(prep_bin<false>(v[r][j], p.pre_scale, p.pre_expo)));
 #pragma unroll
                         for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                        if (DECOMP) m = decomp_bound(m, p.pre_scale, p.pre_expo);
                         if (lane == 0 && row < NF) {
                             const bool live = row < ncols && c0 + row < p.n_frames;
                             const float ny = prep_bin<DECOMP>(vn[r], p.pre_scale, p.pre_expo).x * p.edge_gain;

@@ -2135,6 +2135,13 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ItLayout<32>::SMEM_BYTES) != cudaSuccess)
                 rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_t_kernel<32>)");
+        const void* tkernels_odd[4] = {
+            (const void*)istft_t_kernel<1, false, false, 32, true>, (const void*)istft_t_kernel<1, true, false, 32, true>,
+            (const void*)istft_t_kernel<1, false, true, 32, true>, (const void*)istft_t_kernel<1, true, true, 32, true>};
+        for (const void* k : tkernels_odd)
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ItLayout<32, true>::SMEM_BYTES) != cudaSuccess)
+                rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_t_kernel<odd>)");
     }
     if (rc != BRV_OK) {
         free_fold(fp);
@@ -2323,7 +2330,7 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     // Variants 6 / 7 force the strip kernel (64- / 32-frame tiles), variant 4 the tile kernel.
     const int64_t cols = n_sig * (int64_t)prm.n_blocks;
     bool use_t = false, nf32 = true;
-    if (!fp->odd && (fp->hq == 1 || fp->hq == 2) && cols < (1LL << 31)) {
+    if ((fp->hq == 1 || (fp->hq == 2 && !fp->odd)) && cols < (1LL << 31)) {
         if (g_brv_fold_variant == 6 || g_brv_fold_variant == 7) {
             use_t = true;
             nf32 = g_brv_fold_variant == 7;
@@ -2344,7 +2351,23 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
             istft_t_kernel<HQ_, FF_, false, NF_>                                                  \
                 <<<ctas, IT_THREADS, ItLayout<NF_>::SMEM_BYTES, st>>>(fp->inv.map, prm);          \
     } while (0)
-        if (fp->hq == 1) {
+        if (fp->odd) {                               // n_fft = 4Q - 2: 32-frame tiles only
+            if (decomp) {
+                if (frames_fast)
+                    istft_t_kernel<1, true, true, 32, true>
+                        <<<ctas, IT_THREADS, ItLayout<32, true>::SMEM_BYTES, st>>>(fp->inv.map, prm);
+                else
+                    istft_t_kernel<1, false, true, 32, true>
+                        <<<ctas, IT_THREADS, ItLayout<32, true>::SMEM_BYTES, st>>>(fp->inv.map, prm);
+            } else {
+                if (frames_fast)
+                    istft_t_kernel<1, true, false, 32, true>
+                        <<<ctas, IT_THREADS, ItLayout<32, true>::SMEM_BYTES, st>>>(fp->inv.map, prm);
+                else
+                    istft_t_kernel<1, false, false, 32, true>
+                        <<<ctas, IT_THREADS, ItLayout<32, true>::SMEM_BYTES, st>>>(fp->inv.map, prm);
+            }
+        } else if (fp->hq == 1) {
             if (frames_fast) { if (nf32) BRV_LAUNCH_INV_T(1, true, 32); else BRV_LAUNCH_INV_T(1, true, 64); }
             else if (nf32) BRV_LAUNCH_INV_T(1, false, 32);
             else BRV_LAUNCH_INV_T(1, false, 64);

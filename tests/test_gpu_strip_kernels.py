@@ -86,6 +86,9 @@ INV_CASES = [
     dict(frame_length=128, hop_length=32),
     dict(frame_length=384, hop_length=96, compression_factor=0.5, scale_factor=0.15),
     dict(frame_length=400, hop_length=128, n_fft=512),
+    dict(frame_length=510, hop_length=128, normalized=False),                # n_fft = 4Q - 2
+    dict(frame_length=510, hop_length=128, normalized=False, compression_factor=0.5, scale_factor=0.15),
+    dict(frame_length=254, hop_length=64),
 ]
 
 
