@@ -444,6 +444,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                 const int rows_w = min(ROWS_W, ncols - bw * ROWS_W);
                 const int s_lo = (bw * ROWS_W * H + shift) & ~31;
                 const int s_hi = ((bw * ROWS_W + rows_w - 1) * H + shift + N + 31) & ~31;   // whole blocks (<= span_pad)
+#pragma unroll 4
                 for (int i0 = s_lo; i0 < s_hi; i0 += 128) {
                     const int i = i0 + lane * 4;
                     float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -459,16 +460,24 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                     if ((lane & 7) == 0 && i < s_hi) bmax[i >> 5] = __float_as_uint(m);
                 }
                 __syncwarp();
-                if (lane < rows_w) {
-                    const int row = bw * ROWS_W + lane;
+                {
+                    // eight lanes per frame walk its block maxima (a frame covers up to 17 blocks)
+                    const int rr = lane >> 3, part = lane & 7;
+                    const int row = bw * ROWS_W + rr;
                     const int b0 = (row * H + shift) >> 5, b1 = (row * H + shift + N - 1) >> 5;
                     uint32_t mx = 0u;
-                    for (int k = b0; k <= b1; ++k) mx = max(mx, bmax[k]);
-                    const float xq = span[shift + row * H + Q] * p.wq,
-                                x3q = span[shift + row * H + 3 * Q] * p.w3q;
-                    // scale, (nyquist sum: below), ee[Q], oo[Q]
-                    rowinfo[row] = make_float4(row_scale(4.f * p.wmax * __uint_as_float(mx)), 0.f,
-                                               xq + x3q, xq - x3q);
+                    if (rr < rows_w)
+                        for (int k = b0 + part; k <= b1; k += 8) mx = max(mx, bmax[k]);
+                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+                    if (part == 0 && rr < rows_w) {
+                        const float xq = span[shift + row * H + Q] * p.wq,
+                                    x3q = span[shift + row * H + 3 * Q] * p.w3q;
+                        // scale, (nyquist sum: below), ee[Q], oo[Q]
+                        rowinfo[row] = make_float4(row_scale(4.f * p.wmax * __uint_as_float(mx)), 0.f,
+                                                   xq + x3q, xq - x3q);
+                    }
                 }
                 __syncwarp();
             }
