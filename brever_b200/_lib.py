@@ -40,6 +40,10 @@ PROTOTYPES = {
                                  _ptr, _ptr, _sz, _ptr]),
     'brv_istft_forward_grad': (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _sz,
                                       _ptr]),
+    'brv_stft_forward_f64': (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr]),
+    'brv_istft_forward_f64': (_int, [_ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr]),
+    'brv_stft_forward_grad_f64': (_int, [_ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr]),
+    'brv_istft_forward_grad_f64': (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr]),
     'brv_stft_workspace_bytes': (_sz, [_ptr, _i64, _i64]),
     'brv_stft_workspace_bytes_op': (_sz, [_ptr, _i64, _i64, _int]),
     'brv_convstft_geometry': (_int, [_ptr, _i64, _ptr]),

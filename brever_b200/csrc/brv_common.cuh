@@ -57,11 +57,14 @@ struct brv_stft_plan {
     void* tc_inv;        // inverse basis^T  [2 parts][n_fft][k_pad] half
     int tc_fwd_cols, tc_inv_k;
     void* fold;          // symmetry-folded tensor-core plan, see brv_stft_fold.cu
+    double* win64;       // float64 path (brv_stft_f64.cu): window and (cos, sin)(2 pi j / N), built on first use
+    double* tw64;
     std::map<int64_t, bool> nola_cache;  // n_frames -> envelope is invertible
     std::mutex mu;
 };
 
 int brv_check_nola(const brv_stft_plan* p, int64_t n_frames);
+void brv_f64_plan_free(brv_stft_plan* p);
 static inline int brv_left(const brv_stft_plan* p) { return p->center ? p->n_fft / 2 : 0; }
 
 // simt (generic) path, brv_stft_simt.cu

@@ -119,6 +119,7 @@ extern "C" int brv_stft_plan_create(brv_stft_plan** out, int frame_length,
     p->basis_fwd = p->basis_fwd_t = p->basis_inv = p->basis_inv_t = p->window_sq = nullptr;
     p->tc_fwd = p->tc_inv = nullptr;
     p->fold = nullptr;
+    p->win64 = p->tw64 = nullptr;
     p->tc_fwd_cols = p->tc_inv_k = 0;
     if (cudaGetDevice(&p->device) != cudaSuccess) {
         delete p;
@@ -196,6 +197,7 @@ extern "C" int brv_stft_plan_destroy(brv_stft_plan* p) {
     cudaFree(p->window_sq);
     brv_tc_plan_free(p);
     brv_fold_plan_free(p);
+    brv_f64_plan_free(p);
     delete p;
     return BRV_OK;
 }

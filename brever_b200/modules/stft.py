@@ -95,6 +95,31 @@ class _IstftFunction(torch.autograd.Function):
         return g.to(ctx.in_dtype), None
 
 
+class _StftFunction64(torch.autograd.Function):
+    """float64 tensors: the double-precision kernels (brv_stft_f64.cu)."""
+    @staticmethod
+    def forward(ctx, x2d, stft):
+        ctx.stft = stft
+        ctx.samples = x2d.shape[-1]
+        return stft._forward_raw64(x2d)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return ctx.stft._forward_grad_raw64(grad, ctx.samples), None
+
+
+class _IstftFunction64(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec3d, stft):
+        ctx.stft = stft
+        ctx.frames = spec3d.shape[-1]
+        return stft._inverse_raw64(spec3d)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return ctx.stft._inverse_grad_raw64(grad, ctx.frames), None
+
+
 class STFT:
     """Short-time Fourier transform with the reference's conventions.
 
@@ -274,6 +299,58 @@ class STFT:
                     _lib.ptr(ws), nbytes, _lib.stream_ptr(grad.device)))
         return gX.transpose(1, 2)
 
+    # -- float64 tensors: double-precision kernels (torch.stft / istft compute in the input's
+    #    precision; the tensor-core path is fp32-grade) -----------------------------------------
+    def _forward_raw64(self, x2d):
+        n_sig, samples = x2d.shape
+        if x2d.stride(-1) != 1:
+            x2d = x2d.contiguous()
+        out = torch.empty((n_sig, self.n_frames(samples), self.n_bins), dtype=torch.complex128,
+                          device=x2d.device)
+        if n_sig:
+            with _lib.on_device(x2d.device):
+                _lib.check(_lib.lib().brv_stft_forward_f64(
+                    self._plan(x2d.device), _lib.ptr(x2d), n_sig, samples,
+                    x2d.stride(0) if n_sig > 1 else samples, _lib.ptr(out), _lib.stream_ptr(x2d.device)))
+        return out.transpose(1, 2)
+
+    def _forward_grad_raw64(self, grad, samples):
+        n_sig, bins, frames = grad.shape
+        grad = grad.to(torch.complex128).resolve_conj().resolve_neg()
+        gx = torch.empty((n_sig, samples), dtype=torch.float64, device=grad.device)
+        if n_sig:
+            with _lib.on_device(grad.device):
+                _lib.check(_lib.lib().brv_stft_forward_grad_f64(
+                    self._plan(grad.device), _lib.ptr(grad), grad.stride(0), grad.stride(1), grad.stride(2),
+                    n_sig, samples, _lib.ptr(gx), _lib.stream_ptr(grad.device)))
+        return gx
+
+    def _inverse_raw64(self, spec3d):
+        n_sig, bins, frames = spec3d.shape
+        if bins != self.n_bins:
+            raise RuntimeError(f'expected {self.n_bins} frequency bins, got {bins}')
+        if not self.center:
+            raise NotImplementedError('STFT.backward is implemented for center=True only')
+        spec3d = spec3d.resolve_conj().resolve_neg()
+        out_len = self.hop_length * (frames - 1) + self.n_fft - 2 * (self.n_fft // 2)
+        y = torch.empty((n_sig, out_len), dtype=torch.float64, device=spec3d.device)
+        with _lib.on_device(spec3d.device):
+            _lib.check(_lib.lib().brv_istft_forward_f64(
+                self._plan(spec3d.device, inverse=True), _lib.ptr(spec3d), spec3d.stride(0), spec3d.stride(1),
+                spec3d.stride(2), n_sig, frames, _lib.ptr(y), _lib.stream_ptr(spec3d.device)))
+        return y
+
+    def _inverse_grad_raw64(self, grad, frames):
+        n_sig = grad.shape[0]
+        grad = grad.to(torch.float64).contiguous()
+        gX = torch.empty((n_sig, frames, self.n_bins), dtype=torch.complex128, device=grad.device)
+        if n_sig:
+            with _lib.on_device(grad.device):
+                _lib.check(_lib.lib().brv_istft_forward_grad_f64(
+                    self._plan(grad.device, inverse=True), _lib.ptr(grad), n_sig, frames, _lib.ptr(gX),
+                    _lib.stream_ptr(grad.device)))
+        return gX.transpose(1, 2)
+
     # -- public API (stft.py:56-138) -------------------------------------------
     def __call__(self, x, return_type='complex'):
         return self.forward(x, return_type=return_type)
@@ -288,6 +365,16 @@ class STFT:
         in_dtype = x.dtype
         lead = x.shape[:-1]
         x2d = x.reshape(-1, x.shape[-1])
+        if in_dtype == torch.float64 and self.pad_mode == 'constant':
+            # double-precision kernels (reflect padding of float64 input still computes fp32-grade)
+            if torch.is_grad_enabled() and x2d.requires_grad:
+                spec = _StftFunction64.apply(x2d, self)
+            else:
+                spec = self._forward_raw64(x2d)
+            spec = spec.view(*lead, *spec.shape[-2:])
+            if return_type == 'complex':
+                return spec
+            return (spec.real, spec.imag) if return_type == 'real_imag' else (spec.abs(), spec.angle())
         if x2d.dtype != torch.float32:
             x2d = x2d.float()  # fp16/bf16 (AMP) and fp64 compute in fp32
         if self.pad_mode == 'reflect':
@@ -327,6 +414,12 @@ class STFT:
                      torch.complex128: torch.float64}.get(x.dtype, torch.float32)
         lead = x.shape[:-2]
         spec3d = x.reshape(-1, *x.shape[-2:])
+        if x.dtype == torch.complex128:
+            if torch.is_grad_enabled() and spec3d.requires_grad:
+                y = _IstftFunction64.apply(spec3d, self)
+            else:
+                y = self._inverse_raw64(spec3d)
+            return y.view(*lead, -1)
         if torch.is_grad_enabled() and spec3d.requires_grad:
             y = _IstftFunction.apply(spec3d, self)
         else:

@@ -150,6 +150,26 @@ size_t brv_stft_workspace_bytes(const brv_stft_plan* plan, int64_t n_signals,
 size_t brv_stft_workspace_bytes_op(const brv_stft_plan* plan, int64_t n_signals,
                                    int64_t n_frames, int op);
 
+/* ---- float64 tensors (stft.py:59-138 called with double precision input) ----
+ * torch.stft / torch.istft compute in the input's precision; the entries above are
+ * fp32-grade.  These four run the same operators as direct sums in double arithmetic
+ * (x, y, gx, gy: double; X, gX: complex128, same layouts and strides as above; no
+ * workspace).  A fidelity path: milliseconds, not microseconds.                  */
+int brv_stft_forward_f64(const brv_stft_plan* plan, const double* x,
+                         int64_t n_signals, int64_t samples, int64_t x_stride,
+                         void* out, void* stream);
+int brv_istft_forward_f64(const brv_stft_plan* plan, const void* X,
+                          int64_t stride_signal, int64_t stride_bin,
+                          int64_t stride_frame, int64_t n_signals, int64_t n_frames,
+                          double* y, void* stream);
+int brv_stft_forward_grad_f64(const brv_stft_plan* plan, const void* gX,
+                              int64_t stride_signal, int64_t stride_bin,
+                              int64_t stride_frame, int64_t n_signals,
+                              int64_t samples, double* gx, void* stream);
+int brv_istft_forward_grad_f64(const brv_stft_plan* plan, const double* gy,
+                               int64_t n_signals, int64_t n_frames, void* gX,
+                               void* stream);
+
 /* ---- ConvSTFT (stft.py:201-319) ---------------------------------------------
  * The convolutional STFT pair: analysis = F.conv1d with the windowed one-sided
  * DFT rows (DC row / sqrt(2), all / (0.5 L / sqrt(H)) when `normalized`) after
