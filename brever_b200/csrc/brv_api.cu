@@ -195,13 +195,20 @@ extern "C" int brv_istft_forward_grad(const brv_stft_plan* p, const float* gy, i
 }
 
 // ---- ConvSTFT (brever/modules/stft.py:201-319) ------------------------------------------
+int brv_direct_conv_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
+                            int64_t x_stride, double gain, void* out, int64_t n_frames, cudaStream_t st);
+int brv_direct_conv_backward(const brv_stft_plan* p, const void* X, int64_t ss, int64_t sb, int64_t sf,
+                             int64_t n_sig, int64_t n_frames, int64_t out_len, double gain, float* y,
+                             cudaStream_t st);
+
+// frame_length in {128, 256, 384, 512} with hop = L/4, L/2 or L runs on the folded tensor-core
+// kernels; any other size on the direct-sum kernels of brv_stft_f64.cu (correct, not fast)
 static int conv_check(const brv_stft_plan* p) {
     BRV_REQUIRE(p, "plan is null");
-    if (!brv_fold_conv_supported(p))
+    if (p->normalized || p->n_fft != p->frame_length || p->frame_length < p->hop || !p->onesided)
         return brv_fail(BRV_ERR_UNSUPPORTED,
-                        "ConvSTFT runs on the folded tensor-core kernels only: frame_length in "
-                        "{128, 256, 384, 512}, hop_length = frame_length / 4, / 2 or / 1, and a "
-                        "plan created with normalized = 0, n_fft = frame_length");
+                        "ConvSTFT needs a one-sided plan created with normalized = 0, n_fft = frame_length "
+                        "and hop_length <= frame_length");
     return BRV_OK;
 }
 
@@ -236,6 +243,9 @@ extern "C" int brv_convstft_forward(const brv_stft_plan* p, const float* x, int6
     if (rc != BRV_OK) return rc;
     if (n_signals == 0) return BRV_OK;
     const double gain = normalized ? 1.0 / conv_normalization(p) : 1.0;
+    if (force_generic() || !brv_fold_conv_supported(p))
+        return brv_direct_conv_forward(p, x, n_signals, samples, x_stride, gain, out, n_frames,
+                                       (cudaStream_t)stream);
     return brv_fold_conv_forward(p, x, n_signals, samples, x_stride, gain, (float2*)out, n_frames,
                                  (cudaStream_t)stream);
 }
@@ -252,6 +262,9 @@ extern "C" int brv_convstft_backward(const brv_stft_plan* p, const void* X, int6
     BRV_REQUIRE(y, "output pointer is null");
     const double nf = conv_normalization(p);
     const double gain = normalized ? 1.0 / nf : 1.0 / (nf * nf);
+    if (force_generic() || !brv_fold_conv_supported(p))
+        return brv_direct_conv_backward(p, X, ss, sb, sf, n_signals, n_frames, out_len, gain, y,
+                                        (cudaStream_t)stream);
     return brv_fold_conv_backward(p, (const float2*)X, ss, sb, sf, n_signals, n_frames, out_len,
                                   gain, y, (cudaStream_t)stream);
 }

@@ -39,17 +39,24 @@ __device__ double ola_envelope_f64(const double* __restrict__ win, int N, int H,
     return e;
 }
 
+template <typename T> struct Cplx;
+template <> struct Cplx<double> { typedef double2 type; };
+template <> struct Cplx<float> { typedef float2 type; };
+
+// T = double: the float64 entry points; T = float: the generic ConvSTFT sizes (float tensors,
+// double arithmetic)
+template <typename T>
 __global__ void __launch_bounds__(F64_THREADS)
-analysis_f64_kernel(const double* __restrict__ in, int64_t in_stride, int64_t in_len, int left, int H, int N,
+analysis_f64_kernel(const T* __restrict__ in, int64_t in_stride, int64_t in_len, int left, int H, int N,
                     int F, int64_t n_frames, const double* __restrict__ win, const double2* __restrict__ tw,
-                    double gain, double w_edge, double w_mid, double compression, double post, int use_env,
-                    double2* __restrict__ out) {
+                    double gain, double w_dc, double w_ny, double w_mid, double compression, double post,
+                    int use_env, typename Cplx<T>::type* __restrict__ out) {
     extern __shared__ double fr[];                         // windowed frame, N doubles
     const int64_t t = blockIdx.x, s = blockIdx.y;
-    const double* x = in + s * in_stride;
+    const T* x = in + s * in_stride;
     for (int n = threadIdx.x; n < N; n += F64_THREADS) {
         const int64_t j = t * H + n - left;
-        double v = (j >= 0 && j < in_len) ? x[j] : 0.0;
+        double v = (j >= 0 && j < in_len) ? (double)x[j] : 0.0;
         if (use_env && v != 0.0) v /= ola_envelope_f64(win, N, H, n_frames, j + left);
         fr[n] = v * win[n];
     }
@@ -64,7 +71,7 @@ analysis_f64_kernel(const double* __restrict__ in, int64_t in_stride, int64_t in
             idx += k;
             if (idx >= N) idx -= N;
         }
-        const double w = gain * ((k == 0 || 2 * k == N) ? w_edge : w_mid);
+        const double w = gain * (k == 0 ? w_dc : (2 * k == N ? w_ny : w_mid));
         re *= w;
         im *= w;
         if (compression != 1.0) {
@@ -73,15 +80,19 @@ analysis_f64_kernel(const double* __restrict__ in, int64_t in_stride, int64_t in
             re *= g;
             im *= g;
         }
-        out[(s * n_frames + t) * F + k] = make_double2(re * post, im * post);
+        typename Cplx<T>::type o;
+        o.x = (T)(re * post);
+        o.y = (T)(im * post);
+        out[(s * n_frames + t) * F + k] = o;
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(F64_THREADS)
-synthesis_f64_kernel(const double2* __restrict__ X, int64_t ss, int64_t sb, int64_t sf, int F, int64_t n_frames,
-                     int left, int H, int N, const double* __restrict__ win, const double2* __restrict__ tw,
-                     double pre, double decompression, double w_edge, double w_mid, double gain, int use_env,
-                     int64_t out_len, double* __restrict__ y) {
+synthesis_f64_kernel(const typename Cplx<T>::type* __restrict__ X, int64_t ss, int64_t sb, int64_t sf, int F,
+                     int64_t n_frames, int left, int H, int N, const double* __restrict__ win,
+                     const double2* __restrict__ tw, double pre, double decompression, double w_dc, double w_ny,
+                     double w_mid, double gain, int use_env, int64_t out_len, T* __restrict__ y) {
     extern __shared__ double2 row[];                       // one frame's weighted bins, F values
     const int64_t s = blockIdx.y;
     const int64_t i0 = (int64_t)blockIdx.x * F64_THREADS;
@@ -96,16 +107,15 @@ synthesis_f64_kernel(const double2* __restrict__ X, int64_t ss, int64_t sb, int6
     for (int64_t t = t_lo; t <= t_hi; ++t) {
         __syncthreads();
         for (int k = threadIdx.x; k < F; k += F64_THREADS) {
-            double2 v = X[s * ss + (int64_t)k * sb + t * sf];
-            v.x *= pre;
-            v.y *= pre;
+            const typename Cplx<T>::type xv = X[s * ss + (int64_t)k * sb + t * sf];
+            double2 v = make_double2((double)xv.x * pre, (double)xv.y * pre);
             if (decompression != 1.0) {
                 const double mag = hypot(v.x, v.y);
                 const double g = mag > 0.0 ? pow(mag, decompression - 1.0) : 0.0;
                 v.x *= g;
                 v.y *= g;
             }
-            const double w = (k == 0 || 2 * k == N) ? w_edge : w_mid;
+            const double w = k == 0 ? w_dc : (2 * k == N ? w_ny : w_mid);
             row[k] = make_double2(v.x * w, v.y * w);
         }
         __syncthreads();
@@ -126,7 +136,7 @@ synthesis_f64_kernel(const double2* __restrict__ X, int64_t ss, int64_t sb, int6
     if (i < out_len) {
         double v = acc * gain;
         if (use_env) v /= ola_envelope_f64(win, N, H, n_frames, pos);
-        y[s * out_len + i] = v;
+        y[s * out_len + i] = (T)v;
     }
 }
 
@@ -164,44 +174,62 @@ int f64_tables(const brv_stft_plan* cp, const double** win, const double2** tw) 
     return BRV_OK;
 }
 
-int launch_analysis(const brv_stft_plan* p, const double* in, int64_t n_sig, int64_t in_stride, int64_t in_len,
-                    int F, int64_t n_frames, double gain, double w_edge, double w_mid, double compression,
-                    double post, int use_env, void* out, cudaStream_t st) {
+template <typename T>
+int launch_analysis(const brv_stft_plan* p, const T* in, int64_t n_sig, int64_t in_stride, int64_t in_len, int left,
+                    int F, int64_t n_frames, double gain, double w_dc, double w_ny, double w_mid,
+                    double compression, double post, int use_env, void* out, cudaStream_t st) {
     const double* win;
     const double2* tw;
     int rc = f64_tables(p, &win, &tw);
     if (rc != BRV_OK) return rc;
-    BRV_REQUIRE(n_frames < (1LL << 31) && n_sig < 65536, "float64 path: too many frames / signals per call");
+    BRV_REQUIRE(n_frames < (1LL << 31) && n_sig < 65536, "direct-sum path: too many frames / signals per call");
     dim3 grid((unsigned)n_frames, (unsigned)n_sig);
     if (p->n_fft * sizeof(double) > 48 * 1024)
-        BRV_CUDA(cudaFuncSetAttribute(analysis_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    analysis_f64_kernel<<<grid, F64_THREADS, p->n_fft * sizeof(double), st>>>(
-        in, in_stride, in_len, brv_left(p), p->hop, p->n_fft, F, n_frames, win, tw, gain, w_edge, w_mid,
-        compression, post, use_env, (double2*)out);
+        BRV_CUDA(cudaFuncSetAttribute(analysis_f64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    analysis_f64_kernel<T><<<grid, F64_THREADS, p->n_fft * sizeof(double), st>>>(
+        in, in_stride, in_len, left, p->hop, p->n_fft, F, n_frames, win, tw, gain, w_dc, w_ny, w_mid,
+        compression, post, use_env, (typename Cplx<T>::type*)out);
     BRV_LAUNCH_CHECK("analysis_f64_kernel");
     return BRV_OK;
 }
 
+template <typename T>
 int launch_synthesis(const brv_stft_plan* p, const void* X, int64_t ss, int64_t sb, int64_t sf, int64_t n_sig,
-                     int F, int64_t n_frames, double pre, double decompression, double w_edge, double w_mid,
-                     double gain, int use_env, int64_t out_len, double* y, cudaStream_t st) {
+                     int left, int F, int64_t n_frames, double pre, double decompression, double w_dc, double w_ny,
+                     double w_mid, double gain, int use_env, int64_t out_len, T* y, cudaStream_t st) {
     const double* win;
     const double2* tw;
     int rc = f64_tables(p, &win, &tw);
     if (rc != BRV_OK) return rc;
     const int64_t blocks = brv_ceil_div(out_len, F64_THREADS);
-    BRV_REQUIRE(blocks < (1LL << 31) && n_sig < 65536, "float64 path: too many samples / signals per call");
+    BRV_REQUIRE(blocks < (1LL << 31) && n_sig < 65536, "direct-sum path: too many samples / signals per call");
     dim3 grid((unsigned)blocks, (unsigned)n_sig);
     if (F * sizeof(double2) > 48 * 1024)
-        BRV_CUDA(cudaFuncSetAttribute(synthesis_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    synthesis_f64_kernel<<<grid, F64_THREADS, F * sizeof(double2), st>>>(
-        (const double2*)X, ss, sb, sf, F, n_frames, brv_left(p), p->hop, p->n_fft, win, tw, pre, decompression,
-        w_edge, w_mid, gain, use_env, out_len, y);
+        BRV_CUDA(cudaFuncSetAttribute(synthesis_f64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    synthesis_f64_kernel<T><<<grid, F64_THREADS, F * sizeof(double2), st>>>(
+        (const typename Cplx<T>::type*)X, ss, sb, sf, F, n_frames, left, p->hop, p->n_fft, win, tw, pre,
+        decompression, w_dc, w_ny, w_mid, gain, use_env, out_len, y);
     BRV_LAUNCH_CHECK("synthesis_f64_kernel");
     return BRV_OK;
 }
 
 }  // namespace
+
+// ConvSTFT (brever/modules/stft.py:201-319) at sizes the folded tensor-core kernels do not cover:
+// float tensors, the same two direct-sum kernels.  Analysis: frames start L - H before t hop, DC
+// row 1 / sqrt(2), `gain` = 1 / normalisation; synthesis = its adjoint (no envelope), cut by L - H.
+int brv_direct_conv_forward(const brv_stft_plan* p, const float* x, int64_t n_sig, int64_t samples,
+                            int64_t x_stride, double gain, void* out, int64_t n_frames, cudaStream_t st) {
+    return launch_analysis<float>(p, x, n_sig, x_stride, samples, p->frame_length - p->hop, p->n_bins, n_frames,
+                                  gain, sqrt(0.5), 1.0, 1.0, p->compression, p->scale, 0, out, st);
+}
+int brv_direct_conv_backward(const brv_stft_plan* p, const void* X, int64_t ss, int64_t sb, int64_t sf,
+                             int64_t n_sig, int64_t n_frames, int64_t out_len, double gain, float* y,
+                             cudaStream_t st) {
+    return launch_synthesis<float>(p, X, ss, sb, sf, n_sig, p->frame_length - p->hop, p->n_bins, n_frames,
+                                   1.0 / p->scale, 1.0 / p->compression, sqrt(0.5), 1.0, 1.0, gain, 0, out_len, y,
+                                   st);
+}
 
 void brv_f64_plan_free(brv_stft_plan* p) {
     cudaFree(p->win64);
@@ -218,8 +246,9 @@ extern "C" int brv_stft_forward_f64(const brv_stft_plan* p, const double* x, int
     if (rc != BRV_OK) return rc;
     if (n_signals == 0) return BRV_OK;
     BRV_REQUIRE(x, "input pointer is null");
-    return launch_analysis(p, x, n_signals, x_stride, samples, p->n_bins, n_frames, 1.0 / p->norm, 1.0, 1.0,
-                           p->compression, p->scale, 0, out, (cudaStream_t)stream);
+    return launch_analysis<double>(p, x, n_signals, x_stride, samples, brv_left(p), p->n_bins, n_frames,
+                                   1.0 / p->norm, 1.0, 1.0, 1.0, p->compression, p->scale, 0, out,
+                                   (cudaStream_t)stream);
 }
 
 extern "C" int brv_istft_forward_f64(const brv_stft_plan* p, const void* X, int64_t ss, int64_t sb, int64_t sf,
@@ -235,9 +264,9 @@ extern "C" int brv_istft_forward_f64(const brv_stft_plan* p, const void* X, int6
     if (rc != BRV_OK) return rc;
     if (n_signals == 0 || out_len == 0) return BRV_OK;
     BRV_REQUIRE(y, "output pointer is null");
-    return launch_synthesis(p, X, ss, sb, sf, n_signals, p->n_bins_inv, n_frames, 1.0 / p->scale,
-                            1.0 / p->compression, 1.0, 2.0, p->norm / p->n_fft, 1, out_len, y,
-                            (cudaStream_t)stream);
+    return launch_synthesis<double>(p, X, ss, sb, sf, n_signals, brv_left(p), p->n_bins_inv, n_frames,
+                                    1.0 / p->scale, 1.0 / p->compression, 1.0, 1.0, 2.0, p->norm / p->n_fft, 1,
+                                    out_len, y, (cudaStream_t)stream);
 }
 
 extern "C" int brv_stft_forward_grad_f64(const brv_stft_plan* p, const void* gX, int64_t ss, int64_t sb,
@@ -251,8 +280,8 @@ extern "C" int brv_stft_forward_grad_f64(const brv_stft_plan* p, const void* gX,
     int rc = brv_stft_geometry(p, samples, &n_frames, nullptr, nullptr);
     if (rc != BRV_OK) return rc;
     if (n_signals == 0 || samples == 0) return BRV_OK;
-    return launch_synthesis(p, gX, ss, sb, sf, n_signals, p->n_bins, n_frames, 1.0, 1.0, 1.0, 1.0,
-                            p->scale / p->norm, 0, samples, gx, (cudaStream_t)stream);
+    return launch_synthesis<double>(p, gX, ss, sb, sf, n_signals, brv_left(p), p->n_bins, n_frames, 1.0, 1.0, 1.0,
+                                    1.0, 1.0, p->scale / p->norm, 0, samples, gx, (cudaStream_t)stream);
 }
 
 extern "C" int brv_istft_forward_grad_f64(const brv_stft_plan* p, const double* gy, int64_t n_signals,
@@ -268,7 +297,7 @@ extern "C" int brv_istft_forward_grad_f64(const brv_stft_plan* p, const double* 
     int rc = brv_istft_geometry(p, n_frames, &out_len);
     if (rc != BRV_OK) return rc;
     if (n_signals == 0) return BRV_OK;
-    return launch_analysis(p, gy, n_signals, out_len, out_len, p->n_bins_inv, n_frames,
-                           p->norm / ((double)p->n_fft * p->scale), 1.0, 2.0, 1.0, 1.0, 1, gX,
-                           (cudaStream_t)stream);
+    return launch_analysis<double>(p, gy, n_signals, out_len, out_len, brv_left(p), p->n_bins_inv, n_frames,
+                                   p->norm / ((double)p->n_fft * p->scale), 1.0, 1.0, 2.0, 1.0, 1.0, 1, gX,
+                                   (cudaStream_t)stream);
 }

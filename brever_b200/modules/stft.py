@@ -438,8 +438,9 @@ class ConvSTFT:
     the folded tensor-core pair of ``brv_convstft_forward`` / ``brv_convstft_backward``:
     frames start ``L - H`` samples before ``t * H``, the DC row carries ``1 / sqrt(2)``, the
     synthesis is the exact adjoint (no envelope division) trimmed by ``L - H`` per side.
-    Supported on the kernels' sizes only (``frame_length`` in {128, 256, 384, 512} and
-    ``hop_length`` = L/4, L/2 or L); differentiable in both directions through the adjoint pair
+    ``frame_length`` in {128, 256, 384, 512} with ``hop_length`` = L/4, L/2 or L runs on the folded
+    tensor-core kernels, every other size on the direct-sum kernels of ``brv_stft_f64.cu`` (correct,
+    not fast); differentiable in both directions through the adjoint pair
     (``compression_factor == 1``).
     """
 
@@ -588,6 +589,12 @@ class _ConvForwardFunction(torch.autograd.Function):
         conv = ctx.conv
         ga, gs = conv._gains()
         g = grad.to(torch.complex64).resolve_conj().resolve_neg()
+        L, H = conv.frame_length, conv.hop_length
+        short = ctx.samples - ((g.shape[-1] + 1) * H - L)
+        if short > 0:
+            # hop does not divide 2 (L - H): the synthesis' trimmed output ends before the input did;
+            # zero frames appended to the gradient extend it without changing the values
+            g = torch.nn.functional.pad(g, (0, -(-short // H)))
         full = conv._conv_backward_raw(g)              # right-padded length >= samples
         return full[..., :ctx.samples] * (conv.scale_factor ** 2 * ga / gs), None
 

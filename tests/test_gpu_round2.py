@@ -7,6 +7,8 @@ import torch
 
 import brever_b200 as brv
 
+from oracle import tf_oracle as O
+
 from _util import assert_parity, crandn, golden, randn
 
 pytestmark = pytest.mark.gpu
@@ -245,3 +247,42 @@ def test_channel_mean_mask_and_accumulate():
     brv.ffnn.accumulate_mean(total, v)
     brv.ffnn.accumulate_mean(total, v)
     assert abs(float(total) - 2 * float(v.mean())) < 1e-6
+
+
+@pytest.mark.parametrize('kw', [dict(frame_length=400, hop_length=100),
+                                dict(frame_length=320, hop_length=160, normalized=False, scale_factor=0.5),
+                                dict(frame_length=250, hop_length=125, window='hamming'),
+                                dict(frame_length=64, hop_length=24, compression_factor=0.5, scale_factor=0.15),
+                                dict(frame_length=101, hop_length=50)])
+def test_conv_stft_arbitrary_sizes(kw):
+    """ConvSTFT (stft.py:201-319) at sizes the folded tensor-core kernels do not cover: analysis,
+    synthesis and, without compression, both gradients (the synthesis is the analysis' adjoint)."""
+    conv = brv.ConvSTFT(**kw)
+    x = randn((3, 5000), 61)
+    spec = conv(x.to(DEV))
+    ref = O.conv_stft(x.numpy(), **kw)
+    assert spec.shape == ref.shape and spec.dtype == torch.complex64
+    assert_parity(cpu(spec), ref, 2e-5, 'ConvSTFT')
+    y = conv.backward(spec)
+    assert_parity(cpu(y), O.conv_istft(ref, **kw), 2e-5, 'ConvSTFT.backward')
+    assert_parity(cpu(conv.backward(spec.contiguous())), cpu(y), 1e-6, 'layouts')
+    if kw.get('compression_factor', 1) != 1:
+        return
+    # <A x, w> == <x, A^H w>: the gradient of the analysis is the synthesis kernel and vice versa
+    w = crandn(tuple(spec.shape), 62)
+    xg = x.clone().to(DEV).requires_grad_(True)
+    (conv(xg) * w.conj().to(DEV)).real.sum().backward()
+    v = randn(tuple(y.shape), 63)
+    Xg = w.clone().to(DEV).requires_grad_(True)
+    (conv.backward(Xg) * v.to(DEV)).sum().backward()
+    eps = 1e-3
+    d = randn((3, 5000), 64)
+    f = lambda t: float((conv(t.to(DEV)) * w.conj().to(DEV)).real.sum())   # noqa: E731
+    num = (f(x + eps * d) - f(x - eps * d)) / (2 * eps)
+    ana = float((xg.grad.cpu() * d).sum())
+    assert abs(num - ana) <= 2e-3 * max(1.0, abs(ana)), (kw, num, ana)
+    D = crandn(tuple(spec.shape), 65)
+    h = lambda S: float((conv.backward(S.to(DEV)) * v.to(DEV)).sum())      # noqa: E731
+    num = (h(w + eps * D) - h(w - eps * D)) / (2 * eps)
+    ana = float((Xg.grad.cpu().real * D.real + Xg.grad.cpu().imag * D.imag).sum())
+    assert abs(num - ana) <= 2e-3 * max(1.0, abs(ana)), (kw, num, ana)
