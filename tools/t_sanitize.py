@@ -17,7 +17,7 @@ for kw in (dict(frame_length=512, hop_length=128), dict(frame_length=256, hop_le
            dict(frame_length=510, hop_length=128, normalized=False, compression_factor=0.5, scale_factor=0.15)):
     stft = brv.STFT(**kw)
     x = 0.05 * torch.randn(5, 30000, device='cuda')
-    for variant in (4, 2, 3, 5, 6):
+    for variant in (4, 2, 3, 5, 6, 7, 0):
         lib.brv_set_tc_variant(variant)
         xg = x.clone().requires_grad_(kw.get('compression_factor', 1.0) == 1.0)
         spec = stft(xg)
@@ -28,3 +28,22 @@ for kw in (dict(frame_length=512, hop_length=128), dict(frame_length=256, hop_le
         torch.cuda.synchronize()
         print(kw, 'variant', variant, 'ok', float(y.abs().max()), float((y - y2).abs().max()), flush=True)
 lib.brv_set_tc_variant(0)
+# float64 direct-sum kernels, ConvSTFT on them, the feature kernel, the small round-2 kernels
+stft = brv.STFT(512, 128)
+x64 = torch.randn(2, 5000, device='cuda', dtype=torch.float64, requires_grad=True)
+y64 = stft.backward(stft(x64))
+y64.square().sum().backward()
+conv = brv.ConvSTFT(frame_length=400, hop_length=100)
+xc = torch.randn(2, 5000, device='cuda', requires_grad=True)
+conv.backward(conv(xc)).square().sum().backward()
+front = brv.ffnn.FFNNFrontEnd()
+mix = 0.05 * torch.randn(3, 2, 16000, device='cuda')
+spec = front.stft(mix)
+feats = front.features(spec)
+m = brv.ffnn.channel_mean(spec)
+tot = torch.zeros((), device='cuda')
+brv.ffnn.accumulate_mean(tot, torch.randn(7, device='cuda'))
+a, b = brv.modules.specfmt.split(spec, 'mag_phase')
+brv.modules.specfmt.join(a, b, 'mag_phase')
+torch.cuda.synchronize()
+print('float64 / conv / features / specfmt ok', float(y64.abs().max()), tuple(feats.shape), flush=True)
