@@ -305,8 +305,9 @@ class STFT:
         n_sig, samples = x2d.shape
         if x2d.stride(-1) != 1:
             x2d = x2d.contiguous()
-        out = torch.empty((n_sig, self.n_frames(samples), self.n_bins), dtype=torch.complex128,
-                          device=x2d.device)
+        frames = self.n_frames(samples) if self.pad_mode == 'constant' else \
+            1 + (samples - self.n_fft) // self.hop_length      # reflect: x2d is already padded
+        out = torch.empty((n_sig, frames, self.n_bins), dtype=torch.complex128, device=x2d.device)
         if n_sig:
             with _lib.on_device(x2d.device):
                 _lib.check(_lib.lib().brv_stft_forward_f64(
@@ -365,8 +366,15 @@ class STFT:
         in_dtype = x.dtype
         lead = x.shape[:-1]
         x2d = x.reshape(-1, x.shape[-1])
-        if in_dtype == torch.float64 and self.pad_mode == 'constant':
-            # double-precision kernels (reflect padding of float64 input still computes fp32-grade)
+        if in_dtype == torch.float64:
+            # double-precision kernels; reflect padding by torch (a fidelity path, not a fast one)
+            if self.pad_mode == 'reflect':
+                pad = torch.nn.functional.pad
+                right = 0 if self._raw_framing else self._right_pad(x2d.shape[-1])
+                if right:
+                    x2d = pad(x2d.unsqueeze(1), (0, right), mode='reflect').squeeze(1)
+                if self.center:
+                    x2d = pad(x2d.unsqueeze(1), (self.n_fft // 2, self.n_fft // 2), mode='reflect').squeeze(1)
             if torch.is_grad_enabled() and x2d.requires_grad:
                 spec = _StftFunction64.apply(x2d, self)
             else:

@@ -64,6 +64,22 @@ def test_f64_inverse_matches_oracle(kw, frames, layout):
     assert e[0] < TOL and e[1] < TOL, (kw, frames, layout, e)
 
 
+@pytest.mark.parametrize('kw', [dict(frame_length=512, hop_length=128, pad_mode='reflect'),
+                                dict(frame_length=400, hop_length=100, n_fft=512, pad_mode='reflect'),
+                                dict(frame_length=512, hop_length=128, center=False)])
+def test_f64_padding_modes(kw):
+    x = randn64((3, 4097), 13)
+    xg = x.clone().to(DEV).requires_grad_(True)
+    spec = brv.STFT(**kw)(xg)
+    ref = O.stft(x.numpy(), **kw)
+    e = rel_err(spec.detach().cpu().numpy(), ref)
+    assert e[0] < TOL and e[1] < TOL, (kw, e)
+    w = torch.complex(randn64(tuple(spec.shape), 14), randn64(tuple(spec.shape), 15))
+    (spec * w.conj().to(DEV)).real.sum().backward()
+    e = rel_err(xg.grad.cpu().numpy(), O.stft_grad(w.numpy(), x.shape[-1], **kw))
+    assert e[0] < TOL and e[1] < TOL, ('gradient', kw, e)
+
+
 def test_f64_round_trip_and_return_types():
     stft = brv.STFT(512, 128)
     x = randn64((4, 16000), 9).to(DEV)
