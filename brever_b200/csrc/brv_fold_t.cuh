@@ -723,11 +723,15 @@ __device__ __forceinline__ void it_store_range(int64_t ibase, int64_t out_len, i
 #else
 #define IT_BUILD_FENCE() fence_proxy_async()
 #endif
-template <int HQ, bool FRAMES_FAST, bool DECOMP, int NF, bool ODD = false>
+// DUP (Q = 64, hop = 2Q): the basis rows are staged twice, so TMEM lanes 64..127 hold a copy of the
+// accumulators and the epilogue warps that would idle (sample offsets >= Q) take the second half of
+// every tile's columns (one column of warm-up for the carried values).
+template <int HQ, bool FRAMES_FAST, bool DECOMP, int NF, bool ODD = false, bool DUP = false>
 __global__ void __launch_bounds__(IT_THREADS, 1)
 istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParams p) {
     using L = ItLayout<NF, ODD>;
     static_assert(!ODD || HQ == 1, "n_fft = 4Q - 2 runs with hop = Q only");
+    static_assert(!DUP || (HQ == 2 && !ODD && NF == 32), "duplicated lanes: hop = 2Q, 32-frame tiles");
     constexpr int NBUF = L::NBUF, NSTAGE = L::STAGES, STAGE_BYTES = L::STAGE_BYTES, DATA_TILE = L::DATA_TILE;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[4];
@@ -797,14 +801,18 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                     const uint32_t ph = (g / NSTAGE) & 1;
                     const int kc = it >> 1, pair = it & 1;
                     T_WAITED(0, mbar_wait_relaxed(&empty_bar[s], ph ^ 1));
-                    mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
+                    mbar_arrive_expect_tx(&full_bar[s], (DUP ? 8u : 4u) * (uint32_t)Q * BK * 2);
                     uint8_t* sb = stages + (size_t)s * STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
-                        for (int pl = 0; pl < 2; ++pl)
+                        for (int pl = 0; pl < 2; ++pl) {
                             tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
                                         &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
+                            if (DUP)                   // the same Q rows again below them (rows Q .. 2Q - 1)
+                                tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE + Q * (BK * 2)), &basis_map,
+                                            &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
+                        }
                     T_WAIT_FLUSH(4);
                 }
         }
@@ -857,7 +865,9 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
         T_WAIT_DECL;
         const int set = (warp - IT_EPI_WARP0) >> 2;      // even / odd tiles; also the TMEM buffer
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
-        const int nn = q * 32 + lane;              // sample offset n (row of Ce, Co, Se, So)
+        const int lane_row = q * 32 + lane;        // TMEM lane
+        const int half = DUP ? (lane_row >= Q ? 1 : 0) : 0;      // DUP: which half of a tile's columns
+        const int nn = DUP ? lane_row - half * Q : lane_row;     // sample offset n (row of Ce, Co, Se, So)
         const bool valid = nn < Q;
         const float4 wn = valid ? __ldg(p.wtab + nn) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float sgn = (nn & 1) ? -1.f : 1.f;
@@ -885,7 +895,14 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
             tcgen05_fence_after();
             if (q == 0) T_STAMP(3, n, 1);
             const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * NF);
-            if (cont) {
+            if (cont && DUP && half == 0) {
+                // (the other half of the warps owns the tile's last columns; the waits keep every
+                //  warp's arrivals one per barrier phase)
+                T_WAITED(2, mbar_wait_relaxed(&carry_empty[set ^ 1], (n_out & 1) ^ 1));
+                ++n_out;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&carry_full[set ^ 1]);
+            } else if (cont) {
                 // ---- the values the next tile's first hop blocks need from this tile's last
                 //      R - 1 frames go out first, so that the other set can start ----
                 uint32_t A[4][8];
@@ -910,7 +927,26 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 if (lane == 0) mbar_arrive(&carry_full[set ^ 1]);
             }
             float c1 = 0.f, c2 = 0.f, b1 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;   // previous frames' values
-            if (!fresh) {
+            // DUP: columns [c_begin, c_end) of the tile are this warp's
+            const int c_begin = half * (NF / 2);
+            const int c_end = DUP ? (half == 0 ? min(ncols, NF / 2) : ncols) : ncols;
+            if (DUP && half == 1) {
+                if (!fresh) {                      // the hand-off is for the first half: only keep the count
+                    T_WAITED(2, mbar_wait_relaxed(&carry_full[set], n_in & 1));
+                    ++n_in;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&carry_empty[set]);
+                }
+                if (c_begin < c_end) {             // warm-up: the values of the column before this half
+                    uint32_t A[4][8];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) tmem_ld8_nowait(tq + (uint32_t)(a * NF + c_begin - 8), A[a]);
+                    tmem_ld_wait();
+                    float a_, b_;
+                    it_frame_values<ODD>(A[0][7], A[1][7], A[2][7], A[3][7], rowinfo[c_begin - 1], t0, sgn, wn,
+                                         a_, b_, c1, d1);
+                }
+            } else if (!fresh) {
                 T_WAITED(2, mbar_wait_relaxed(&carry_full[set], n_in & 1));
                 ++n_in;
                 const float* ci = carry_in + (int)(((n - 1) >> 1) & 1) * (6 * 128) + nn;
@@ -927,10 +963,22 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
             int lo, hi, lo_m = 0, hi_m = 0;
             it_store_range(ibase, p.out_len, H, skip, ncols, valid, lo, hi);
             if (HQ == 2) it_store_range(ibase + (moff - nn), p.out_len, H, skip, ncols, valid, lo_m, hi_m);
+            if (DUP) {
+                lo = max(lo, c_begin); hi = min(hi, c_end);
+                lo_m = max(lo_m, c_begin); hi_m = min(hi_m, c_end);
+                if (c_begin >= c_end) {            // nothing to read in this tile: hand it back at once
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&tmem_empty[buf]);
+                        mbar_arrive(&scale_empty[buf]);
+                    }
+                }
+            }
             const int e_lo = p.no_env ? 0 : (int)max((int64_t)0, (int64_t)(R - 1) - c0);
             const int e_hi = p.no_env ? ncols : (int)max((int64_t)0, min((int64_t)ncols, p.n_frames - c0));
 #pragma unroll 1
-            for (int cb = 0; cb < ncols; cb += 8) {
+            for (int cb = c_begin; cb < c_end; cb += 8) {
                 uint32_t A[4][8];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) tmem_ld8_nowait(tq + (uint32_t)(a * NF + cb), A[a]);
@@ -963,7 +1011,7 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         c1 = c; d1 = d;
                     }
                 }
-                if (cb + 8 >= ncols) {
+                if (cb + 8 >= c_end) {
                     // last read of this tile's accumulators and row info: hand both back
                     tcgen05_fence_before();
                     __syncwarp();

@@ -2135,6 +2135,13 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ItLayout<32>::SMEM_BYTES) != cudaSuccess)
                 rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_t_kernel<32>)");
+        const void* tkernels_dup[4] = {
+            (const void*)istft_t_kernel<2, false, false, 32, false, true>, (const void*)istft_t_kernel<2, true, false, 32, false, true>,
+            (const void*)istft_t_kernel<2, false, true, 32, false, true>, (const void*)istft_t_kernel<2, true, true, 32, false, true>};
+        for (const void* k : tkernels_dup)
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ItLayout<32>::SMEM_BYTES) != cudaSuccess)
+                rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(istft_t_kernel<dup>)");
         const void* tkernels_odd[4] = {
             (const void*)istft_t_kernel<1, false, false, 32, true>, (const void*)istft_t_kernel<1, true, false, 32, true>,
             (const void*)istft_t_kernel<1, false, true, 32, true>, (const void*)istft_t_kernel<1, true, true, 32, true>};
@@ -2325,8 +2332,9 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     // Which kernel (measured on B200, tools/t_sweep.py):
     //   * the transposed strip kernel (istft_t_kernel, 32-frame tiles) for Q = 128 (n_fft 512-class)
     //     and for Q = 64 with hop = Q, at any launch size and for both spectrogram layouts;
-    //   * the one-tile-per-TMEM kernel for everything else: odd folds, hop = 4Q, Q = 64 with hop = 2Q
-    //     (half of the strip kernel's epilogue lanes idle there), Q = 32.
+    //     for Q = 64 with hop = 2Q on frame-major spectrograms its duplicated-lane flavour (cfg5: 1034 -> 915 us);
+    //   * the one-tile-per-TMEM kernel for everything else: hop = 4Q, Q = 64 with hop = 2Q on bin-major
+    //     input (911 vs 933 us), Q = 32, Q = 96.
     // Variants 6 / 7 force the strip kernel (64- / 32-frame tiles), variant 4 the tile kernel.
     const int64_t cols = n_sig * (int64_t)prm.n_blocks;
     bool use_t = false, nf32 = true;
@@ -2335,7 +2343,7 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
             use_t = true;
             nf32 = g_brv_fold_variant == 7;
         } else if (g_brv_fold_variant == 0) {
-            use_t = fp->q == 128 || (fp->q == 64 && fp->hq == 1);
+            use_t = fp->q == 128 || (fp->q == 64 && (fp->hq == 1 || !frames_fast));
         }
     }
     if (use_t) {
@@ -2367,6 +2375,14 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
                     istft_t_kernel<1, false, false, 32, true>
                         <<<ctas, IT_THREADS, ItLayout<32, true>::SMEM_BYTES, st>>>(fp->inv.map, prm);
             }
+        } else if (fp->hq == 2 && fp->q == 64 && nf32) {
+            // duplicated accumulator lanes: all eight epilogue warps work although Q = 64
+#define BRV_LAUNCH_INV_DUP(FF_, DC_)                                                              \
+    istft_t_kernel<2, FF_, DC_, 32, false, true>                                                  \
+        <<<ctas, IT_THREADS, ItLayout<32>::SMEM_BYTES, st>>>(fp->inv.map, prm)
+            if (decomp) { if (frames_fast) BRV_LAUNCH_INV_DUP(true, true); else BRV_LAUNCH_INV_DUP(false, true); }
+            else { if (frames_fast) BRV_LAUNCH_INV_DUP(true, false); else BRV_LAUNCH_INV_DUP(false, false); }
+#undef BRV_LAUNCH_INV_DUP
         } else if (fp->hq == 1) {
             if (frames_fast) { if (nf32) BRV_LAUNCH_INV_T(1, true, 32); else BRV_LAUNCH_INV_T(1, true, 64); }
             else if (nf32) BRV_LAUNCH_INV_T(1, false, 32);
