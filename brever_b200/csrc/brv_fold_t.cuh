@@ -169,6 +169,9 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
     const int N = p.n_fft, H = p.hop, Q = p.q, Hf = N / 2;
     const int n_kc = Q / BK;
     const int n_it = 2 * n_kc;
+    // Q = 64: the basis rows are staged twice, TMEM lanes 64..127 hold a copy of the accumulators and
+    // the epilogue warps of those lanes (idle otherwise) take half of the columns
+    const bool dup = Q == 64;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < T_STAGES; ++s) {
@@ -215,7 +218,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                     mbar_arrive(&full_bar[s]);
                     (void)kc; (void)pair;
 #else
-                    mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)Q * BK * 2);
+                    mbar_arrive_expect_tx(&full_bar[s], (dup ? 8u : 4u) * (uint32_t)Q * BK * 2);
                     uint8_t* sb = stages + (size_t)s * T_STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
@@ -223,6 +226,9 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                         for (int pl = 0; pl < 2; ++pl) {
                             tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE), &basis_map,
                                         &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
+                            if (dup)                   // the same Q rows again below them (rows Q .. 2Q - 1)
+                                tma_load_2d(smem_u32(sb + (j * 2 + pl) * SUB_TILE + Q * (BK * 2)), &basis_map,
+                                            &full_bar[s], kc * BK, (pl * 4 + pair * 2 + j) * Q);
                         }
 #endif
                     T_WAIT_FLUSH(4);
@@ -333,7 +339,9 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
         const int e = warp - FT_EPI_WARP0;         // 0..7
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         const int chalf = e >> 2;                  // which 32 frames of the tile
-        const int m = q * 32 + lane;               // bin pair: bins 2m, 2m+1
+        const int m = dup ? (q & 1) * 32 + lane : q * 32 + lane;       // bin pair: bins 2m, 2m+1
+        const int c_lo = chalf * 32 + (dup ? (q >> 1) * 16 : 0);       // this warp's columns
+        const int c_n = dup ? 16 : 32;
         const bool valid = m < Q;
         const float sgn = (m & 1) ? -1.f : 1.f;
         const int pitch = 2 * p.n_bins;
@@ -354,8 +362,8 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
             float* obase = p.out + ((sig * p.n_frames + t0) * (int64_t)pitch + 4 * m);
             const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * T_NF);
 #pragma unroll 1
-            for (int cb = 0; cb < 32; cb += 8) {
-                const int c0 = chalf * 32 + cb;
+            for (int cb = 0; cb < c_n; cb += 8) {
+                const int c0 = c_lo + cb;
 #ifdef BRV_T_NO_EPI                                     // dev experiment: timing without the epilogue stores
                 if (p.n_fft > 0) break;
 #endif
