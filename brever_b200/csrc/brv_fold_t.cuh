@@ -10,9 +10,10 @@
 // i.e. the trigonometric basis is the M-side operand (M = 128 lanes, rows >= Q are never
 // read back) and the frames are the N side.  Three things follow:
 //   * a tile is up to 64 frames = 4 x 64 accumulator columns, so TWO tiles fit in the 512
-//     TMEM columns: the tensor core works on tile i+1 while the epilogue drains tile i, and the
-//     operand builders never wait for an epilogue (the one-tile-per-TMEM kernels serialise
-//     build -> MMA -> epilogue on every tile);
+//     TMEM columns (the inverse kernel's default is 32 frames and FOUR resident tiles): the
+//     tensor core works on tile i+1 while the epilogue drains tile i, and the operand builders
+//     never wait for an epilogue (the one-tile-per-TMEM kernels serialise build -> MMA ->
+//     epilogue on every tile);
 //   * a thread of the epilogue owns one bin pair (forward) or one sample offset (inverse) and
 //     walks along the frames: the forward epilogue stores 16 contiguous bytes per thread and
 //     512 per warp straight from registers (no shared-memory transpose), the inverse epilogue
@@ -609,14 +610,18 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
 // concurrently.  A strip that starts inside a signal recomputes the R - 1 frames before it (`skip`
 // columns whose hop blocks belong to the previous CTA).
 //
-//   warp 0        TMA producer: basis k-chunks (3-stage ring)
+//   warp 0        TMA producer: basis k-chunks (3- or 4-stage ring)
 //   warp 1        TMEM owner + MMA issuer
 //   warps 4-7     epilogue set 0 (even tiles)      warps 8-11  epilogue set 1 (odd tiles)
 //   warps 12-19   operand builders: spectrogram (L2-resident after the scouts) -> scaled fp16
-//                 hi / lo planes; two register buffers alternate so that the next k-chunk's loads
-//                 (also across tiles) are in flight while one is converted
-//   warps 20-27   scouts: per-frame maxima of the NEXT tile straight from HBM (18 loads in
-//                 flight per lane), which also leaves that tile L2-resident for the builders
+//                 hi / lo planes; frame-major input: the k-chunks of all tiles form one stream
+//                 over two register buffers, so the next chunk's loads (also across tiles) fly
+//                 while one is converted; bin-major input: two groups of threads alternate chunks
+//   warps 20-27   scouts: per-frame maxima of the tiles ahead straight from HBM (18 loads in
+//                 flight per lane), which also leaves them L2-resident for the builders
+// Template flavours: NF = 64 / 32 frames per tile (2 / 4 tiles resident in TMEM), ODD (n_fft =
+// 4Q - 2: three exchange planes for the one-sample shifts of the segments), DUP (Q = 64, hop 2Q:
+// accumulators duplicated on lanes 64..127 so that every epilogue warp has columns to work on).
 constexpr int IT_THREADS = 896;
 constexpr int IT_EPI_WARP0 = 4, IT_EPI_SET_WARPS = 4;
 constexpr int IT_BUILD_WARP0 = 12, IT_BUILD_WARPS = 8, IT_BUILD_THREADS = IT_BUILD_WARPS * 32;
