@@ -1309,11 +1309,13 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                     mbar_arrive(&full_bar[s1]);
                 }
             };
-            // The k-chunks of all the strip's tiles form one stream; NB register buffers rotate
-            // over it, so the loads of the next NB - 1 chunks (also across tiles) are in flight while
-            // one is converted: a warp's few KB per chunk need that depth to cover the L2 latency.
+            // The k-chunks of all the strip's tiles form one stream over NB register buffers (NB > 1:
+            // the loads of the next NB - 1 chunks, also across tiles, fly while one is converted).
+            // Measured: NB = 1 is the fastest (cfg4 247 -> 218 us, cfg5 914 -> 824 us against NB = 2):
+            // the other warps hide the L2 latency, and every extra buffer is another inlined copy of
+            // the conversion in kernels whose top stall is instruction fetch.
 #ifndef BRV_T_NB
-#define BRV_T_NB 2
+#define BRV_T_NB 1
 #endif
             constexpr int NB = NF == 32 ? BRV_T_NB : 2;
             float2 ring[NB][RI][4];

@@ -48,52 +48,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Wait used by the roles that are NOT on the critical path of the CUDA cores (TMA producer,
 // MMA issuer, epilogue / scout warps waiting for work): backs off with nanosleep so the
 // polling does not take issue slots from the warps that do the arithmetic.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok;
+}
+// exponential back-off: a short wait is answered at once, a long one (a role that is a tile ahead
+// of its producer) polls a few times per microsecond instead of every ~100 ns -- ~20 waiting warps
+// polling at the short period took a quarter of the SM's issue slots.  Kept small (one counter as
+// the never-hang-the-device guard): the warp-specialised kernels wait at ~25 sites each and their
+// code size shows up as instruction-fetch stalls.  (An out-of-line polling loop does not compile
+// inside the setmaxnreg regions: ptxas C7600.)
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 64) {
     const uint32_t addr = smem_u32(bar);
-    long long start = 0;
-#ifdef BRV_WAIT_HINT
-    // try_wait with a suspend-time hint: the hardware parks the thread until the phase flips (or
-    // the hint expires), so a waiting warp issues a handful of instructions per wake-up instead
-    // of a try_wait / nanosleep loop (polling was 20 - 40 % of all issued instructions)
-    const uint32_t hint = ns * 64u;
-    for (uint32_t spins = 0;; ++spins) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity), "r"(hint)
-            : "memory");
-        if (ok) return;
-        if ((spins & 255) == 255) {                          // never hang the device
-            if (start == 0) start = clock64();
-            else if (clock64() - start > 4000000000LL) __trap();
-        }
-    }
-#else
-    // exponential back-off: a short wait is answered at once, a long one (a role that is a tile
-    // ahead of its producer) polls a few times per microsecond instead of every ~100 ns --
-    // ~20 waiting warps polling at the short period took a quarter of the SM's issue slots
     uint32_t nap = ns;
-    for (uint32_t spins = 0;; ++spins) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (ok) return;
+    for (uint32_t spins = 0; !mbar_try_wait(addr, parity); ++spins) {
         __nanosleep(nap);
         nap = min(nap * 2u, BRV_WAIT_NAP_MAX);
-        if ((spins & 255) == 255) {                          // never hang the device
-            if (start == 0) start = clock64();
-            else if (clock64() - start > 4000000000LL) __trap();
-        }
+        if (spins == (1u << 24)) __trap();                   // ~4 s at the capped nap: a lost arrival
     }
-#endif
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

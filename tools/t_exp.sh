@@ -1,7 +1,5 @@
 #!/bin/bash
-# Dev harness (GPU box): builder register-ring depth of the strip inverse kernel (timing only).
-for flag in "-DBRV_T_NB=1" "-DBRV_T_NB=2"; do
-  NVCC_EXTRA="$flag" python __graft_entry__.py --force > /dev/null 2>&1
-  echo "== flags: $flag"
-  FOLD_CHECK_VARIANTS=0 python tools/fold_check.py bench 2>&1 | grep -E "time" | cut -c1-100
-done
+# Dev harness (GPU box): parity then timing after code-size changes.
+for v in 0; do BRV_TC_VARIANT=$v timeout 200 python tools/fold_check.py inv > gpurun_out/t${v}_inv.log 2>&1; echo "inv variant $v rc $? ok $(grep -c 'ok ' gpurun_out/t${v}_inv.log) bad $(grep -c BAD gpurun_out/t${v}_inv.log)"; done
+for v in 0 5; do BRV_TC_VARIANT=$v timeout 200 python tools/fold_check.py fwd > gpurun_out/t${v}_fwd.log 2>&1; echo "fwd variant $v rc $? ok $(grep -c 'ok ' gpurun_out/t${v}_fwd.log) bad $(grep -c BAD gpurun_out/t${v}_fwd.log)"; done
+FOLD_CHECK_VARIANTS=0,4 timeout 200 python tools/fold_check.py bench 2>&1 | grep -E "time" | cut -c1-100
