@@ -163,6 +163,9 @@ __device__ __forceinline__ void split_store(uint8_t* hi_ptr, uint8_t* lo_ptr, fl
     *reinterpret_cast<__half2*>(lo_ptr) = l;
 }
 
+// COMPRESS: magnitude compression in the epilogue (32 inlined power evaluations: a third of the
+// kernel's code, kept out of the plain instantiation -- instruction fetch is a top stall here)
+template <bool COMPRESS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -437,7 +440,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
                 f2[j] = f2[j] * g0;
                 f3[j] = f3[j] * g0 - sg * ooq;
             }
-            if (p.post_expo != 0.f) {
+            if (COMPRESS) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     compress(f0[j], f2[j], p.post_expo);
@@ -462,7 +465,7 @@ stft_fold_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdPar
         }
         if (hsel == 1 && live && !p.odd) {         // Nyquist bin: purely real
             float v = ny * p.edge_scale;
-            if (p.post_expo != 0.f) v = compress_real(v, p.post_expo);
+            if (COMPRESS) v = compress_real(v, p.post_expo);
             *reinterpret_cast<float2*>(obase + (int64_t)lane * pitch + 2 * Hf) =
                 make_float2(v * p.post_scale, 0.f);
         }
@@ -2021,8 +2024,10 @@ int brv_fold_plan_init(brv_stft_plan* p) {
             rc = brv_fail_cuda(cudaGetLastError(), "folded gradient window table");
     }
     if (rc == BRV_OK &&
-        cudaFuncSetAttribute(stft_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SMEM_BYTES) != cudaSuccess)
+        (cudaFuncSetAttribute(stft_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              SMEM_BYTES) != cudaSuccess ||
+         cudaFuncSetAttribute(stft_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              SMEM_BYTES) != cudaSuccess))
         rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(stft_fold_kernel)");
     if (rc == BRV_OK &&
         (cudaFuncSetAttribute(stft_fold2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2231,7 +2236,10 @@ static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool c
         (g_brv_fold_variant != 3 &&
          (grid < 3LL * fp->sm_count || (fp->q == MAX_Q && prm.rows == TILE_M)));
     if (one_per_cta) {
-        stft_fold_kernel<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(fp->fwd.map, prm);
+        if (prm.post_expo != 0.f)
+            stft_fold_kernel<true><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(fp->fwd.map, prm);
+        else
+            stft_fold_kernel<false><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(fp->fwd.map, prm);
         BRV_LAUNCH_CHECK("stft_fold_kernel");
         return BRV_OK;
     }
