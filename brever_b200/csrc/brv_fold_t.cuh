@@ -660,18 +660,21 @@ __device__ __forceinline__ float decomp_bound(float m2, float pre_scale, float e
 
 struct InvStrip {
     uint32_t g, g1, per_signal;
+    uint32_t s, v;                                     // signal and hop block of column g (one division, at construction)
     int nf, halo;
     bool first;
     __device__ InvStrip(int64_t total, int64_t per_signal_, int nf_, int halo_, int cta, int ctas)
         : g((uint32_t)(total * cta / ctas)), g1((uint32_t)(total * (cta + 1) / ctas)),
-          per_signal((uint32_t)per_signal_), nf(nf_), halo(halo_), first(true) {}
+          per_signal((uint32_t)per_signal_), nf(nf_), halo(halo_), first(true) {
+        s = g / per_signal;
+        v = g - s * per_signal;
+    }
     // tile = columns [c0, c0 + ncols) of signal `sig`; the first `skip` columns only warm up
     // the carried state (their hop blocks belong to the previous strip); `fresh`: no carried
     // state from the previous tile.  A tile that is followed by a non-fresh one is always full
     // (ncols == nf): only the end of a signal or of the strip cuts a tile short.
     __device__ __forceinline__ bool next(int64_t& sig, int64_t& c0, int& ncols, int& skip, bool& fresh) {
         if (g >= g1) return false;
-        const uint32_t s = g / per_signal, v = g - s * per_signal;
         sig = s;
         fresh = first || v == 0;
         skip = first ? (int)min((uint32_t)halo, v) : 0;
@@ -679,6 +682,11 @@ struct InvStrip {
         const uint32_t m = min((uint32_t)nf, min(per_signal - (v - skip), g1 - g + skip));
         ncols = (int)m;
         g += m - skip;
+        v += m - skip;
+        if (v >= per_signal) {                         // the tile ended at the signal's end
+            v = 0;
+            ++s;
+        }
         first = false;
         return true;
     }

@@ -2340,9 +2340,8 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
     // Which kernel (measured on B200, tools/t_sweep.py):
     //   * the transposed strip kernel (istft_t_kernel, 32-frame tiles) for Q = 128 (n_fft 512-class)
     //     and for Q = 64 with hop = Q, at any launch size and for both spectrogram layouts;
-    //     for Q = 64 with hop = 2Q on frame-major spectrograms its duplicated-lane flavour (cfg5: 1034 -> 915 us);
-    //   * the one-tile-per-TMEM kernel for everything else: hop = 4Q, Q = 64 with hop = 2Q on bin-major
-    //     input (911 vs 933 us), Q = 32, Q = 96.
+    //     for Q = 64 with hop = 2Q its duplicated-lane flavour (2048 x 4 s: 1034 -> 856 us, bin-major 908 -> 860 us);
+    //   * the one-tile-per-TMEM kernel for everything else: hop = 4Q, Q = 32, Q = 96.
     // Variants 6 / 7 force the strip kernel (64- / 32-frame tiles), variant 4 the tile kernel.
     const int64_t cols = n_sig * (int64_t)prm.n_blocks;
     bool use_t = false, nf32 = true;
@@ -2351,7 +2350,7 @@ static int fold_inverse_launch(const brv_stft_plan* p, FoldInvParams prm, bool d
             use_t = true;
             nf32 = g_brv_fold_variant == 7;
         } else if (g_brv_fold_variant == 0) {
-            use_t = fp->q == 128 || (fp->q == 64 && (fp->hq == 1 || !frames_fast));
+            use_t = fp->q == 128 || fp->q == 64;
         }
     }
     if (use_t) {
