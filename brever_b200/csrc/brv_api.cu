@@ -49,7 +49,7 @@ static int tc_variant() {
     if (g_tc_variant < 0) {
         const char* e = getenv("BRV_TC_VARIANT");
         const int v = e ? atoi(e) : 0;
-        g_tc_variant = (v >= 1 && v <= 7) ? v : 0;
+        g_tc_variant = (v >= 1 && v <= 8) ? v : 0;
         g_brv_fold_variant = g_tc_variant >= 2 ? g_tc_variant : 0;
     }
     return g_tc_variant;
@@ -57,7 +57,7 @@ static int tc_variant() {
 
 extern "C" int brv_set_tc_variant(int variant) {
     int prev = tc_variant();
-    g_tc_variant = (variant >= 1 && variant <= 7) ? variant : 0;
+    g_tc_variant = (variant >= 1 && variant <= 8) ? variant : 0;
     g_brv_fold_variant = g_tc_variant >= 2 ? g_tc_variant : 0;
     return prev;
 }

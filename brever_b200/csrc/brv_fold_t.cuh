@@ -111,19 +111,29 @@ constexpr int FT_THREADS = 896;
 constexpr int FT_LOADER_WARP0 = 2;
 constexpr int FT_EPI_WARP0 = 4, FT_EPI_WARPS = 8;
 constexpr int FT_BUILD_WARP0 = 12, FT_BUILD_WARPS = 16;
-constexpr int FT_SPAN = (T_NF - 1) * 128 + 512 + 64;        // floats per span buffer (8640)
 constexpr int FT_BMAX_W = 72;                               // per-builder-warp maxima (<= (3 H + N) / 32 + 2)
-constexpr int FT_OFF_SPAN = T_SMEM_STAGES;
-constexpr int FT_OFF_WTAB = FT_OFF_SPAN + 2 * FT_SPAN * 4;
-constexpr int FT_OFF_ROWINFO = FT_OFF_WTAB + SMEM_WTAB;      // 2 slots x 64 float4
-constexpr int FT_OFF_BMAX = FT_OFF_ROWINFO + 2 * T_NF * 16;
-constexpr int FT_SMEM_BYTES = 1024 + FT_OFF_BMAX + FT_BUILD_WARPS * FT_BMAX_W * 4 + 32;
-static_assert(FT_SMEM_BYTES <= 227 * 1024, "transposed forward kernel shared memory");
+// Shared memory of the forward kernel for NF frames per tile (64: two TMEM buffers, 3 stages; 32: four
+// TMEM buffers, 4 stages -- a shorter pipeline fill for launches of a few tiles per SM)
+template <int NF>
+struct FtLayout {
+    static constexpr int NBUF = T_TMEM_COLS / (4 * NF);
+    static constexpr int DATA_TILE = NF * BK * 2;
+    static constexpr int STAGE_BYTES = T_STAGE_BASIS + 4 * DATA_TILE;
+    static constexpr int STAGES = NF == 64 ? 3 : 4;
+    static constexpr int SPAN = (NF - 1) * 128 + 512 + 64;      // floats per span buffer
+    static constexpr int OFF_SPAN = STAGES * STAGE_BYTES;
+    static constexpr int OFF_WTAB = OFF_SPAN + 2 * SPAN * 4;
+    static constexpr int OFF_ROWINFO = OFF_WTAB + SMEM_WTAB;     // NBUF slots x NF float4
+    static constexpr int OFF_BMAX = OFF_ROWINFO + NBUF * NF * 16;
+    static constexpr int SMEM_BYTES = 1024 + OFF_BMAX + FT_BUILD_WARPS * FT_BMAX_W * 4 + 32;
+    static_assert(SMEM_BYTES <= 227 * 1024, "transposed forward kernel shared memory");
+};
 
 // frames per tile for a given geometry: the tile's span must fit one span buffer
-static inline int ft_tile_frames(int n_fft, int hop, int shift) {
-    int nf = (FT_SPAN - 32 - n_fft - shift) / hop + 1;
-    return nf > T_NF ? T_NF : nf;
+static inline int ft_tile_frames(int n_fft, int hop, int shift, int nf_max) {
+    const int span = (nf_max - 1) * 128 + 512 + 64;
+    int nf = (span - 32 - n_fft - shift) / hop + 1;
+    return nf > nf_max ? nf_max : nf;
 }
 
 // iSTFT gradient: span[i] *= 1 / (overlap-added w^2) of sample span0 + i (position + origin)
@@ -145,27 +155,30 @@ __device__ __noinline__ void ft_apply_envelope(float* span, int i_begin, int i_e
     }
 }
 
-template <bool COMPRESS>
+template <bool COMPRESS, int NF>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams p) {
+    using L = FtLayout<NF>;
+    constexpr int NBUF = L::NBUF, NSTAGE = L::STAGES, STAGE_BYTES = L::STAGE_BYTES, DATA_TILE = L::DATA_TILE;
+    constexpr int SPAN = L::SPAN;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[T_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[T_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full[2];     // MMA -> epilogue
-    __shared__ __align__(8) uint64_t tmem_empty[2];    // epilogue -> MMA
+    __shared__ __align__(8) uint64_t full_bar[4];
+    __shared__ __align__(8) uint64_t empty_bar[4];
+    __shared__ __align__(8) uint64_t tmem_full[4];     // MMA -> epilogue
+    __shared__ __align__(8) uint64_t tmem_empty[4];    // epilogue -> MMA
     __shared__ __align__(8) uint64_t span_empty[2];    // builders -> loader
-    __shared__ __align__(8) uint64_t ri_full[2];       // builders -> epilogue (row info complete)
-    __shared__ __align__(8) uint64_t ri_empty[2];      // epilogue -> builders (row info slot)
+    __shared__ __align__(8) uint64_t ri_full[4];       // builders -> epilogue (row info complete)
+    __shared__ __align__(8) uint64_t ri_empty[4];      // epilogue -> builders (row info slot)
     __shared__ __align__(8) uint64_t span_landed[2];   // loader -> builders: span staged (bulk copy + edges)
     __shared__ __align__(8) uint64_t span_copied[2];   // bulk copy landed (loader's own, gradient use)
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     uint8_t* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* span2 = reinterpret_cast<float*>(stages + FT_OFF_SPAN);
-    float4* wtab = reinterpret_cast<float4*>(stages + FT_OFF_WTAB);
-    float4* rowinfo2 = reinterpret_cast<float4*>(stages + FT_OFF_ROWINFO);
-    uint32_t* bmax_all = reinterpret_cast<uint32_t*>(stages + FT_OFF_BMAX);
+    float* span2 = reinterpret_cast<float*>(stages + L::OFF_SPAN);
+    float4* wtab = reinterpret_cast<float4*>(stages + L::OFF_WTAB);
+    float4* rowinfo2 = reinterpret_cast<float4*>(stages + L::OFF_ROWINFO);
+    uint32_t* bmax_all = reinterpret_cast<uint32_t*>(stages + L::OFF_BMAX);
 
     const int N = p.n_fft, H = p.hop, Q = p.q, Hf = N / 2;
     const int n_kc = Q / BK;
@@ -175,16 +188,18 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
     const bool dup = Q == 64;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < T_STAGES; ++s) {
+        for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full_bar[s], 1 + FT_BUILD_WARPS);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             mbar_init(&tmem_full[b], 1);
             mbar_init(&tmem_empty[b], FT_EPI_WARPS);
-            mbar_init(&span_empty[b], FT_BUILD_WARPS);
             mbar_init(&ri_full[b], FT_BUILD_WARPS);
             mbar_init(&ri_empty[b], FT_EPI_WARPS);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&span_empty[b], FT_BUILD_WARPS);
             mbar_init(&span_landed[b], 2);              // expect_tx arrive + edge fills done
             mbar_init(&span_copied[b], 1);
         }
@@ -211,8 +226,8 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
             int g = 0;
             while (strip.next(sig, t0, ncols))
                 for (int it = 0; it < n_it; ++it, ++g) {
-                    const int s = g % T_STAGES;
-                    const uint32_t ph = (g / T_STAGES) & 1;
+                    const int s = g % NSTAGE;
+                    const uint32_t ph = (g / NSTAGE) & 1;
                     const int kc = it >> 1, pair = it & 1;
                     T_WAITED(0, mbar_wait_relaxed(&empty_bar[s], ph ^ 1));
 #ifdef BRV_T_NO_TMA                                     // dev experiment: timing without the basis stream
@@ -220,7 +235,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                     (void)kc; (void)pair;
 #else
                     mbar_arrive_expect_tx(&full_bar[s], (dup ? 8u : 4u) * (uint32_t)Q * BK * 2);
-                    uint8_t* sb = stages + (size_t)s * T_STAGE_BYTES;
+                    uint8_t* sb = stages + (size_t)s * STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -241,30 +256,30 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
             T_WAIT_DECL;
             int g = 0, n = 0;
             for (; strip.next(sig, t0, ncols); ++n) {
-                const int buf = n & 1;
+                const int buf = n % NBUF;
                 const uint32_t idesc = umma_idesc_f16(TILE_M, (ncols + 15) & ~15);
                 T_STAMP(2, n, 0);
-                T_WAITED(0, mbar_wait_relaxed(&tmem_empty[buf], (uint32_t)(((n >> 1) & 1) ^ 1)));
+                T_WAITED(0, mbar_wait_relaxed(&tmem_empty[buf], (uint32_t)(((n / NBUF) & 1) ^ 1)));
                 tcgen05_fence_after();
                 T_STAMP(2, n, 1);
                 for (int it = 0; it < n_it; ++it, ++g) {
-                    const int s = g % T_STAGES;
-                    const uint32_t ph = (g / T_STAGES) & 1;
+                    const int s = g % NSTAGE;
+                    const uint32_t ph = (g / NSTAGE) & 1;
                     const int kc = it >> 1, pair = it & 1;
                     T_WAITED(1, mbar_wait_relaxed(&full_bar[s], ph, 32));
                     tcgen05_fence_after();
-                    const uint32_t a0 = smem_u32(stages + (size_t)s * T_STAGE_BYTES);
+                    const uint32_t a0 = smem_u32(stages + (size_t)s * STAGE_BYTES);
                     const uint32_t b0 = a0 + T_STAGE_BASIS;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        const uint32_t d = tmem_base + (uint32_t)(buf * 4 * T_NF + (pair * 2 + j) * T_NF);
+                        const uint32_t d = tmem_base + (uint32_t)(buf * 4 * NF + (pair * 2 + j) * NF);
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
                             const uint32_t off = ks * UMMA_K * 2;
                             const uint64_t bh = umma_desc_sw64(a0 + (j * 2) * SUB_TILE + off);
                             const uint64_t bl = umma_desc_sw64(a0 + (j * 2 + 1) * SUB_TILE + off);
-                            const uint64_t dh = umma_desc_sw64(b0 + (j * 2) * T_DATA_TILE + off);
-                            const uint64_t dl = umma_desc_sw64(b0 + (j * 2 + 1) * T_DATA_TILE + off);
+                            const uint64_t dh = umma_desc_sw64(b0 + (j * 2) * DATA_TILE + off);
+                            const uint64_t dl = umma_desc_sw64(b0 + (j * 2 + 1) * DATA_TILE + off);
 #ifndef BRV_T_NO_MMA                                    // dev experiments: MMA count
                             umma_f16(d, bh, dh, idesc, (kc | ks) != 0);
 #ifndef BRV_T_ONE_PRODUCT
@@ -290,7 +305,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
         const bool mul = p.in_mul != nullptr || p.grad_env;
         for (int n = 0; strip.next(sig, t0, ncols); ++n) {
             const int b = n & 1;
-            float* span = span2 + b * FT_SPAN;
+            float* span = span2 + b * SPAN;
             const float* xs = p.x + sig * p.x_stride;
             const int64_t span0 = t0 * H - p.origin - shift;       // first sample of the span (may be < 0)
             const int span_len = (ncols - 1) * H + N + shift;
@@ -339,10 +354,10 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
         T_WAIT_DECL;
         const int e = warp - FT_EPI_WARP0;         // 0..7
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
-        const int chalf = e >> 2;                  // which 32 frames of the tile
+        const int chalf = e >> 2;                  // which half of the tile's frames
         const int m = dup ? (q & 1) * 32 + lane : q * 32 + lane;       // bin pair: bins 2m, 2m+1
-        const int c_lo = chalf * 32 + (dup ? (q >> 1) * 16 : 0);       // this warp's columns
-        const int c_n = dup ? 16 : 32;
+        const int c_lo = chalf * (NF / 2) + (dup ? (q >> 1) * (NF / 4) : 0);       // this warp's columns
+        const int c_n = dup ? NF / 4 : NF / 2;
         const bool valid = m < Q;
         const float sgn = (m & 1) ? -1.f : 1.f;
         const int pitch = 2 * p.n_bins;
@@ -352,16 +367,16 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
         const float nys = (p.odd && m == Q - 1) ? p.edge_scale : 1.f;   // n_fft = 4Q - 2: Nyquist = last odd bin
         const float gb = ps * p.basis_scale_inv;
         for (int n = 0; strip.next(sig, t0, ncols); ++n) {
-            const int buf = n & 1;
-            const float4* rowinfo = rowinfo2 + buf * T_NF;
-            const uint32_t kph = (uint32_t)((n >> 1) & 1);
+            const int buf = n % NBUF;
+            const float4* rowinfo = rowinfo2 + buf * NF;
+            const uint32_t kph = (uint32_t)((n / NBUF) & 1);
             if (warp == FT_EPI_WARP0) T_STAMP(3, n, 0);
             T_WAITED(0, mbar_wait_relaxed(&ri_full[buf], kph));
             T_WAITED(1, mbar_wait_relaxed(&tmem_full[buf], kph));
             tcgen05_fence_after();
             if (warp == FT_EPI_WARP0) T_STAMP(3, n, 1);
             float* obase = p.out + ((sig * p.n_frames + t0) * (int64_t)pitch + 4 * m);
-            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * T_NF);
+            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * NF);
 #pragma unroll 1
             for (int cb = 0; cb < c_n; cb += 8) {
                 const int c0 = c_lo + cb;
@@ -371,9 +386,9 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                 if (c0 >= ncols) break;
                 uint32_t r0[8], r1[8], r2[8], r3[8];
                 tmem_ld8_nowait(tq + (uint32_t)(c0), r0);              // Re X[2m]
-                tmem_ld8_nowait(tq + (uint32_t)(T_NF + c0), r1);       // Re X[2m+1]
-                tmem_ld8_nowait(tq + (uint32_t)(2 * T_NF + c0), r2);   // Im X[2m]
-                tmem_ld8_nowait(tq + (uint32_t)(3 * T_NF + c0), r3);   // Im X[2m+1]
+                tmem_ld8_nowait(tq + (uint32_t)(NF + c0), r1);       // Re X[2m+1]
+                tmem_ld8_nowait(tq + (uint32_t)(2 * NF + c0), r2);   // Im X[2m]
+                tmem_ld8_nowait(tq + (uint32_t)(3 * NF + c0), r3);   // Im X[2m+1]
                 float* o0 = obase + (int64_t)c0 * pitch;
                 const bool a0 = (reinterpret_cast<uintptr_t>(o0) & 15) == 0;    // c0 is even
                 tmem_ld_wait();
@@ -427,7 +442,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
         const int pr = lane & 15;                  // n pair inside the 32-wide k-chunk
         const uint32_t chunk = (uint32_t)(pr >> 2);
         const int shift = p.shift;
-        constexpr int RI = T_NF / FT_BUILD_WARPS / 2;     // row pairs per warp (2)
+        constexpr int RI = NF / FT_BUILD_WARPS / 2;     // row pairs per warp (2)
         constexpr int ROWS_W = 2 * RI;                    // rows per warp (4)
         uint32_t soff[RI];                                // swizzled byte offset of this lane's 4 bytes per row
 #pragma unroll
@@ -437,13 +452,13 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
         }
         int g = 0;
         for (int n = 0; strip.next(sig, t0, ncols); ++n) {
-            const int b = n & 1;
-            const float* span = span2 + b * FT_SPAN;
-            float4* rowinfo = rowinfo2 + b * T_NF;
+            const int b = n & 1, slot = n % NBUF;
+            const float* span = span2 + b * SPAN;
+            float4* rowinfo = rowinfo2 + slot * NF;
             if (bw == 0) T_STAMP(1, n, 0);
             const uint32_t kph = (uint32_t)((n >> 1) & 1);
             mbar_wait_relaxed(&span_landed[b], kph, 20);
-            mbar_wait_relaxed(&ri_empty[b], kph ^ 1, 20);
+            mbar_wait_relaxed(&ri_empty[slot], (uint32_t)(((n / NBUF) & 1) ^ 1), 20);
             if (bw == 0) T_STAMP(1, n, 1);
             if (bw * ROWS_W < ncols) {
                 // ---- this warp's frames: per-32-sample maxima of the samples they cover (the
@@ -522,13 +537,13 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
 #endif
 #pragma unroll
                 for (int pair = 0; pair < 2; ++pair, ++g) {
-                    const int s = g % T_STAGES;
-                    const uint32_t ph = (g / T_STAGES) & 1;
+                    const int s = g % NSTAGE;
+                    const uint32_t ph = (g / NSTAGE) & 1;
                     T_WAITED(2, mbar_wait_relaxed(&empty_bar[s], ph ^ 1, 20));
 #ifdef BRV_PHASE_TIMING
                     const long long ts0_ = clock64();
 #endif
-                    uint8_t* sa = stages + (size_t)s * T_STAGE_BYTES + T_STAGE_BASIS;
+                    uint8_t* sa = stages + (size_t)s * STAGE_BYTES + T_STAGE_BASIS;
 #ifdef BRV_T_NO_BUILD                                   // dev experiment: timing without the operand build
                     if (p.n_fft < 0)
 #endif
@@ -545,8 +560,8 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
                         }
                         const float sc = rscale[i];
                         uint8_t* dst = sa + soff[i];
-                        split_store(dst, dst + T_DATA_TILE, u0 * sc, u1 * sc);
-                        split_store(dst + 2 * T_DATA_TILE, dst + 3 * T_DATA_TILE, v0 * sc, v1 * sc);
+                        split_store(dst, dst + DATA_TILE, u0 * sc, u1 * sc);
+                        split_store(dst + 2 * DATA_TILE, dst + 3 * DATA_TILE, v0 * sc, v1 * sc);
                     }
                     if (pair == 1 && kc == n_kc - 1) {
                         // the Nyquist sums must be visible before the tile's last stage is released
@@ -575,7 +590,7 @@ stft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldFwdParams
             }
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&ri_full[b]);
+                mbar_arrive(&ri_full[slot]);
                 mbar_arrive(&span_empty[b]);
             }
             if (bw == 0) T_STAMP(1, n, 2);

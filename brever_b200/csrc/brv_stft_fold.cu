@@ -2036,10 +2036,14 @@ int brv_fold_plan_init(brv_stft_plan* p) {
                               F2_SMEM_BYTES) != cudaSuccess))
         rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(stft_fold2_kernel)");
     if (rc == BRV_OK &&
-        (cudaFuncSetAttribute(stft_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              FT_SMEM_BYTES) != cudaSuccess ||
-         cudaFuncSetAttribute(stft_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              FT_SMEM_BYTES) != cudaSuccess))
+        (cudaFuncSetAttribute(stft_t_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              FtLayout<64>::SMEM_BYTES) != cudaSuccess ||
+         cudaFuncSetAttribute(stft_t_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              FtLayout<64>::SMEM_BYTES) != cudaSuccess ||
+         cudaFuncSetAttribute(stft_t_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              FtLayout<32>::SMEM_BYTES) != cudaSuccess ||
+         cudaFuncSetAttribute(stft_t_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              FtLayout<32>::SMEM_BYTES) != cudaSuccess))
         rc = brv_fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(stft_t_kernel)");
     if (rc == BRV_OK &&
         cudaDeviceGetAttribute(&fp->sm_count, cudaDevAttrMultiProcessorCount, p->device) !=
@@ -2177,8 +2181,8 @@ static bool fold_forward_uses_t(const brv_stft_plan* p, int64_t n_sig, int64_t n
     const FoldPlan* fp = (const FoldPlan*)p->fold;
     if (origin < 0) origin = brv_left(p);
     const int shift = p->hop % 4 == 0 ? (4 - (origin & 3)) & 3 : 0;
-    if (ft_tile_frames(p->n_fft, p->hop, shift) < 16) return false;
-    return g_brv_fold_variant == 5 ||
+    if (ft_tile_frames(p->n_fft, p->hop, shift, 32) < 16) return false;
+    return g_brv_fold_variant == 5 || g_brv_fold_variant == 8 ||
            (g_brv_fold_variant == 0 && n_sig * n_frames >= 512LL * fp->sm_count);
 }
 
@@ -2197,7 +2201,9 @@ static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool c
     prm.tmem_cols = fp->tmem_cols;
     prm.basis_scale_inv = fp->fwd.scale_inv;
     if (fold_forward_uses_t(p, n_sig, n_frames, prm.origin)) {
-        const int nf = ft_tile_frames(p->n_fft, p->hop, prm.shift);
+        // variant 8: 32-frame tiles, four of them resident in TMEM (shorter pipeline fill)
+        const bool nf32 = g_brv_fold_variant == 8;
+        const int nf = ft_tile_frames(p->n_fft, p->hop, prm.shift, nf32 ? 32 : 64);
         {
             prm.rows = nf;
             prm.tiles_per_signal = 0;
@@ -2205,10 +2211,15 @@ static int fold_forward_launch(const brv_stft_plan* p, FoldFwdParams prm, bool c
             BRV_REQUIRE(prm.total_tiles < (1LL << 31), "too many frames (%lld)", (long long)prm.total_tiles);
             const int64_t want = brv_ceil_div(prm.total_tiles, 16);
             const unsigned ctas = (unsigned)(want < fp->sm_count ? want : fp->sm_count);
-            if (compress)
-                stft_t_kernel<true><<<ctas, FT_THREADS, FT_SMEM_BYTES, st>>>(fp->fwd.map, prm);
+            if (nf32) {
+                if (compress)
+                    stft_t_kernel<true, 32><<<ctas, FT_THREADS, FtLayout<32>::SMEM_BYTES, st>>>(fp->fwd.map, prm);
+                else
+                    stft_t_kernel<false, 32><<<ctas, FT_THREADS, FtLayout<32>::SMEM_BYTES, st>>>(fp->fwd.map, prm);
+            } else if (compress)
+                stft_t_kernel<true, 64><<<ctas, FT_THREADS, FtLayout<64>::SMEM_BYTES, st>>>(fp->fwd.map, prm);
             else
-                stft_t_kernel<false><<<ctas, FT_THREADS, FT_SMEM_BYTES, st>>>(fp->fwd.map, prm);
+                stft_t_kernel<false, 64><<<ctas, FT_THREADS, FtLayout<64>::SMEM_BYTES, st>>>(fp->fwd.map, prm);
             BRV_LAUNCH_CHECK("stft_t_kernel");
             return BRV_OK;
         }
