@@ -225,6 +225,53 @@ channel_mean_mask_kernel(const float2* __restrict__ X, int64_t xb, int64_t xc, i
     }
 }
 
+// The common case -- frame-major spectrogram (bins contiguous) and a bin-major mask (frames
+// contiguous: what MelFilterbank.backward returns) -- reads the mask through a 32 x 32 shared
+// memory tile so that both streams and the output are coalesced (the element-wise kernel above
+// touches one 32-byte sector per mask value there).
+__global__ void __launch_bounds__(256)
+channel_mean_mask_tiled_kernel(const float2* __restrict__ X, int64_t xb, int64_t xc, int64_t xt,
+                               const float* __restrict__ mask, int64_t mb, int64_t mf, int n_channels,
+                               int n_bins, int64_t n_frames, float2* __restrict__ out) {
+    __shared__ float tile[32][33];                         // [bin][frame]
+    const int64_t b = blockIdx.z;
+    const int64_t t0 = (int64_t)blockIdx.y * 32;
+    const int f0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const float inv_c = 1.f / (float)n_channels;
+    const float* mp = mask + b * mb;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                          // rows = bins, lanes along frames
+        const int f = f0 + ty + 8 * r;
+        const int64_t t = t0 + tx;
+        tile[ty + 8 * r][tx] = (f < n_bins && t < n_frames) ? __ldg(mp + (int64_t)f * mf + t) : 0.f;
+    }
+    __syncthreads();
+    const float2* xs = X + b * xb;
+    float2 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                          // rows = frames, lanes along bins
+        const int64_t t = t0 + ty + 8 * r;
+        const int f = f0 + tx;
+        acc[r] = make_float2(0.f, 0.f);
+        if (f < n_bins && t < n_frames)
+            for (int c = 0; c < n_channels; ++c) {
+                const float2 v = __ldg(xs + (int64_t)c * xc + t * xt + f);
+                acc[r].x += v.x;
+                acc[r].y += v.y;
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t t = t0 + ty + 8 * r;
+        const int f = f0 + tx;
+        if (f < n_bins && t < n_frames) {
+            const float m = tile[tx][ty + 8 * r] * inv_c;
+            out[(b * n_frames + t) * n_bins + f] = make_float2(acc[r].x * m, acc[r].y * m);
+        }
+    }
+}
+
 // total += mean(v): the running metric of the training loop (training.py:369-373) without two
 // ATen launches per step
 __global__ void accumulate_mean_kernel(const float* __restrict__ v, int64_t n, float* __restrict__ total) {
@@ -252,6 +299,13 @@ extern "C" int brv_channel_mean_mask(const void* X, int64_t xb, int64_t xc, int6
     BRV_REQUIRE(X && out, "null pointer argument");
     BRV_REQUIRE(n_batch < 65536, "more than 65535 batch items per call");
     BRV_REQUIRE(n_frames * n_bins < (1LL << 40), "spectrogram too large");
+    if (mask && xf == 1 && mt == 1 && brv_ceil_div(n_frames, 32) < 65536) {
+        dim3 tgrid((unsigned)brv_ceil_div(n_bins, 32), (unsigned)brv_ceil_div(n_frames, 32), (unsigned)n_batch);
+        channel_mean_mask_tiled_kernel<<<tgrid, 256, 0, (cudaStream_t)stream>>>(
+            (const float2*)X, xb, xc, xt, mask, mb, mf, n_channels, n_bins, n_frames, (float2*)out);
+        BRV_LAUNCH_CHECK("channel_mean_mask_tiled_kernel");
+        return BRV_OK;
+    }
     dim3 grid((unsigned)brv_ceil_div(n_frames * n_bins, 256 * CM_ITEMS), (unsigned)n_batch);
     channel_mean_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const float2*)X, xb, xc, xf, xt, mask, mb, mf, mt, n_channels, n_bins, n_frames, (float2*)out);

@@ -242,6 +242,12 @@ def test_channel_mean_mask_and_accumulate():
     assert torch.allclose(out, ref, rtol=1e-6, atol=1e-7)
     assert torch.allclose(brv.ffnn.channel_mean(spec.transpose(2, 3).contiguous().transpose(2, 3)), spec.mean(1),
                           rtol=1e-6, atol=1e-7)
+    # the layout pair of the real call (frame-major STFT output, bin-major mask): tiled kernel
+    fm = crandn((3, 2, 257, 45), 64).to(DEV).transpose(2, 3).contiguous().transpose(2, 3)
+    m2 = randn((3, 257, 45), 65).abs().to(DEV)
+    out2 = brv.ffnn.channel_mean(fm, m2)
+    assert out2.transpose(1, 2).is_contiguous()
+    assert torch.allclose(out2, fm.mean(1) * m2, rtol=1e-6, atol=1e-7)
     total = torch.zeros((), device=DEV)
     v = randn((37,), 63).to(DEV)
     brv.ffnn.accumulate_mean(total, v)
