@@ -724,8 +724,9 @@ __device__ __forceinline__ void it_frame_values(uint32_t ace, uint32_t aco, uint
     const float fse = __uint_as_float(ase), fso = __uint_as_float(aso);
     if (ODD) {
         // n_fft = 4Q - 2: no Nyquist term outside the contraction, no self-paired samples
-        const float cp = (fce + fco) * ri.x, cm = (fce - fco) * ri.x;
-        const float sp = (fse + fso) * ri.x, sm = (fse - fso) * ri.x;
+        // (1 / scales travel in ri.y here: the bin-major builders write it without a barrier)
+        const float cp = (fce + fco) * ri.y, cm = (fce - fco) * ri.y;
+        const float sp = (fse + fso) * ri.y, sm = (fse - fso) * ri.y;
         a = (cp - sp) * wn.x;           // f[n]
         b = (cm + sm) * wn.y;           // f[N/2 - n]
         c = (cm - sm) * wn.z;           // f[N/2 + n]   (n >= 1)
@@ -1205,6 +1206,16 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                         mbar_arrive(&full_bar[s1]);
                     }
                 }
+                if (ODD) {
+                    // n_fft = 4Q - 2 has no rank-1 terms: only 1 / scales for the epilogue, in a field
+                    // nobody reads during the tile -- no CTA-wide barrier needed
+                    if (kq == 0 && grp == 0) rowinfo[row].y = sc > 0.f ? p.basis_scale_inv * pow2_inv(sc) : 0.f;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ri_full[slot]);
+                    if (bw == 0) T_STAMP(1, n, 2);
+                    if (bw == 0) T_WAIT_FLUSH(1);
+                    continue;
+                }
                 // rank-1 sums: 4 NGRP partials per frame through the scratch rows
                 scratch[(grp * 4 + kq) * NF + row] = pacc;
                 scratch[(4 * NGRP + grp * 4 + kq) * NF + row] = racc;
@@ -1319,9 +1330,10 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                             const float4 ri = rowinfo[row0 + 2 * i];
                             a *= 2.f * fold_scale;
                             b *= 2.f * fold_scale;
-                            rowinfo[row0 + 2 * i] =
-                                make_float4(rscale[i] != 0.f ? p.basis_scale_inv * pow2_inv(ri.x) : 0.f,
-                                            (a - b + ri.w) * p.wq, (a + b + ri.w) * p.w3q, ri.w);
+                            const float g0 = rscale[i] != 0.f ? p.basis_scale_inv * pow2_inv(ri.x) : 0.f;
+                            rowinfo[row0 + 2 * i] = ODD ? make_float4(g0, g0, 0.f, 0.f)
+                                                        : make_float4(g0, (a - b + ri.w) * p.wq,
+                                                                      (a + b + ri.w) * p.w3q, ri.w);
                         }
                     }
                 }
