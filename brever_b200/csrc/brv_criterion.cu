@@ -510,25 +510,28 @@ __global__ void apply_mask_kernel(const float* __restrict__ x, const int64_t* __
 
 }  // namespace
 
-// samples per CTA = ITERS * 4096; ITERS from BRV_CR_ITERS (1, 2 or 4; tuning knob)
-static int cr_iters() {
-    static int iters = 0;
-    if (!iters) {
+// samples per CTA = ITERS * 4096.  Measured on B200: 2 for problems of a few MB per array (64 x 4 s:
+// 11.4 us against 13.4 / 12.4 with 1 / 4), 4 once the arrays reach tens of MB (256 x 4 s: 27.2 us
+// against 28.8).  BRV_CR_ITERS (1, 2 or 4) overrides.
+static int cr_iters(int64_t n_pairs, int64_t length) {
+    static int forced = -1;
+    if (forced < 0) {
         const char* e = getenv("BRV_CR_ITERS");
-        int v = e ? atoi(e) : 2;
-        iters = (v == 1 || v == 2 || v == 4) ? v : 2;
+        const int v = e ? atoi(e) : 0;
+        forced = (v == 1 || v == 2 || v == 4) ? v : 0;
     }
-    return iters;
+    if (forced) return forced;
+    return n_pairs * length >= 12LL * 1000 * 1000 ? 4 : 2;
 }
-static int chunks_for(int64_t length) {
-    int64_t c = brv_ceil_div(length, (int64_t)CR_BLOCK * cr_iters());
+static int chunks_for(int64_t n_pairs, int64_t length) {
+    int64_t c = brv_ceil_div(length, (int64_t)CR_BLOCK * cr_iters(n_pairs, length));
     return (int)(c < 1 ? 1 : c);
 }
 
 extern "C" size_t brv_snr_workspace_bytes(int64_t n_pairs, int64_t length) {
     if (n_pairs <= 0) return 256;
     size_t tickets = ((size_t)n_pairs * sizeof(unsigned int) + 255) & ~(size_t)255;
-    return tickets + (size_t)n_pairs * chunks_for(length) * CR_MOMENTS * sizeof(double);
+    return tickets + (size_t)n_pairs * chunks_for(n_pairs, length) * CR_MOMENTS * sizeof(double);
 }
 
 extern "C" int brv_snr_forward(const float* x, const float* y, const int64_t* lengths,
@@ -541,7 +544,7 @@ extern "C" int brv_snr_forward(const float* x, const float* y, const int64_t* le
     BRV_REQUIRE(n_batch >= 0 && n_rows >= 1 && length >= 0, "bad criterion shape");
     const int64_t n_pairs = pairwise ? n_batch * n_rows * n_rows : n_batch * n_rows;
     if (n_pairs == 0) return BRV_OK;
-    const int chunks = chunks_for(length);
+    const int chunks = chunks_for(n_pairs, length);
     BRV_REQUIRE(n_pairs <= 2147483647LL && chunks < 65536, "criterion problem too large");
     BRV_REQUIRE(workspace_bytes >= brv_snr_workspace_bytes(n_pairs, length),
                 "criterion workspace too small: %zu < %zu", workspace_bytes,
@@ -555,7 +558,7 @@ extern "C" int brv_snr_forward(const float* x, const float* y, const int64_t* le
     snr_moments_kernel<PW_, IT_><<<grid, CR_THREADS, 0, (cudaStream_t)stream>>>(                \
         x, y, lengths, n_rows, length, xsb, xsr, ysb, ysr, eps, out_sign, chunks, out_db,       \
         moments, partial, ticket)
-    switch (cr_iters() * 2 + (pairwise ? 1 : 0)) {
+    switch (cr_iters(n_pairs, length) * 2 + (pairwise ? 1 : 0)) {
         case 2: BRV_LAUNCH_SNR(false, 1); break;
         case 3: BRV_LAUNCH_SNR(true, 1); break;
         case 4: BRV_LAUNCH_SNR(false, 2); break;
