@@ -55,8 +55,13 @@ uint64_t brv_launch_count(void);
  * of the tensor-core kernels (also: env BRV_FORCE_GENERIC=1).  Returns the
  * previous setting.  Both are CUDA paths; there is no CPU path to select. */
 int brv_set_force_generic(int on);
-/* Testing hook: 0 (default) = symmetry-folded tensor-core kernels where the plan
- * supports them, 1 = the dense DFT contraction only.  Returns the previous value. */
+/* Testing hook (also: env BRV_TC_VARIANT).  0 (default) = symmetry-folded tensor-core
+ * kernels where the plan supports them, picked per geometry and launch size; 1 = the
+ * dense DFT contraction only; 2 / 3 = forward tile kernel: one tile per CTA / persistent
+ * two-pass; 4 = the one-tile-per-TMEM kernels only; 5 = forward strip kernel at any size;
+ * 6 / 7 = inverse strip kernel with 64- / 32-frame tiles at any size; 8 = forward strip
+ * kernel with 32-frame tiles.  Every variant computes the same result to fp32 rounding;
+ * the parity tests run them against each other.  Returns the previous value. */
 int brv_set_tc_variant(int variant);
 /* SM count / compute capability of the current device; fails without a GPU. */
 int brv_device_query(int* sm_count, int* cc_major, int* cc_minor);
