@@ -171,3 +171,25 @@ def test_strip_conv_stft_round_trip():
         y1 = conv.backward(X0)
     assert rel_err(cpu(X1), cpu(X0))[0] < 2e-6
     assert rel_err(cpu(y1), cpu(y0))[0] < 5e-6
+
+
+@pytest.mark.parametrize('kw', [dict(frame_length=512, hop_length=128),
+                                dict(frame_length=256, hop_length=128, normalized=False),
+                                dict(frame_length=510, hop_length=128, normalized=False)])
+@pytest.mark.parametrize('shape', [(1, 2_000_000), (4096, 1500), (7, 123_457)])
+def test_round_trip_extreme_aspect_ratios(kw, shape):
+    """Default dispatch, size-independent property: iSTFT(STFT(x)) == x on one very long signal
+    (every CTA's strip lies inside the same signal), on thousands of very short ones (every tile
+    ends at a signal end) and on a ragged in-between, with a loud and a quiet stretch per signal."""
+    x = randn(shape, 71)
+    x[..., : shape[1] // 3] *= 1e-3
+    dev = x.to(DEV)
+    stft = brv.STFT(**kw)
+    y = stft.backward(stft(dev))[..., : shape[1]]
+    n = y.shape[-1]                    # hop * (T - 1): a few samples short of the input when hop does not divide n_fft
+    assert shape[1] - n < stft.hop_length
+    err = (y - dev[..., :n]).abs()
+    assert float(err.max()) < 2e-5, (kw, shape, float(err.max()))
+    if shape[1] // 3 > 1200:           # frames that only see the quiet stretch: per-frame scales keep them exact
+        quiet = err[..., : shape[1] // 3 - 600]
+        assert float(quiet.max()) < 2e-8, (kw, shape, float(quiet.max()))
