@@ -1468,41 +1468,53 @@ istft_t_kernel(const __grid_constant__ CUtensorMap basis_map, const FoldInvParam
                 }
                 T_WAITED(1, named_bar_sync(2, IT_SCOUT_THREADS));
             } else {
-                // warp = frame (bins contiguous), two frames in flight per warp
+                // warp = frame (bins contiguous), SR frames in flight per warp: one for Q = 128 (the
+                // builders take long enough per tile, and the smaller loop is measurably faster: cfg4
+                // 184 -> 174 us), two for Q <= 64 (short tiles: the scouts need the bytes in flight,
+                // cfg5 462 -> 384 us)
                 const int nj = Q / 16;             // 32-bin groups below the Nyquist bin
+                auto scan_rows = [&](auto sr_c) {
+                    constexpr int SR = decltype(sr_c)::value;
 #pragma unroll 1
-                for (int r0 = 2 * sw; r0 < NF; r0 += 2 * IT_SCOUT_WARPS) {
-                    float2 v[2][8];
-                    float2 vn[2];
+                    for (int r0 = SR * sw; r0 < NF; r0 += SR * IT_SCOUT_WARPS) {
+                        float2 v[SR][8];
+                        float2 vn[SR];
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const int row = r0 + r;
-                        const bool live = row < ncols && c0 + row < p.n_frames;
-                        const float2* xr = xs + (c0 + row) * p.sf;      // sb == 1
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            v[r][j] = (live && j < nj) ? __ldg(xr + j * 32 + lane) : make_float2(0.f, 0.f);
-                        vn[r] = (live && lane == 0 && !ODD) ? __ldg(xr + Hf) : make_float2(0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const int row = r0 + r;
-                        if (lane == 0) v[r][0].y = 0.f;   // Im X[0] never reaches the output
-                        float m = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            m = fmaxf(m, DECOMP ? norm2_finite(v[r][j])
-                                                : abs2_finite(prep_bin<false>(v[r][j], p.pre_scale, p.pre_expo)));
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                        if (DECOMP) m = decomp_bound(m, p.pre_scale, p.pre_expo);
-                        if (lane == 0 && row < NF) {
+                        for (int r = 0; r < SR; ++r) {
+                            const int row = r0 + r;
                             const bool live = row < ncols && c0 + row < p.n_frames;
-                            const float ny = prep_bin<DECOMP>(vn[r], p.pre_scale, p.pre_expo).x * p.edge_gain;
-                            ri[row] = make_float4(live ? row_scale(m) : 1.f, 0.f, 0.f, live ? ny : 0.f);
+                            const float2* xr = xs + (c0 + row) * p.sf;      // sb == 1
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                v[r][j] = (live && j < nj) ? __ldg(xr + j * 32 + lane) : make_float2(0.f, 0.f);
+                            vn[r] = (live && lane == 0 && !ODD) ? __ldg(xr + Hf) : make_float2(0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int r = 0; r < SR; ++r) {
+                            const int row = r0 + r;
+                            if (lane == 0) v[r][0].y = 0.f;   // Im X[0] never reaches the output
+                            float m = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                m = fmaxf(m, DECOMP ? norm2_finite(v[r][j])
+                                                    : abs2_finite(prep_bin<false>(v[r][j], p.pre_scale, p.pre_expo)));
+#pragma unroll
+                            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                            if (DECOMP) m = decomp_bound(m, p.pre_scale, p.pre_expo);
+                            if (lane == 0 && row < NF) {
+                                const bool live = row < ncols && c0 + row < p.n_frames;
+                                const float ny = prep_bin<DECOMP>(vn[r], p.pre_scale, p.pre_expo).x * p.edge_gain;
+                                ri[row] = make_float4(live ? row_scale(m) : 1.f, 0.f, 0.f, live ? ny : 0.f);
+                            }
                         }
                     }
-                }
+                };
+#ifdef BRV_T_SCOUT_FIXED2              // dev A/B switch
+                scan_rows(std::integral_constant<int, 2>{});
+#else
+                if (Q <= 64) scan_rows(std::integral_constant<int, 2>{});
+                else scan_rows(std::integral_constant<int, 1>{});
+#endif
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&scale_full[slot]);

@@ -36,6 +36,7 @@
 //     corrections, |X|^(c-1) compression, scale_factor, interleave
 //     (Re, Im) of even / odd bins, per-warp shared-memory transpose, 256-byte
 //     contiguous row stores into the frame-major complex64 output.
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
